@@ -1,0 +1,217 @@
+/*
+ * embrace_b200.h -- C ABI of libembrace_sm100.so, the B200 (sm_100a) engine for the
+ * EmbraceNet training / inference hot path of the reference
+ * (BIOINF_tesi/models/*, BIOINF_tesi/models/utils/training_models_multimodal.py).
+ *
+ * The reference has no FFI boundary of its own (it is pure Python on top of PyTorch);
+ * the entry points below are what its Python surface binds through ctypes
+ * (see INTEGRATION.md).  Each entry cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer is a DEVICE pointer unless the name ends in
+ *     `_host`; sizes in elements unless the name says bytes.
+ *   - every function returns 0 on success or a negative EMB_E_* code; the message is
+ *     available from emb_last_error() (thread local).
+ *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*);
+ *     no function synchronises unless documented; nothing allocates after emb_bind().
+ *   - activations/gradients are laid out channels-last ([B, L, C]); parameters and their
+ *     gradients keep the reference's state_dict shapes (row-major) in flat fp32 arenas.
+ *   - there is NO CPU fallback: if no sm_100 device is present every compute entry fails
+ *     with EMB_E_NO_DEVICE.
+ */
+#ifndef EMBRACE_B200_H
+#define EMBRACE_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMB_ABI_VERSION 1
+
+#define EMB_MAX_FFNN 4   /* FFNN_pre.py:19  suggest_int("FFNN_n_layers", 1, 4) */
+#define EMB_MAX_CNN 4    /* CNN_pre.py:24   suggest_int("CNN_n_layers", 1, 4)  */
+#define EMB_MAX_POST 2   /* EmbraceNetMultimodal.py:135 suggest_int("n_post_layers", 0, 2) */
+#define EMB_SEQ_LEN 256  /* CNN_pre.py:21 */
+#define EMB_POOL_K 10    /* CNN_pre.py:18 */
+#define EMB_POOL_S 2     /* CNN_pre.py:20 */
+
+enum { EMB_OK = 0, EMB_E_ARG = -1, EMB_E_NO_DEVICE = -2, EMB_E_CUDA = -3, EMB_E_STATE = -4, EMB_E_UNSUPPORTED = -5 };
+
+/* model kind: EmbraceNetMultimodal.py:94 / FF_net.py:8 / CNN_net.py:10 */
+enum { EMB_KIND_EMBRACENET = 0, EMB_KIND_FFNN = 1, EMB_KIND_CNN = 2 };
+/* arithmetic of activations and GEMM operands (accumulation, BN statistics, loss, master
+ * weights and optimizer state are always fp32) */
+enum { EMB_PREC_FP32 = 0, EMB_PREC_BF16 = 1 };
+/* optimizer rules of training_models_multimodal.py:318-325 (+ north_star's AdamW) */
+enum { EMB_OPT_ADAM = 0, EMB_OPT_ADAMW = 1, EMB_OPT_NADAM = 2, EMB_OPT_RMSPROP = 3 };
+
+/* The architecture an Optuna trial (or a checkpoint's model_params dict) selects.
+ * Replaces: the trial.suggest_* calls in FFNN_pre.py:19-39, CNN_pre.py:24-51,
+ * EmbraceNetMultimodal.py:123-157 and their *_NoTrain twins. */
+typedef struct EmbArchSpec {
+    int32_t kind;
+    int32_t in_features;                       /* in_features_FFNN */
+    int32_t n_ffnn;
+    int32_t ffnn_units[EMB_MAX_FFNN];
+    float   ffnn_dropout[EMB_MAX_FFNN];
+    int32_t n_cnn;
+    int32_t cnn_channels[EMB_MAX_CNN];
+    int32_t cnn_kernels[EMB_MAX_CNN];          /* odd; padding = (k-1)/2 */
+    float   cnn_dropout[EMB_MAX_CNN];
+    int32_t embracement_size;                  /* "c" of EmbraceNet */
+    int32_t n_post;
+    int32_t post_units[EMB_MAX_POST];
+    float   post_dropout[EMB_MAX_POST];
+    double  p_ffnn;                            /* selection_probabilities_FFNN */
+    int32_t embracenet_dropout;                /* modality dropout during training (default 1) */
+    int32_t reserved;
+} EmbArchSpec;
+
+/* Explicit random draws for one forward (replay mode; every pointer may be NULL, meaning
+ * "draw with the engine's counter-based Philox generator").  Layouts are the REFERENCE's:
+ * dropout uniforms are indexed like the tensor nn.Dropout sees ([B,units] / [B,C,Lpool]),
+ * keep = (u >= p); embrace_u is [B, embracement_size] fp64, idx = (u > cum0)
+ * (torch.multinomial's CPU path, EmbraceNetMultimodal.py:84). */
+typedef struct EmbDraws {
+    const float*  ffnn_drop[EMB_MAX_FFNN];
+    const float*  cnn_drop[EMB_MAX_CNN];
+    const float*  post_drop[EMB_MAX_POST];
+    const double* embrace_u;
+    const float*  modal_rows;       /* [B] per-row coin of EmbraceNetMultimodal.py:181 */
+    float         modal_u0;         /* the rand(1) coin of EmbraceNetMultimodal.py:179 */
+    int32_t       has_modal_u0;     /* 0: draw it with Philox */
+} EmbDraws;
+
+typedef struct EmbOptConfig {
+    int32_t kind;                   /* EMB_OPT_* */
+    float lr, weight_decay;
+    float beta1, beta2, eps;        /* Adam/Nadam: 0.9, 0.999, 1e-8 */
+    float alpha;                    /* RMSprop: 0.99 */
+    float momentum_decay;           /* Nadam schedule_decay: 4e-3 */
+} EmbOptConfig;
+
+/* One row of the parameter table (state_dict key <-> arena offset). */
+typedef struct EmbParamInfo {
+    char    name[64];               /* e.g. "CNN.CNN_model.0.weight" */
+    int64_t offset;                 /* element offset into the params/grads (or buffers) arena */
+    int64_t numel;
+    int32_t ndim;
+    int32_t shape[3];
+    int32_t is_buffer;              /* running_mean / running_var live in the buffers arena */
+} EmbParamInfo;
+
+/* Per-step results accumulated on the device, one record per step since emb_metrics_reset
+ * (replaces loss.item() and AUPRC()/F1_precision_recall() per batch,
+ * training_models_multimodal.py:160-162, utils.py:80-94). */
+typedef struct EmbStepMetrics {
+    float   loss;
+    int32_t tp, fp, fn, tn;
+} EmbStepMetrics;
+
+typedef struct EmbEngine EmbEngine;
+
+const char* emb_last_error(void);
+int emb_abi_version(void);
+/* number of sm_100 devices visible (0 = none: compute entry points will fail) */
+int emb_device_count(void);
+
+/* ---- lifetime ------------------------------------------------------------------------------
+ * emb_create plans the layer shapes (utils.py:143-153 size_out_convolution chain), the parameter
+ * table and the workspace for batches up to max_batch.  No device memory is touched. */
+int emb_create(const EmbArchSpec* spec, int32_t max_batch, int32_t precision, EmbEngine** out);
+void emb_destroy(EmbEngine* e);
+
+int64_t emb_param_count(const EmbEngine* e);       /* trainable fp32 elements */
+int64_t emb_buffer_count(const EmbEngine* e);      /* BatchNorm running stats, fp32 elements */
+int64_t emb_workspace_bytes(const EmbEngine* e);
+int32_t emb_num_tensors(const EmbEngine* e);
+int emb_param_info(const EmbEngine* e, int32_t i, EmbParamInfo* out);
+int32_t emb_output_size(const EmbEngine* e, int32_t which); /* 0: FFNN_pre_output_size, 1: CNN_pre_output_size */
+
+/* Bind caller-owned device memory (PyTorch owns it in the Python host).  opt_m/opt_v may be
+ * NULL for inference-only use.  Passing all NULL makes the engine cudaMalloc its own. */
+int emb_bind(EmbEngine* e, float* params, float* grads, float* buffers, float* opt_m, float* opt_v,
+             void* workspace, int64_t workspace_bytes);
+
+/* seed of the counter-based generator used where EmbDraws leaves a draw NULL */
+int emb_set_seed(EmbEngine* e, uint64_t seed);
+/* data-parallel context: this rank's batch rows are global rows [row_offset, row_offset+B) of a
+ * global batch of global_batch rows (Philox counters, loss weights and BatchNorm n use the
+ * global view; the collectives themselves are issued by the host, see emb_bn_partial_*). */
+int emb_set_shard(EmbEngine* e, int64_t row_offset, int64_t global_batch);
+
+/* ---- the hot path --------------------------------------------------------------------------*/
+/* EmbraceNetMultimodal.forward(..., is_training=True) (EmbraceNetMultimodal.py:159-193), or
+ * FFNN.forward / CNN.forward for the single-modality kinds.
+ *   x_ffnn  [B, in_features] fp32 row-major (ignored for EMB_KIND_CNN)
+ *   bases   [B, 256] uint8 codes 0..3 = a,c,g,t: the argmax of the one-hot [B,4,256] tensor the
+ *           reference feeds its first Conv1d (data_pipe/utils.py:268-276)
+ *   availabilities [B,2] fp32 or NULL (EmbraceNet.forward's argument)
+ *   logits_out [B,2] fp32 */
+int emb_forward_train(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const float* availabilities,
+                      int32_t B, const EmbDraws* draws, float* logits_out, void* stream);
+/* model.eval() forward (BatchNorm running stats, no dropout, multinomial still sampled).
+ * probs_out (optional) [B] = softmax(logits)[:,1], the value the predict loop keeps
+ * (EmbraceNetMultimodal_NoTrain.py:210-214, visual.py:290-293). */
+int emb_forward_infer(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const float* availabilities,
+                      int32_t B, const EmbDraws* draws, float* logits_out, float* probs_out, void* stream);
+/* nn.CrossEntropyLoss(weight=[w_neg,w_pos]) with get_loss_weights_from_labels
+ * (training_models_multimodal.py:140-154, utils.py:121-140) on fp32 logits; also the confusion
+ * counts behind AUPRC()/F1_precision_recall() (utils.py:80-94).  Appends one EmbStepMetrics record.
+ * dlogits_out [B,2] fp32 (may be NULL when only the loss/metrics are wanted). */
+int emb_loss_ce_weighted(EmbEngine* e, const float* logits, const int32_t* labels, int32_t B,
+                         float* dlogits_out, void* stream);
+/* loss.backward(): gradients of every parameter into the grads arena (overwritten, not accumulated)
+ * for the most recent emb_forward_train. */
+int emb_backward(EmbEngine* e, const float* dlogits, void* stream);
+/* optimizer.step() over the whole parameter arena (torch.optim.Adam / RMSprop, timm Nadam, all with
+ * coupled L2 weight decay; EMB_OPT_ADAMW decoupled). */
+int emb_opt_step(EmbEngine* e, const EmbOptConfig* cfg, void* stream);
+/* One iteration of the loop body at training_models_multimodal.py:132-162: forward, loss,
+ * backward, optimizer step, metrics; nothing returns to the host. */
+int emb_train_step(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const int32_t* labels, int32_t B,
+                   const EmbDraws* draws, const EmbOptConfig* cfg, void* stream);
+/* Same through HOST buffers: copies the batch host->device on `stream`, runs emb_train_step, and
+ * copies this step's EmbStepMetrics back into *metrics_host (synchronises the stream). */
+int emb_train_step_host(EmbEngine* e, const float* x_ffnn_host, const uint8_t* bases_host,
+                        const int32_t* labels_host, int32_t B, const EmbOptConfig* cfg,
+                        EmbStepMetrics* metrics_host, void* stream);
+/* Predict through HOST buffers (probs_host [B]); synchronises the stream. */
+int emb_predict_host(EmbEngine* e, const float* x_ffnn_host, const uint8_t* bases_host,
+                     const float* availabilities_host, int32_t B, float* probs_host, void* stream);
+
+int emb_metrics_reset(EmbEngine* e, void* stream);
+/* copies up to max_records records to host (synchronises); returns the number copied or <0 */
+int emb_metrics_read(EmbEngine* e, EmbStepMetrics* out_host, int32_t max_records, void* stream);
+/* the modality index map of the last forward: [B, embracement_size] uint8 */
+int emb_last_selection(EmbEngine* e, uint8_t* idx_out, int32_t B, void* stream);
+/* number of kernel launches issued by this engine since creation (bench.py's gpu_launches) */
+int64_t emb_launch_count(const EmbEngine* e);
+/* select GEMM back end: 0 = SIMT fp32-accumulate kernels only, 1 = tcgen05/TMEM/TMA where the shape
+ * allows (bf16 precision only) */
+int emb_set_tensor_core(EmbEngine* e, int32_t on);
+
+/* ---- data-parallel hooks (SyncBN / global loss weights) --------------------------------------
+ * When set, BatchNorm statistics are finished by the host's allreduce: the engine writes the local
+ * partial sums into a device buffer and calls back between the stats and the finalize kernels. */
+typedef int (*EmbAllreduceFn)(void* user, double* device_buf, int64_t count, void* stream);
+int emb_set_allreduce(EmbEngine* e, EmbAllreduceFn fn, void* user);
+
+/* ---- single-kernel entry points (unit tests and micro-benchmarks) ----------------------------*/
+/* K1: Conv1d(4->C1,k) over one-hot input as a gather-sum (CNN_pre.py:39 with in_channels=4).
+ * w [C1,4,k] fp32 (reference layout), y [B,256,C1] (fp32 or bf16 by `precision`). */
+int emb_k_onehot_conv_fwd(const uint8_t* bases, const float* w, const float* bias, int32_t B, int32_t C1,
+                          int32_t k, int32_t precision, void* y, void* stream);
+int emb_k_onehot_conv_bwd(const uint8_t* bases, const void* dy, int32_t B, int32_t C1, int32_t k,
+                          int32_t precision, float* dw, float* dbias, void* stream);
+/* out[M,N] = A[M,K] * W[N,K]^T + bias  (nn.Linear), fp32 in/out, via the engine's GEMM back end */
+int emb_k_linear_fwd(const float* a, const float* w, const float* bias, int32_t M, int32_t N, int32_t K,
+                     int32_t relu, int32_t tensor_core, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMBRACE_B200_H */

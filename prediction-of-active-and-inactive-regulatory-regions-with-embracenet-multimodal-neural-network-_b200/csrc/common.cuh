@@ -1,0 +1,105 @@
+// Shared device/host helpers for libembrace_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace emb {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: every ABI entry returns a code, the text is kept thread-local
+// ---------------------------------------------------------------------------------------------
+extern thread_local std::string g_last_error;
+int set_error(int code, const char* fmt, ...);
+
+#define EMB_CUDA_OK(expr)                                                                              \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return emb::set_error(-3, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                                  __LINE__);                                                           \
+    } while (0)
+
+#define EMB_CHECK_LAUNCH()                                                                          \
+    do {                                                                                            \
+        cudaError_t _e = cudaGetLastError();                                                        \
+        if (_e != cudaSuccess)                                                                      \
+            return emb::set_error(-3, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),   \
+                                  __FILE__, __LINE__);                                              \
+    } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// activation element type: float (EMB_PREC_FP32) or bf16 (EMB_PREC_BF16)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float load_act(const void* p, int dtype, size_t i) {
+    return dtype ? __bfloat162float(((const bf16*)p)[i]) : ((const float*)p)[i];
+}
+__device__ __forceinline__ void store_act(void* p, int dtype, size_t i, float v) {
+    if (dtype) ((bf16*)p)[i] = __float2bfloat16_rn(v);
+    else ((float*)p)[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10: counter-based generator, keyed by (seed); counter = (element index, stream, step).
+// Draws therefore do not depend on how a batch is partitioned across GPUs or thread blocks.
+// ---------------------------------------------------------------------------------------------
+struct RngState {
+    uint64_t seed;
+    uint32_t step;
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+enum RngStream : uint32_t {
+    RNG_FFNN_DROP = 0x10, RNG_CNN_DROP = 0x20, RNG_POST_DROP = 0x30, RNG_EMBRACE = 0x40, RNG_MODAL_COIN = 0x50,
+    RNG_MODAL_ROWS = 0x51
+};
+
+__device__ __forceinline__ uint4 rng_raw(const RngState& s, uint32_t stream, uint64_t elem) {
+    uint4 ctr = make_uint4((uint32_t)elem, (uint32_t)(elem >> 32), stream, s.step);
+    uint2 key = make_uint2((uint32_t)s.seed, (uint32_t)(s.seed >> 32));
+    return philox4x32_10(ctr, key);
+}
+// uniform in [0,1), 24 bits
+__device__ __forceinline__ float rng_uniform_f32(const RngState& s, uint32_t stream, uint64_t elem) {
+    return (float)(rng_raw(s, stream, elem).x >> 8) * (1.0f / 16777216.0f);
+}
+// uniform in [0,1), 53 bits (what torch's CPU generator gives torch.multinomial)
+__device__ __forceinline__ double rng_uniform_f64(const RngState& s, uint32_t stream, uint64_t elem) {
+    uint4 r = rng_raw(s, stream, elem);
+    uint64_t bits = (((uint64_t)r.x << 32) | r.y) >> 11;
+    return (double)bits * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace emb

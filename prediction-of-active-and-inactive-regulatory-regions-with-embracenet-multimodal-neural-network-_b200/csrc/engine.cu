@@ -1,0 +1,1031 @@
+// libembrace_sm100.so -- planning, orchestration and the C ABI (include/embrace_b200.h).
+//
+// Path rebuilt here (reference file:line):
+//   EmbraceNetMultimodal.forward   BIOINF_tesi/models/EmbraceNetMultimodal.py:159-193
+//   EmbraceNet.forward             BIOINF_tesi/models/EmbraceNetMultimodal.py:34-90
+//   FFNN_pre / CNN_pre             BIOINF_tesi/models/FFNN_pre.py:10-49, CNN_pre.py:12-76
+//   FFNN / CNN (single modality)   BIOINF_tesi/models/FF_net.py:8-50, CNN_net.py:10-83
+//   loss / metrics / optimizer     BIOINF_tesi/models/utils/training_models_multimodal.py:132-162, utils.py:80-140
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <string>
+
+#include "../../include/embrace_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+
+namespace emb {
+
+thread_local std::string g_last_error;
+
+int set_error(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+struct Tensor {       // one state_dict entry
+    std::string name;
+    int64_t offset, numel;
+    int ndim, shape[3];
+    bool is_buffer;
+};
+
+struct LinearLayer {
+    int in, out;
+    int64_t w, b;     // offsets into the params arena
+    float drop;
+    bool relu;
+    bool perm_in;     // input is the channels-last flattened CNN activation (docking_1, last_layer1)
+};
+
+struct ConvLayer {
+    int cin, cout, k, pad, Lc, Lp, ld;
+    int64_t w, b, gamma, beta;   // params arena
+    int64_t rm, rv;              // buffers arena
+    float drop;
+    // workspace
+    void *y, *a, *dy, *ga;
+    float *scale, *shift, *mean, *rstd;
+    double *stats, *bstats;
+};
+
+struct Act {        // [rows, width] activation with leading dimension ld
+    void* p = nullptr;
+    int width = 0, ld = 0;
+};
+
+}  // namespace emb
+
+using namespace emb;
+
+struct EmbEngine {
+    EmbArchSpec spec;
+    int max_batch, prec, esize;      // esize: bytes per activation element
+    bool use_tc = false;
+    std::vector<Tensor> tensors;
+    int64_t n_params = 0, n_buffers = 0;
+    std::vector<LinearLayer> ffnn, post, head;   // head: FFNN final Linear / CNN last_layer1..last_output
+    LinearLayer dock0{}, dock1{};
+    std::vector<ConvLayer> cnn;
+    int ffnn_out = 0, cnn_out = 0, cnn_Lp_last = 0, cnn_C_last = 0, cnn_ld_last = 0;
+
+    // bound memory
+    float *params = nullptr, *grads = nullptr, *buffers = nullptr, *opt_m = nullptr, *opt_v = nullptr;
+    char* ws = nullptr;
+    int64_t ws_bytes = 0;
+    bool owns_memory = false;
+
+    // workspace carve-out
+    Act x0, d0, e, dd0, dd1;
+    std::vector<Act> ffnn_h, ffnn_g, post_h, post_g, head_h, head_g;
+    Act gflat;                       // gradient w.r.t. the flattened CNN output (== cnn.back().ga)
+    uint8_t* idx = nullptr;
+    double* cum0 = nullptr;
+    float *logits = nullptr, *dlogits = nullptr, *probs = nullptr;
+    float* in_x = nullptr;           // staging for the *_host entries
+    uint8_t* in_bases = nullptr;
+    int32_t* in_labels = nullptr;
+    float* in_avail = nullptr;
+    RngState* rng = nullptr;
+    StepMetricsDev* rec = nullptr;
+    OptScalars* opt_scalars = nullptr;
+    int* rec_count = nullptr;
+    static const int MAX_REC = 1 << 16;
+
+    // per-forward state needed by backward
+    int last_B = 0;
+    bool last_training = false;
+    const uint8_t* last_bases = nullptr;
+
+    // optimizer / shard state
+    int64_t opt_t = 0;
+    double nadam_mu_product = 1.0;
+    int64_t row_offset = 0, global_batch = -1;
+    uint64_t seed = 0x5EEDull;
+    EmbAllreduceFn allreduce = nullptr;
+    void* allreduce_user = nullptr;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int dtype_of(const EmbEngine* e) { return e->prec == EMB_PREC_BF16 ? 1 : 0; }
+
+void add_tensor(EmbEngine* e, const std::string& name, std::initializer_list<int> shape, bool is_buffer, int64_t* off) {
+    Tensor t;
+    t.name = name;
+    t.ndim = (int)shape.size();
+    t.numel = 1;
+    int i = 0;
+    t.shape[0] = t.shape[1] = t.shape[2] = 1;
+    for (int s : shape) { t.shape[i++] = s; t.numel *= s; }
+    t.is_buffer = is_buffer;
+    int64_t& cursor = is_buffer ? e->n_buffers : e->n_params;
+    t.offset = cursor;
+    cursor += round_up64(t.numel, 4);   // keep every tensor 16-byte aligned in the arena
+    *off = t.offset;
+    e->tensors.push_back(t);
+}
+
+LinearLayer add_linear(EmbEngine* e, const std::string& prefix, int in, int out, float drop, bool relu, bool perm_in) {
+    LinearLayer l{};
+    l.in = in; l.out = out; l.drop = drop; l.relu = relu; l.perm_in = perm_in;
+    add_tensor(e, prefix + ".weight", {out, in}, false, &l.w);
+    add_tensor(e, prefix + ".bias", {out}, false, &l.b);
+    return l;
+}
+
+int plan(EmbEngine* e) {
+    const EmbArchSpec& s = e->spec;
+    const bool emb_kind = s.kind == EMB_KIND_EMBRACENET;
+    const std::string pf = emb_kind ? "FFNN.model." : "model.";
+    const std::string pc = emb_kind ? "CNN.CNN_model." : "CNN_model.";
+    if (s.kind != EMB_KIND_CNN) {
+        if (s.n_ffnn < 1 || s.n_ffnn > EMB_MAX_FFNN || s.in_features < 1) return set_error(EMB_E_ARG, "bad FFNN spec");
+        int in = s.in_features;
+        for (int i = 0; i < s.n_ffnn; ++i) {
+            if (s.ffnn_units[i] < 1 || s.ffnn_dropout[i] < 0 || s.ffnn_dropout[i] >= 1) return set_error(EMB_E_ARG, "bad FFNN layer %d", i);
+            e->ffnn.push_back(add_linear(e, pf + std::to_string(3 * i), in, s.ffnn_units[i], s.ffnn_dropout[i], true, false));
+            in = s.ffnn_units[i];
+        }
+        e->ffnn_out = in;
+        if (s.kind == EMB_KIND_FFNN) e->head.push_back(add_linear(e, pf + std::to_string(3 * s.n_ffnn), in, 2, 0.f, false, false));
+    }
+    if (s.kind != EMB_KIND_FFNN) {
+        if (s.n_cnn < 1 || s.n_cnn > EMB_MAX_CNN) return set_error(EMB_E_ARG, "bad CNN spec");
+        int cin = 4, L = SEQ_LEN;
+        for (int i = 0; i < s.n_cnn; ++i) {
+            ConvLayer c{};
+            c.cin = cin; c.cout = s.cnn_channels[i]; c.k = s.cnn_kernels[i]; c.drop = s.cnn_dropout[i];
+            if (c.cout < 1 || c.k < 1 || (c.k & 1) == 0 || c.drop < 0 || c.drop >= 1) return set_error(EMB_E_ARG, "bad CNN layer %d (odd kernel sizes only)", i);
+            if (i == 0 && c.cout * c.k > OHB_MAXP * 256) return set_error(EMB_E_UNSUPPORTED, "first conv: out_channels*kernel_size > %d", OHB_MAXP * 256);
+            c.pad = (c.k - 1) / 2;
+            c.Lc = (L + 2 * c.pad - c.k) + 1;                 // size_out_convolution, stride 1
+            c.Lp = (c.Lc - POOL_K) / POOL_S + 1;              // size_out_convolution(.., 10, 0, 2)
+            if (c.Lc < POOL_K) return set_error(EMB_E_ARG, "sequence too short at CNN layer %d", i);
+            c.ld = round_up(c.cout, 8);
+            add_tensor(e, pc + std::to_string(5 * i) + ".weight", {c.cout, c.cin, c.k}, false, &c.w);
+            add_tensor(e, pc + std::to_string(5 * i) + ".bias", {c.cout}, false, &c.b);
+            add_tensor(e, pc + std::to_string(5 * i + 1) + ".weight", {c.cout}, false, &c.gamma);
+            add_tensor(e, pc + std::to_string(5 * i + 1) + ".bias", {c.cout}, false, &c.beta);
+            add_tensor(e, pc + std::to_string(5 * i + 1) + ".running_mean", {c.cout}, true, &c.rm);
+            add_tensor(e, pc + std::to_string(5 * i + 1) + ".running_var", {c.cout}, true, &c.rv);
+            e->cnn.push_back(c);
+            cin = c.cout;
+            L = c.Lp;
+        }
+        e->cnn_Lp_last = L;
+        e->cnn_C_last = cin;
+        e->cnn_ld_last = e->cnn.back().ld;
+        e->cnn_out = cin * L;
+        if (s.kind == EMB_KIND_CNN) {   // CNN_net.py:71-81: three Linear layers, no activation in between
+            e->head.push_back(add_linear(e, "last_layer1", e->cnn_out, 1000, 0.f, false, true));
+            e->head.push_back(add_linear(e, "last_layer2", 1000, 64, 0.f, false, false));
+            e->head.push_back(add_linear(e, "last_output", 64, 2, 0.f, false, false));
+        }
+    }
+    if (emb_kind) {
+        const int C = s.embracement_size;
+        if (C < 1 || s.n_post < 0 || s.n_post > EMB_MAX_POST || s.p_ffnn < 0 || s.p_ffnn > 1) return set_error(EMB_E_ARG, "bad EmbraceNet spec");
+        e->dock0 = add_linear(e, "embracenet.docking_0", e->ffnn_out, C, 0.f, true, false);
+        e->dock1 = add_linear(e, "embracenet.docking_1", e->cnn_out, C, 0.f, true, true);
+        int in = C;
+        for (int i = 0; i < s.n_post; ++i) {
+            e->post.push_back(add_linear(e, "post." + std::to_string(3 * i), in, s.post_units[i], s.post_dropout[i], true, false));
+            in = s.post_units[i];
+        }
+        e->head.push_back(add_linear(e, "post." + std::to_string(3 * s.n_post), in, 2, 0.f, false, false));
+    }
+    return EMB_OK;
+}
+
+struct Bump {
+    char* base;
+    int64_t off = 0;
+    template <typename T> T* take(int64_t count) {
+        off = round_up64(off, 256);
+        T* p = base ? (T*)(base + off) : nullptr;
+        off += count * (int64_t)sizeof(T);
+        return p;
+    }
+    void* take_bytes(int64_t bytes) { return (void*)take<char>(bytes); }
+};
+
+Act take_act(Bump& bp, int64_t rows, int width, int esize) {
+    Act a;
+    a.width = width;
+    a.ld = round_up(width, 8);
+    a.p = bp.take_bytes(rows * a.ld * esize);
+    return a;
+}
+
+// carve the workspace; with base == nullptr only the size is computed
+int64_t carve(EmbEngine* e, char* base) {
+    Bump bp{base};
+    const int64_t Bm = e->max_batch;
+    const int es = e->esize;
+    const EmbArchSpec& s = e->spec;
+    e->ffnn_h.clear(); e->ffnn_g.clear(); e->post_h.clear(); e->post_g.clear(); e->head_h.clear(); e->head_g.clear();
+    e->rng = bp.take<RngState>(1);
+    e->rec_count = bp.take<int>(1);
+    e->rec = bp.take<StepMetricsDev>(EmbEngine::MAX_REC);
+    e->opt_scalars = bp.take<OptScalars>(1);
+    e->logits = bp.take<float>(Bm * 2);
+    e->dlogits = bp.take<float>(Bm * 2);
+    e->probs = bp.take<float>(Bm);
+    e->in_x = bp.take<float>(Bm * std::max(1, s.in_features));
+    e->in_bases = bp.take<uint8_t>(Bm * SEQ_LEN);
+    e->in_labels = bp.take<int32_t>(Bm);
+    e->in_avail = bp.take<float>(Bm * 2);
+    if (s.kind != EMB_KIND_CNN) {
+        e->x0 = take_act(bp, Bm, s.in_features, es);
+        for (auto& l : e->ffnn) {
+            e->ffnn_h.push_back(take_act(bp, Bm, l.out, es));
+            e->ffnn_g.push_back(take_act(bp, Bm, l.out, es));
+        }
+    }
+    for (auto& c : e->cnn) {
+        c.y = bp.take_bytes(Bm * c.Lc * c.ld * es);
+        c.dy = bp.take_bytes(Bm * c.Lc * c.ld * es);
+        c.a = bp.take_bytes(Bm * c.Lp * c.ld * es);
+        c.ga = bp.take_bytes(Bm * c.Lp * c.ld * es);
+        c.scale = bp.take<float>(c.cout);
+        c.shift = bp.take<float>(c.cout);
+        c.mean = bp.take<float>(c.cout);
+        c.rstd = bp.take<float>(c.cout);
+        c.stats = bp.take<double>(2 * c.cout);
+        c.bstats = bp.take<double>(2 * c.cout);
+    }
+    if (s.kind == EMB_KIND_EMBRACENET) {
+        const int C = s.embracement_size;
+        e->d0 = take_act(bp, Bm, C, es);
+        e->e = take_act(bp, Bm, C, es);
+        e->dd0 = take_act(bp, Bm, C, es);
+        e->dd1 = take_act(bp, Bm, C, es);
+        e->idx = bp.take<uint8_t>(Bm * C);
+        e->cum0 = bp.take<double>(Bm);
+        for (auto& l : e->post) {
+            e->post_h.push_back(take_act(bp, Bm, l.out, es));
+            e->post_g.push_back(take_act(bp, Bm, l.out, es));
+        }
+    }
+    if (s.kind == EMB_KIND_CNN)
+        for (size_t i = 0; i + 1 < e->head.size(); ++i) {
+            e->head_h.push_back(take_act(bp, Bm, e->head[i].out, es));
+            e->head_g.push_back(take_act(bp, Bm, e->head[i].out, es));
+        }
+    return round_up64(bp.off, 256);
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------
+#define LAUNCHED(e) ((e)->launches++)
+
+Epilogue base_epi(EmbEngine* e, int mode, void* out, int ldo) {
+    Epilogue ep = {};
+    ep.mode = mode;
+    ep.out = out;
+    ep.out_dtype = dtype_of(e);
+    ep.ldo = ldo;
+    ep.rng = e->rng;
+    ep.row_offset = e->row_offset;
+    ep.scale = 1.f;
+    return ep;
+}
+
+Operand weight_operand(EmbEngine* e, const LinearLayer& l, bool transposed) {
+    // forward: rows = out units, k = in;  transposed (dgrad): rows = in, k = out
+    Operand o;
+    if (!l.perm_in) {
+        o = transposed ? make_operand(e->params + l.w, 0, OP_TRANSPOSED, l.in, l.in, l.out)
+                       : make_operand(e->params + l.w, 0, OP_ROWMAJOR, l.in, l.out, l.in);
+    } else {
+        o = transposed ? make_operand(e->params + l.w, 0, OP_W_PERM_T, 0, l.in, l.out)
+                       : make_operand(e->params + l.w, 0, OP_W_PERM, 0, l.out, l.in);
+        o.L = e->cnn_Lp_last; o.C = e->cnn_C_last; o.wrows = l.in;
+    }
+    o.round_bf16 = e->prec == EMB_PREC_BF16;
+    return o;
+}
+
+// the input activation of a Linear layer as the A operand (rows = batch)
+Operand input_operand(EmbEngine* e, const LinearLayer& l, const Act& in, int B, bool transposed) {
+    Operand o;
+    const int dt = dtype_of(e);
+    if (!l.perm_in) {
+        o = transposed ? make_operand(in.p, dt, OP_TRANSPOSED, in.ld, l.in, B) : make_operand(in.p, dt, OP_ROWMAJOR, in.ld, B, l.in);
+    } else {
+        o = transposed ? make_operand(in.p, dt, OP_FLAT_ACT_T, e->cnn_ld_last, l.in, B)
+                       : make_operand(in.p, dt, OP_FLAT_ACT, e->cnn_ld_last, B, l.in);
+        o.L = e->cnn_Lp_last; o.C = e->cnn_C_last;
+    }
+    return o;
+}
+
+int run_gemm(EmbEngine* e, const Operand& A, const Operand& B, const Epilogue& ep, int M, int N, int K, int split_k, cudaStream_t st) {
+    cudaError_t err = launch_gemm_simt(A, B, ep, M, N, K, split_k, st);
+    if (err != cudaSuccess) return set_error(EMB_E_CUDA, "gemm launch: %s", cudaGetErrorString(err));
+    LAUNCHED(e);
+    return EMB_OK;
+}
+
+int pick_split_k(int M, int N, int K) {
+    int tiles = cdiv(M, SG_BM) * cdiv(N, SG_BN);
+    int want = std::max(1, (148 * 4) / std::max(1, tiles));
+    int maxk = std::max(1, K / 64);
+    return std::min(want, maxk);
+}
+
+// y = [dropout]([relu](x W^T + b))
+int linear_forward(EmbEngine* e, const LinearLayer& l, const Act& in, const Act& out, int B, bool training,
+                   const float* drop_u, uint32_t stream_id, cudaStream_t st) {
+    Operand A = input_operand(e, l, in, B, false);
+    Operand W = weight_operand(e, l, false);
+    Epilogue ep = base_epi(e, EPI_LINEAR, out.p, out.ld);
+    ep.bias = e->params + l.b;
+    ep.relu = l.relu;
+    if (training && l.drop > 0.f) { ep.drop_p = l.drop; ep.drop_u = drop_u; ep.rng_stream = stream_id; }
+    return run_gemm(e, A, W, ep, B, l.out, l.in, 1, st);
+}
+
+// dW += g^T x ; db += colsum(g)          (g: gradient w.r.t. the layer's pre-activation, [B, out])
+int linear_wgrad(EmbEngine* e, const LinearLayer& l, const void* g, int g_dtype, int g_ld, const Act& in, int B, cudaStream_t st) {
+    Operand A = make_operand(g, g_dtype, OP_TRANSPOSED, g_ld, l.out, B);
+    Operand X = input_operand(e, l, in, B, true);
+    Epilogue ep = base_epi(e, EPI_ATOMIC, e->grads + l.w, l.in);
+    if (l.perm_in) { ep.map = MAP_W_PERM; ep.mapC = e->cnn_C_last; ep.mapL = e->cnn_Lp_last; ep.map_wrows = l.in; }
+    int rc = run_gemm(e, A, X, ep, l.out, l.in, B, pick_split_k(l.out, l.in, B), st);
+    if (rc) return rc;
+    dim3 grid(cdiv(l.out, 32), std::min(64, cdiv(B, 8)));
+    if (g_dtype) colsum_kernel<bf16><<<grid, dim3(32, 8), 0, st>>>((const bf16*)g, e->grads + l.b, B, l.out, g_ld);
+    else colsum_kernel<float><<<grid, dim3(32, 8), 0, st>>>((const float*)g, e->grads + l.b, B, l.out, g_ld);
+    EMB_CHECK_LAUNCH();
+    LAUNCHED(e);
+    return EMB_OK;
+}
+
+// gradient w.r.t. the layer input: acc = g W, finished by `ep`
+int linear_dgrad(EmbEngine* e, const LinearLayer& l, const void* g, int g_dtype, int g_ld, int B, Epilogue ep, cudaStream_t st) {
+    Operand A = make_operand(g, g_dtype, OP_ROWMAJOR, g_ld, B, l.out);
+    Operand W = weight_operand(e, l, true);
+    return run_gemm(e, A, W, ep, B, l.in, l.out, 1, st);
+}
+
+template <typename T>
+int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, const EmbDraws* dr, cudaStream_t st) {
+    const int dt = dtype_of(e);
+    for (size_t i = 0; i < e->cnn.size(); ++i) {
+        ConvLayer& c = e->cnn[i];
+        if (i == 0) {
+            size_t smem = (size_t)(c.k * 4 * c.cout + c.cout) * sizeof(float) + SEQ_LEN + 2 * c.pad + 16;
+            int grid = std::min(B, 148 * 8);
+            onehot_conv_fwd_kernel<T><<<grid, 256, smem, st>>>(bases, e->params + c.w, e->params + c.b, (T*)c.y, B, c.cout, c.k, c.ld, 0);
+            EMB_CHECK_LAUNCH();
+            LAUNCHED(e);
+        } else {
+            ConvLayer& pr = e->cnn[i - 1];
+            Operand A = make_operand(pr.a, dt, OP_CONV_SHIFT, pr.ld, B * c.Lc, c.k * c.cin);
+            A.L = c.Lc; A.C = c.cin; A.taps = c.k; A.pad = c.pad; A.sign = 1;
+            Operand W = make_operand(e->params + c.w, 0, OP_CONV_W_FWD, 0, c.cout, c.k * c.cin);
+            W.C = c.cin; W.taps = c.k; W.round_bf16 = e->prec == EMB_PREC_BF16;
+            Epilogue ep = base_epi(e, EPI_LINEAR, c.y, c.ld);
+            ep.bias = e->params + c.b;
+            int rc = run_gemm(e, A, W, ep, B * c.Lc, c.cout, c.k * c.cin, 1, st);
+            if (rc) return rc;
+        }
+        const int64_t R = (int64_t)B * c.Lc;
+        if (training) {
+            EMB_CUDA_OK(cudaMemsetAsync(c.stats, 0, 2 * c.cout * sizeof(double), st));
+            dim3 grid(cdiv(c.cout, 32), (unsigned)std::min<int64_t>(296, cdiv(R, 8)));
+            bn_stats_kernel<T><<<grid, dim3(32, 8), 0, st>>>((const T*)c.y, c.stats, R, c.cout, c.ld);
+            EMB_CHECK_LAUNCH();
+            LAUNCHED(e);
+            if (e->allreduce) {
+                int rc = e->allreduce(e->allreduce_user, c.stats, 2 * c.cout, st);
+                if (rc) return set_error(EMB_E_STATE, "allreduce callback failed (%d)", rc);
+            }
+        }
+        double n = (double)(e->global_batch > 0 ? e->global_batch : B) * c.Lc;
+        bn_finalize_kernel<<<cdiv(c.cout, 128), 128, 0, st>>>(c.stats, e->params + c.gamma, e->params + c.beta, e->buffers + c.rm,
+                                                              e->buffers + c.rv, c.scale, c.shift, c.mean, c.rstd, n, c.cout, training ? 1 : 0);
+        EMB_CHECK_LAUNCH();
+        LAUNCHED(e);
+        size_t total = (size_t)B * c.Lp * c.cout;
+        float p = training ? c.drop : 0.f;
+        const float* du = (dr && p > 0.f) ? dr->cnn_drop[i] : nullptr;
+        bn_relu_pool_drop_fwd_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)c.y, c.scale, c.shift, (T*)c.a, B, c.Lc, c.Lp, c.cout, c.ld,
+                                                                           p, du, e->rng, RNG_CNN_DROP + (uint32_t)i, e->row_offset);
+        EMB_CHECK_LAUNCH();
+        LAUNCHED(e);
+    }
+    return EMB_OK;
+}
+
+int cnn_forward(EmbEngine* e, const uint8_t* bases, int B, bool training, const EmbDraws* dr, cudaStream_t st) {
+    return e->prec == EMB_PREC_BF16 ? cnn_forward_t<bf16>(e, bases, B, training, dr, st) : cnn_forward_t<float>(e, bases, B, training, dr, st);
+}
+
+// backward through the CNN stack; on entry cnn.back().ga holds the gradient w.r.t. the flattened output
+template <typename T>
+int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
+    const int dt = dtype_of(e);
+    for (int i = (int)e->cnn.size() - 1; i >= 0; --i) {
+        ConvLayer& c = e->cnn[i];
+        const int64_t R = (int64_t)B * c.Lc;
+        EMB_CUDA_OK(cudaMemsetAsync(c.bstats, 0, 2 * c.cout * sizeof(double), st));
+        {
+            dim3 grid(cdiv(c.cout, 32), B);
+            size_t smem = (size_t)2 * c.Lc * 32 * sizeof(float);
+            pool_bn_bwd_stage1_kernel<T><<<grid, dim3(32, 8), smem, st>>>((const T*)c.y, (const T*)c.a, (const T*)c.ga, c.scale, c.shift, c.mean,
+                                                                          c.rstd, (T*)c.dy, c.bstats, B, c.Lc, c.Lp, c.cout, c.ld, c.drop);
+            EMB_CHECK_LAUNCH();
+            LAUNCHED(e);
+        }
+        if (e->allreduce) {
+            int rc = e->allreduce(e->allreduce_user, c.bstats, 2 * c.cout, st);
+            if (rc) return set_error(EMB_E_STATE, "allreduce callback failed (%d)", rc);
+        }
+        bn_bwd_finalize_kernel<<<cdiv(c.cout, 128), 128, 0, st>>>(c.bstats, e->grads + c.gamma, e->grads + c.beta, c.cout);
+        EMB_CHECK_LAUNCH();
+        LAUNCHED(e);
+        double n = (double)(e->global_batch > 0 ? e->global_batch : B) * c.Lc;
+        {
+            dim3 grid(cdiv(c.cout, 32), (unsigned)std::min<int64_t>(296, cdiv(R, 8)));
+            bn_bwd_apply_kernel<T><<<grid, dim3(32, 8), 0, st>>>((const T*)c.y, (T*)c.dy, c.bstats, e->params + c.gamma, c.mean, c.rstd,
+                                                                 e->grads + c.b, R, c.cout, c.ld, n);
+            EMB_CHECK_LAUNCH();
+            LAUNCHED(e);
+        }
+        if (i == 0) {
+            int grid = std::min(B, 148 * 4);
+            // conv-0 dbias was already accumulated by bn_bwd_apply_kernel
+            onehot_conv_bwd_kernel<T><<<grid, 256, 0, st>>>(e->last_bases, (const T*)c.dy, e->grads + c.w, nullptr, B, c.cout, c.k, c.ld);
+            EMB_CHECK_LAUNCH();
+            LAUNCHED(e);
+        } else {
+            ConvLayer& pr = e->cnn[i - 1];
+            // wgrad: dW[o][c][tap] = sum_{b,l} dy[b,l,o] * a_prev[b, l+tap-pad, c]
+            Operand A = make_operand(c.dy, dt, OP_TRANSPOSED, c.ld, c.cout, (int)R);
+            Operand X = make_operand(pr.a, dt, OP_CONV_SHIFT_T, pr.ld, c.k * c.cin, (int)R);
+            X.L = c.Lc; X.C = c.cin; X.taps = c.k; X.pad = c.pad; X.sign = 1;
+            Epilogue ep = base_epi(e, EPI_ATOMIC, e->grads + c.w, 0);
+            ep.map = MAP_CONV_W; ep.mapC = c.cin; ep.map_taps = c.k;
+            int rc = run_gemm(e, A, X, ep, c.cout, c.k * c.cin, (int)R, pick_split_k(c.cout, c.k * c.cin, (int)R), st);
+            if (rc) return rc;
+            // dgrad: ga_prev[b,l',c] = sum_{tap,o} dy[b, l'-tap+pad, o] * W[o][c][tap]
+            Operand G = make_operand(c.dy, dt, OP_CONV_SHIFT, c.ld, (int)R, c.k * c.cout);
+            G.L = c.Lc; G.C = c.cout; G.taps = c.k; G.pad = c.pad; G.sign = -1;
+            Operand W = make_operand(e->params + c.w, 0, OP_CONV_W_DGRAD, 0, c.cin, c.k * c.cout);
+            W.C = c.cout; W.taps = c.k; W.wrows = c.cin; W.round_bf16 = e->prec == EMB_PREC_BF16;
+            Epilogue ed = base_epi(e, EPI_LINEAR, pr.ga, pr.ld);
+            rc = run_gemm(e, G, W, ed, (int)R, c.cin, c.k * c.cout, 1, st);
+            if (rc) return rc;
+        }
+    }
+    return EMB_OK;
+}
+
+int cnn_backward(EmbEngine* e, int B, cudaStream_t st) {
+    return e->prec == EMB_PREC_BF16 ? cnn_backward_t<bf16>(e, B, st) : cnn_backward_t<float>(e, B, st);
+}
+
+int check_ready(EmbEngine* e, int B, bool need_grads) {
+    if (!e) return set_error(EMB_E_ARG, "null engine");
+    if (!e->params || !e->ws) return set_error(EMB_E_STATE, "emb_bind() has not been called");
+    if (need_grads && (!e->grads)) return set_error(EMB_E_STATE, "no gradient arena bound");
+    if (B < 1 || B > e->max_batch) return set_error(EMB_E_ARG, "batch %d outside [1, %d]", B, e->max_batch);
+    return EMB_OK;
+}
+
+int forward_impl(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const float* avail, int B, bool training,
+                 const EmbDraws* dr, float* logits_out, cudaStream_t st) {
+    const EmbArchSpec& s = e->spec;
+    const int dt = dtype_of(e);
+    int rc;
+    e->last_B = B;
+    e->last_training = training;
+    e->last_bases = bases;
+    const Act* ffnn_last = nullptr;
+    if (s.kind != EMB_KIND_CNN) {
+        if (!x_ffnn) return set_error(EMB_E_ARG, "x_ffnn is NULL");
+        size_t tot = (size_t)B * e->x0.ld;
+        if (dt) cast_rows_kernel<bf16><<<cdiv(tot, 256), 256, 0, st>>>(x_ffnn, (bf16*)e->x0.p, B, s.in_features, e->x0.ld);
+        else cast_rows_kernel<float><<<cdiv(tot, 256), 256, 0, st>>>(x_ffnn, (float*)e->x0.p, B, s.in_features, e->x0.ld);
+        EMB_CHECK_LAUNCH();
+        LAUNCHED(e);
+        const Act* in = &e->x0;
+        for (size_t i = 0; i < e->ffnn.size(); ++i) {
+            const float* du = (dr && training && e->ffnn[i].drop > 0) ? dr->ffnn_drop[i] : nullptr;
+            rc = linear_forward(e, e->ffnn[i], *in, e->ffnn_h[i], B, training, du, RNG_FFNN_DROP + (uint32_t)i, st);
+            if (rc) return rc;
+            in = &e->ffnn_h[i];
+        }
+        ffnn_last = in;
+    }
+    Act flat;
+    if (s.kind != EMB_KIND_FFNN) {
+        if (!bases) return set_error(EMB_E_ARG, "bases is NULL");
+        rc = cnn_forward(e, bases, B, training, dr, st);
+        if (rc) return rc;
+        flat.p = e->cnn.back().a;
+        flat.width = e->cnn_out;
+        flat.ld = e->cnn_Lp_last * e->cnn_ld_last;
+    }
+    float* logits = logits_out ? logits_out : e->logits;
+    const Act* head_in = nullptr;
+    if (s.kind == EMB_KIND_EMBRACENET) {
+        const int C = s.embracement_size;
+        const bool mdrop = training && s.embracenet_dropout;
+        embrace_prologue_kernel<<<cdiv(B, 128), 128, 0, st>>>(s.p_ffnn, avail, mdrop ? 1 : 0, dr ? dr->has_modal_u0 : 0, dr ? dr->modal_u0 : 0.f,
+                                                              dr ? dr->modal_rows : nullptr, e->rng, e->row_offset, e->cum0, B);
+        EMB_CHECK_LAUNCH();
+        LAUNCHED(e);
+        rc = linear_forward(e, e->dock0, *ffnn_last, e->d0, B, false, nullptr, 0, st);
+        if (rc) return rc;
+        {   // docking_1 GEMM with the embracement select fused into its epilogue
+            Operand A = input_operand(e, e->dock1, flat, B, false);
+            Operand W = weight_operand(e, e->dock1, false);
+            Epilogue ep = base_epi(e, EPI_EMBRACE, e->e.p, e->e.ld);
+            ep.bias = e->params + e->dock1.b;
+            ep.d0 = e->d0.p; ep.ld_d0 = e->d0.ld;
+            ep.emb_u = dr ? dr->embrace_u : nullptr;
+            ep.cum0 = e->cum0;
+            ep.idx_out = e->idx;
+            rc = run_gemm(e, A, W, ep, B, C, e->dock1.in, 1, st);
+            if (rc) return rc;
+        }
+        const Act* in = &e->e;
+        for (size_t i = 0; i < e->post.size(); ++i) {
+            const float* du = (dr && training && e->post[i].drop > 0) ? dr->post_drop[i] : nullptr;
+            rc = linear_forward(e, e->post[i], *in, e->post_h[i], B, training, du, RNG_POST_DROP + (uint32_t)i, st);
+            if (rc) return rc;
+            in = &e->post_h[i];
+        }
+        head_in = in;
+    } else if (s.kind == EMB_KIND_FFNN) {
+        head_in = ffnn_last;
+    } else {
+        const Act* in = &flat;
+        for (size_t i = 0; i + 1 < e->head.size(); ++i) {
+            rc = linear_forward(e, e->head[i], *in, e->head_h[i], B, false, nullptr, 0, st);
+            if (rc) return rc;
+            in = &e->head_h[i];
+        }
+        head_in = in;
+    }
+    {   // final Linear -> fp32 logits
+        const LinearLayer& l = e->head.back();
+        Operand A = input_operand(e, l, *head_in, B, false);
+        Operand W = weight_operand(e, l, false);
+        Epilogue ep = base_epi(e, EPI_LINEAR, logits, 2);
+        ep.out_dtype = 0;
+        ep.bias = e->params + l.b;
+        rc = run_gemm(e, A, W, ep, B, 2, l.in, 1, st);
+        if (rc) return rc;
+    }
+    rng_advance_kernel<<<1, 1, 0, st>>>(e->rng);   // next forward (train or eval: multinomial is sampled in both) draws afresh
+    EMB_CHECK_LAUNCH();
+    LAUNCHED(e);
+    return EMB_OK;
+}
+
+int backward_impl(EmbEngine* e, const float* dlogits, cudaStream_t st) {
+    const EmbArchSpec& s = e->spec;
+    const int B = e->last_B;
+    const int dt = dtype_of(e);
+    if (!e->last_training || B < 1) return set_error(EMB_E_STATE, "emb_backward needs a preceding emb_forward_train");
+    int rc;
+    EMB_CUDA_OK(cudaMemsetAsync(e->grads, 0, e->n_params * sizeof(float), st));
+    const void* g = dlogits;     // gradient w.r.t. the current layer's pre-activation
+    int g_dt = 0, g_ld = 2;
+
+    auto mask_epi = [&](const Act& ref, float drop, const Act& out) {
+        Epilogue ep = base_epi(e, EPI_MASKGRAD, out.p, out.ld);
+        ep.ref = ref.p; ep.ld_ref = ref.ld;
+        ep.scale = drop > 0.f ? 1.f / (1.f - drop) : 1.f;
+        return ep;
+    };
+
+    if (s.kind == EMB_KIND_EMBRACENET) {
+        const LinearLayer& hl = e->head.back();
+        const int np = (int)e->post.size();
+        const Act& head_in = np ? e->post_h[np - 1] : e->e;
+        rc = linear_wgrad(e, hl, g, g_dt, g_ld, head_in, B, st);
+        if (rc) return rc;
+        auto embrace_bwd_epi = [&]() {
+            Epilogue ep = base_epi(e, EPI_EMBRACE_BWD, e->dd0.p, e->dd0.ld);
+            ep.out2 = e->dd1.p;
+            ep.idx = e->idx;
+            ep.e = e->e.p; ep.ld_e = e->e.ld;
+            return ep;
+        };
+        if (np == 0) rc = linear_dgrad(e, hl, g, g_dt, g_ld, B, embrace_bwd_epi(), st);
+        else rc = linear_dgrad(e, hl, g, g_dt, g_ld, B, mask_epi(e->post_h[np - 1], e->post[np - 1].drop, e->post_g[np - 1]), st);
+        if (rc) return rc;
+        for (int i = np - 1; i >= 0; --i) {
+            const Act& in = i ? e->post_h[i - 1] : e->e;
+            rc = linear_wgrad(e, e->post[i], e->post_g[i].p, dt, e->post_g[i].ld, in, B, st);
+            if (rc) return rc;
+            if (i == 0) rc = linear_dgrad(e, e->post[i], e->post_g[i].p, dt, e->post_g[i].ld, B, embrace_bwd_epi(), st);
+            else rc = linear_dgrad(e, e->post[i], e->post_g[i].p, dt, e->post_g[i].ld, B, mask_epi(e->post_h[i - 1], e->post[i - 1].drop, e->post_g[i - 1]), st);
+            if (rc) return rc;
+        }
+        // docking layers
+        const int nf = (int)e->ffnn.size();
+        rc = linear_wgrad(e, e->dock0, e->dd0.p, dt, e->dd0.ld, e->ffnn_h[nf - 1], B, st);
+        if (rc) return rc;
+        rc = linear_dgrad(e, e->dock0, e->dd0.p, dt, e->dd0.ld, B, mask_epi(e->ffnn_h[nf - 1], e->ffnn[nf - 1].drop, e->ffnn_g[nf - 1]), st);
+        if (rc) return rc;
+        Act flat;
+        flat.p = e->cnn.back().a; flat.width = e->cnn_out; flat.ld = e->cnn_Lp_last * e->cnn_ld_last;
+        rc = linear_wgrad(e, e->dock1, e->dd1.p, dt, e->dd1.ld, flat, B, st);
+        if (rc) return rc;
+        {
+            Epilogue ep = base_epi(e, EPI_LINEAR, e->cnn.back().ga, e->cnn_Lp_last * e->cnn_ld_last);
+            ep.flatC = e->cnn_C_last; ep.flat_ldc = e->cnn_ld_last;
+            rc = linear_dgrad(e, e->dock1, e->dd1.p, dt, e->dd1.ld, B, ep, st);
+            if (rc) return rc;
+        }
+    } else if (s.kind == EMB_KIND_FFNN) {
+        const LinearLayer& hl = e->head.back();
+        const int nf = (int)e->ffnn.size();
+        rc = linear_wgrad(e, hl, g, g_dt, g_ld, e->ffnn_h[nf - 1], B, st);
+        if (rc) return rc;
+        rc = linear_dgrad(e, hl, g, g_dt, g_ld, B, mask_epi(e->ffnn_h[nf - 1], e->ffnn[nf - 1].drop, e->ffnn_g[nf - 1]), st);
+        if (rc) return rc;
+    } else {   // CNN: three plain Linear layers
+        Act flat;
+        flat.p = e->cnn.back().a; flat.width = e->cnn_out; flat.ld = e->cnn_Lp_last * e->cnn_ld_last;
+        for (int i = (int)e->head.size() - 1; i >= 0; --i) {
+            const Act& in = i ? e->head_h[i - 1] : flat;
+            rc = linear_wgrad(e, e->head[i], g, g_dt, g_ld, in, B, st);
+            if (rc) return rc;
+            Epilogue ep;
+            if (i) ep = base_epi(e, EPI_LINEAR, e->head_g[i - 1].p, e->head_g[i - 1].ld);
+            else {
+                ep = base_epi(e, EPI_LINEAR, e->cnn.back().ga, e->cnn_Lp_last * e->cnn_ld_last);
+                ep.flatC = e->cnn_C_last; ep.flat_ldc = e->cnn_ld_last;
+            }
+            rc = linear_dgrad(e, e->head[i], g, g_dt, g_ld, B, ep, st);
+            if (rc) return rc;
+            if (i) { g = e->head_g[i - 1].p; g_dt = dt; g_ld = e->head_g[i - 1].ld; }
+        }
+    }
+    if (s.kind != EMB_KIND_CNN) {
+        for (int i = (int)e->ffnn.size() - 1; i >= 0; --i) {
+            const Act& in = i ? e->ffnn_h[i - 1] : e->x0;
+            rc = linear_wgrad(e, e->ffnn[i], e->ffnn_g[i].p, dt, e->ffnn_g[i].ld, in, B, st);
+            if (rc) return rc;
+            if (i) {
+                rc = linear_dgrad(e, e->ffnn[i], e->ffnn_g[i].p, dt, e->ffnn_g[i].ld, B, mask_epi(e->ffnn_h[i - 1], e->ffnn[i - 1].drop, e->ffnn_g[i - 1]), st);
+                if (rc) return rc;
+            }
+        }
+    }
+    if (s.kind != EMB_KIND_FFNN) {
+        rc = cnn_backward(e, B, st);
+        if (rc) return rc;
+    }
+    return EMB_OK;
+}
+
+void fill_opt_scalars(EmbEngine* e, const EmbOptConfig& c, OptScalars* o) {
+    e->opt_t += 1;
+    const double t = (double)e->opt_t;
+    o->kind = c.kind;
+    o->lr = c.lr; o->wd = c.weight_decay; o->b1 = c.beta1; o->b2 = c.beta2; o->eps = c.eps; o->alpha = c.alpha;
+    o->bc1 = (float)(1.0 - std::pow((double)c.beta1, t));
+    o->bc2 = (float)(1.0 - std::pow((double)c.beta2, t));
+    o->bc2_sqrt = (float)std::sqrt(1.0 - std::pow((double)c.beta2, t));
+    o->nadam_c_g = o->nadam_c_m = 0.f;
+    if (c.kind == EMB_OPT_NADAM) {
+        double psi = c.momentum_decay;
+        double mu = c.beta1 * (1.0 - 0.5 * std::pow(0.96, t * psi));
+        double mu_next = c.beta1 * (1.0 - 0.5 * std::pow(0.96, (t + 1) * psi));
+        e->nadam_mu_product *= mu;
+        double mp = e->nadam_mu_product;
+        o->nadam_c_g = (float)(c.lr * (1.0 - mu) / (1.0 - mp));
+        o->nadam_c_m = (float)(c.lr * mu_next / (1.0 - mp * mu_next));
+    }
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* emb_last_error(void) { return g_last_error.c_str(); }
+int emb_abi_version(void) { return EMB_ABI_VERSION; }
+
+int emb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+int emb_create(const EmbArchSpec* spec, int32_t max_batch, int32_t precision, EmbEngine** out) {
+    if (!spec || !out) return set_error(EMB_E_ARG, "null argument");
+    if (max_batch < 1) return set_error(EMB_E_ARG, "max_batch must be >= 1");
+    if (precision != EMB_PREC_FP32 && precision != EMB_PREC_BF16) return set_error(EMB_E_ARG, "unknown precision %d", precision);
+    if (spec->kind < 0 || spec->kind > 2) return set_error(EMB_E_ARG, "unknown kind %d", spec->kind);
+    EmbEngine* e = new EmbEngine();
+    e->spec = *spec;
+    e->max_batch = max_batch;
+    e->prec = precision;
+    e->esize = precision == EMB_PREC_BF16 ? 2 : 4;
+    int rc = plan(e);
+    if (rc) { delete e; return rc; }
+    e->ws_bytes = carve(e, nullptr);
+    *out = e;
+    return EMB_OK;
+}
+
+void emb_destroy(EmbEngine* e) {
+    if (!e) return;
+    if (e->owns_memory) {
+        cudaFree(e->params); cudaFree(e->grads); cudaFree(e->buffers); cudaFree(e->opt_m); cudaFree(e->opt_v); cudaFree(e->ws);
+    }
+    delete e;
+}
+
+int64_t emb_param_count(const EmbEngine* e) { return e ? e->n_params : 0; }
+int64_t emb_buffer_count(const EmbEngine* e) { return e ? e->n_buffers : 0; }
+int64_t emb_workspace_bytes(const EmbEngine* e) { return e ? e->ws_bytes : 0; }
+int32_t emb_num_tensors(const EmbEngine* e) { return e ? (int32_t)e->tensors.size() : 0; }
+
+int emb_param_info(const EmbEngine* e, int32_t i, EmbParamInfo* out) {
+    if (!e || !out || i < 0 || i >= (int)e->tensors.size()) return set_error(EMB_E_ARG, "bad tensor index");
+    const Tensor& t = e->tensors[i];
+    memset(out, 0, sizeof *out);
+    strncpy(out->name, t.name.c_str(), sizeof(out->name) - 1);
+    out->offset = t.offset; out->numel = t.numel; out->ndim = t.ndim;
+    for (int k = 0; k < 3; ++k) out->shape[k] = t.shape[k];
+    out->is_buffer = t.is_buffer;
+    return EMB_OK;
+}
+
+int32_t emb_output_size(const EmbEngine* e, int32_t which) { return !e ? 0 : (which == 0 ? e->ffnn_out : e->cnn_out); }
+
+int emb_bind(EmbEngine* e, float* params, float* grads, float* buffers, float* opt_m, float* opt_v, void* workspace, int64_t workspace_bytes) {
+    if (!e) return set_error(EMB_E_ARG, "null engine");
+    if (emb_device_count() < 1) return set_error(EMB_E_NO_DEVICE, "no sm_100 (B200) device visible: this library has no CPU path");
+    if (!params && !workspace) {
+        const int64_t np = std::max<int64_t>(e->n_params, 4), nb = std::max<int64_t>(e->n_buffers, 4);
+        EMB_CUDA_OK(cudaMalloc(&e->params, np * sizeof(float)));
+        EMB_CUDA_OK(cudaMalloc(&e->grads, np * sizeof(float)));
+        EMB_CUDA_OK(cudaMalloc(&e->buffers, nb * sizeof(float)));
+        EMB_CUDA_OK(cudaMalloc(&e->opt_m, np * sizeof(float)));
+        EMB_CUDA_OK(cudaMalloc(&e->opt_v, np * sizeof(float)));
+        EMB_CUDA_OK(cudaMalloc(&e->ws, e->ws_bytes));
+        EMB_CUDA_OK(cudaMemset(e->params, 0, np * sizeof(float)));
+        EMB_CUDA_OK(cudaMemset(e->grads, 0, np * sizeof(float)));
+        EMB_CUDA_OK(cudaMemset(e->buffers, 0, nb * sizeof(float)));
+        EMB_CUDA_OK(cudaMemset(e->opt_m, 0, np * sizeof(float)));
+        EMB_CUDA_OK(cudaMemset(e->opt_v, 0, np * sizeof(float)));
+        e->owns_memory = true;
+    } else {
+        if (!params || !workspace) return set_error(EMB_E_ARG, "params and workspace must both be given");
+        if (workspace_bytes < e->ws_bytes) return set_error(EMB_E_ARG, "workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)e->ws_bytes);
+        if (((uintptr_t)workspace & 255) || ((uintptr_t)params & 15)) return set_error(EMB_E_ARG, "workspace must be 256-byte and params 16-byte aligned");
+        e->params = params; e->grads = grads; e->buffers = buffers; e->opt_m = opt_m; e->opt_v = opt_v; e->ws = (char*)workspace;
+    }
+    carve(e, e->ws);
+    RngState rs{e->seed, 0};
+    EMB_CUDA_OK(cudaMemcpy(e->rng, &rs, sizeof rs, cudaMemcpyHostToDevice));
+    EMB_CUDA_OK(cudaMemset(e->rec_count, 0, sizeof(int)));
+    cudaFuncSetAttribute(pool_bn_bwd_stage1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SEQ_LEN * 32 * 4);
+    cudaFuncSetAttribute(pool_bn_bwd_stage1_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SEQ_LEN * 32 * 4);
+    int rc = tc_init();
+    if (rc) return rc;
+    return EMB_OK;
+}
+
+int emb_set_seed(EmbEngine* e, uint64_t seed) {
+    if (!e) return set_error(EMB_E_ARG, "null engine");
+    e->seed = seed;
+    if (e->rng) {
+        RngState rs{seed, 0};
+        EMB_CUDA_OK(cudaMemcpy(e->rng, &rs, sizeof rs, cudaMemcpyHostToDevice));
+    }
+    return EMB_OK;
+}
+
+int emb_set_shard(EmbEngine* e, int64_t row_offset, int64_t global_batch) {
+    if (!e) return set_error(EMB_E_ARG, "null engine");
+    e->row_offset = row_offset;
+    e->global_batch = global_batch;
+    return EMB_OK;
+}
+
+int emb_set_allreduce(EmbEngine* e, EmbAllreduceFn fn, void* user) {
+    if (!e) return set_error(EMB_E_ARG, "null engine");
+    e->allreduce = fn;
+    e->allreduce_user = user;
+    return EMB_OK;
+}
+
+int emb_set_tensor_core(EmbEngine* e, int32_t on) {
+    if (!e) return set_error(EMB_E_ARG, "null engine");
+    if (on && e->prec != EMB_PREC_BF16) return set_error(EMB_E_UNSUPPORTED, "tensor-core GEMMs need EMB_PREC_BF16");
+    e->use_tc = on != 0;
+    return EMB_OK;
+}
+
+int64_t emb_launch_count(const EmbEngine* e) { return e ? e->launches : 0; }
+
+int emb_forward_train(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const float* availabilities, int32_t B,
+                      const EmbDraws* draws, float* logits_out, void* stream) {
+    int rc = check_ready(e, B, false);
+    if (rc) return rc;
+    return forward_impl(e, x_ffnn, bases, availabilities, B, true, draws, logits_out, (cudaStream_t)stream);
+}
+
+int emb_forward_infer(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const float* availabilities, int32_t B,
+                      const EmbDraws* draws, float* logits_out, float* probs_out, void* stream) {
+    int rc = check_ready(e, B, false);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* lg = logits_out ? logits_out : e->logits;
+    rc = forward_impl(e, x_ffnn, bases, availabilities, B, false, draws, lg, st);
+    if (rc) return rc;
+    if (probs_out) {
+        softmax_p1_kernel<<<cdiv(B, 256), 256, 0, st>>>(lg, probs_out, B);
+        EMB_CHECK_LAUNCH();
+        LAUNCHED(e);
+    }
+    return EMB_OK;
+}
+
+int emb_loss_ce_weighted(EmbEngine* e, const float* logits, const int32_t* labels, int32_t B, float* dlogits_out, void* stream) {
+    int rc = check_ready(e, B, false);
+    if (rc) return rc;
+    if (!logits || !labels) return set_error(EMB_E_ARG, "null logits/labels");
+    ce_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, labels, B, -1, -1, dlogits_out, e->rec, e->rec_count, EmbEngine::MAX_REC);
+    EMB_CHECK_LAUNCH();
+    LAUNCHED(e);
+    return EMB_OK;
+}
+
+int emb_backward(EmbEngine* e, const float* dlogits, void* stream) {
+    int rc = check_ready(e, e ? std::max(1, e->last_B) : 1, true);
+    if (rc) return rc;
+    if (!dlogits) return set_error(EMB_E_ARG, "null dlogits");
+    return backward_impl(e, dlogits, (cudaStream_t)stream);
+}
+
+int emb_opt_step(EmbEngine* e, const EmbOptConfig* cfg, void* stream) {
+    int rc = check_ready(e, 1, true);
+    if (rc) return rc;
+    if (!cfg || cfg->kind < 0 || cfg->kind > 3) return set_error(EMB_E_ARG, "bad optimizer config");
+    if (!e->opt_m || !e->opt_v) return set_error(EMB_E_STATE, "no optimizer state bound");
+    cudaStream_t st = (cudaStream_t)stream;
+    OptScalars h;
+    fill_opt_scalars(e, *cfg, &h);
+    // scalars travel through a small device slot written by a stream-ordered copy
+    OptScalars* d = e->opt_scalars;
+    EMB_CUDA_OK(cudaMemcpyAsync(d, &h, sizeof h, cudaMemcpyHostToDevice, st));
+    int grid = std::min<int64_t>(148 * 8, cdiv(e->n_params, 256));
+    opt_step_kernel<<<grid, 256, 0, st>>>(e->params, e->grads, e->opt_m, e->opt_v, d, (size_t)e->n_params);
+    EMB_CHECK_LAUNCH();
+    LAUNCHED(e);
+    return EMB_OK;
+}
+
+int emb_train_step(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const int32_t* labels, int32_t B,
+                   const EmbDraws* draws, const EmbOptConfig* cfg, void* stream) {
+    int rc = check_ready(e, B, true);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = forward_impl(e, x_ffnn, bases, nullptr, B, true, draws, e->logits, st);
+    if (rc) return rc;
+    rc = emb_loss_ce_weighted(e, e->logits, labels, B, e->dlogits, stream);
+    if (rc) return rc;
+    rc = backward_impl(e, e->dlogits, st);
+    if (rc) return rc;
+    if (cfg) rc = emb_opt_step(e, cfg, stream);
+    return rc;
+}
+
+int emb_train_step_host(EmbEngine* e, const float* x_ffnn_host, const uint8_t* bases_host, const int32_t* labels_host, int32_t B,
+                        const EmbOptConfig* cfg, EmbStepMetrics* metrics_host, void* stream) {
+    int rc = check_ready(e, B, true);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (e->spec.kind != EMB_KIND_CNN) EMB_CUDA_OK(cudaMemcpyAsync(e->in_x, x_ffnn_host, (size_t)B * e->spec.in_features * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (e->spec.kind != EMB_KIND_FFNN) EMB_CUDA_OK(cudaMemcpyAsync(e->in_bases, bases_host, (size_t)B * SEQ_LEN, cudaMemcpyHostToDevice, st));
+    EMB_CUDA_OK(cudaMemcpyAsync(e->in_labels, labels_host, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    EMB_CUDA_OK(cudaMemsetAsync(e->rec_count, 0, sizeof(int), st));
+    rc = emb_train_step(e, e->in_x, e->in_bases, e->in_labels, B, nullptr, cfg, stream);
+    if (rc) return rc;
+    if (metrics_host) {
+        EMB_CUDA_OK(cudaMemcpyAsync(metrics_host, e->rec, sizeof(EmbStepMetrics), cudaMemcpyDeviceToHost, st));
+        EMB_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    return EMB_OK;
+}
+
+int emb_predict_host(EmbEngine* e, const float* x_ffnn_host, const uint8_t* bases_host, const float* availabilities_host, int32_t B,
+                     float* probs_host, void* stream) {
+    int rc = check_ready(e, B, false);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (e->spec.kind != EMB_KIND_CNN) EMB_CUDA_OK(cudaMemcpyAsync(e->in_x, x_ffnn_host, (size_t)B * e->spec.in_features * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (e->spec.kind != EMB_KIND_FFNN) EMB_CUDA_OK(cudaMemcpyAsync(e->in_bases, bases_host, (size_t)B * SEQ_LEN, cudaMemcpyHostToDevice, st));
+    if (availabilities_host) EMB_CUDA_OK(cudaMemcpyAsync(e->in_avail, availabilities_host, (size_t)B * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = emb_forward_infer(e, e->in_x, e->in_bases, availabilities_host ? e->in_avail : nullptr, B, nullptr, e->logits, e->probs, stream);
+    if (rc) return rc;
+    EMB_CUDA_OK(cudaMemcpyAsync(probs_host, e->probs, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    EMB_CUDA_OK(cudaStreamSynchronize(st));
+    return EMB_OK;
+}
+
+int emb_metrics_reset(EmbEngine* e, void* stream) {
+    int rc = check_ready(e, 1, false);
+    if (rc) return rc;
+    EMB_CUDA_OK(cudaMemsetAsync(e->rec_count, 0, sizeof(int), (cudaStream_t)stream));
+    return EMB_OK;
+}
+
+int emb_metrics_read(EmbEngine* e, EmbStepMetrics* out_host, int32_t max_records, void* stream) {
+    int rc = check_ready(e, 1, false);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int n = 0;
+    EMB_CUDA_OK(cudaMemcpyAsync(&n, e->rec_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    EMB_CUDA_OK(cudaStreamSynchronize(st));
+    n = std::min(n, std::min(max_records, (int)EmbEngine::MAX_REC));
+    if (n > 0 && out_host) {
+        EMB_CUDA_OK(cudaMemcpyAsync(out_host, e->rec, (size_t)n * sizeof(EmbStepMetrics), cudaMemcpyDeviceToHost, st));
+        EMB_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    return n;
+}
+
+int emb_last_selection(EmbEngine* e, uint8_t* idx_out, int32_t B, void* stream) {
+    int rc = check_ready(e, B, false);
+    if (rc) return rc;
+    if (e->spec.kind != EMB_KIND_EMBRACENET) return set_error(EMB_E_STATE, "not an EmbraceNet engine");
+    EMB_CUDA_OK(cudaMemcpyAsync(idx_out, e->idx, (size_t)B * e->spec.embracement_size, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return EMB_OK;
+}
+
+// ---- single-kernel entry points ---------------------------------------------------------------
+int emb_k_onehot_conv_fwd(const uint8_t* bases, const float* w, const float* bias, int32_t B, int32_t C1, int32_t k, int32_t precision,
+                          void* y, void* stream) {
+    if (emb_device_count() < 1) return set_error(EMB_E_NO_DEVICE, "no sm_100 device");
+    if (B < 1 || C1 < 1 || k < 1 || !(k & 1)) return set_error(EMB_E_ARG, "bad shape");
+    size_t smem = (size_t)(k * 4 * C1 + C1) * sizeof(float) + SEQ_LEN + k + 16;
+    int grid = std::min(B, 148 * 8);
+    int ld = round_up(C1, 8);
+    if (precision) onehot_conv_fwd_kernel<bf16><<<grid, 256, smem, (cudaStream_t)stream>>>(bases, w, bias, (bf16*)y, B, C1, k, ld, 0);
+    else onehot_conv_fwd_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(bases, w, bias, (float*)y, B, C1, k, ld, 0);
+    EMB_CHECK_LAUNCH();
+    return EMB_OK;
+}
+
+int emb_k_onehot_conv_bwd(const uint8_t* bases, const void* dy, int32_t B, int32_t C1, int32_t k, int32_t precision, float* dw, float* dbias,
+                          void* stream) {
+    if (emb_device_count() < 1) return set_error(EMB_E_NO_DEVICE, "no sm_100 device");
+    if (B < 1 || C1 < 1 || k < 1 || !(k & 1) || C1 * k > OHB_MAXP * 256) return set_error(EMB_E_ARG, "bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    EMB_CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)C1 * 4 * k * sizeof(float), st));
+    EMB_CUDA_OK(cudaMemsetAsync(dbias, 0, (size_t)C1 * sizeof(float), st));
+    int grid = std::min(B, 148 * 4);
+    int ld = round_up(C1, 8);
+    if (precision) onehot_conv_bwd_kernel<bf16><<<grid, 256, 0, st>>>(bases, (const bf16*)dy, dw, dbias, B, C1, k, ld);
+    else onehot_conv_bwd_kernel<float><<<grid, 256, 0, st>>>(bases, (const float*)dy, dw, dbias, B, C1, k, ld);
+    EMB_CHECK_LAUNCH();
+    return EMB_OK;
+}
+
+int emb_k_linear_fwd(const float* a, const float* w, const float* bias, int32_t M, int32_t N, int32_t K, int32_t relu, int32_t tensor_core,
+                     float* out, void* stream) {
+    if (emb_device_count() < 1) return set_error(EMB_E_NO_DEVICE, "no sm_100 device");
+    if (tensor_core) return tc_linear_f32(a, w, bias, M, N, K, relu, out, (cudaStream_t)stream);
+    Operand A = make_operand(a, 0, OP_ROWMAJOR, K, M, K);
+    Operand W = make_operand(w, 0, OP_ROWMAJOR, K, N, K);
+    Epilogue ep = {};
+    ep.mode = EPI_LINEAR; ep.out = out; ep.out_dtype = 0; ep.ldo = N; ep.bias = bias; ep.relu = relu;
+    cudaError_t err = launch_gemm_simt(A, W, ep, M, N, K, 1, (cudaStream_t)stream);
+    if (err != cudaSuccess) return set_error(EMB_E_CUDA, "gemm launch: %s", cudaGetErrorString(err));
+    return EMB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,216 @@
+"""Host-side owner of one libembrace_sm100 engine.
+
+PyTorch is plumbing here: it owns the device memory (flat fp32 parameter / gradient / optimizer arenas
+and the workspace) and the stream; every computation is a call through the C ABI with raw device
+pointers.  There is deliberately no fallback: no GPU or no built library -> EmbError.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .archspec import ArchSpec
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine:
+    def __init__(self, spec: ArchSpec, max_batch: int, precision: str = 'fp32', device='cuda', seed: int = 0x5EED,
+                 tensor_core: bool = None):
+        self.lib = N.lib()
+        if not torch.cuda.is_available() or self.lib.emb_device_count() < 1:
+            raise N.EmbError('no B200 (sm_100) device visible: the EmbraceNet engine has no CPU fallback')
+        self.spec = spec
+        self.max_batch = int(max_batch)
+        self.precision = precision
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise N.EmbError('the engine runs on CUDA devices only')
+        self._h = C.c_void_p()
+        cspec = spec.to_c()
+        N.check(self.lib.emb_create(C.byref(cspec), self.max_batch, N.PREC[precision], C.byref(self._h)))
+        self.n_params = self.lib.emb_param_count(self._h)
+        self.n_buffers = self.lib.emb_buffer_count(self._h)
+        self.ws_bytes = self.lib.emb_workspace_bytes(self._h)
+        with torch.cuda.device(self.device):
+            f32 = dict(dtype=torch.float32, device=self.device)
+            self.params = torch.zeros(max(self.n_params, 4), **f32)
+            self.grads = torch.zeros(max(self.n_params, 4), **f32)
+            self.buffers = torch.zeros(max(self.n_buffers, 4), **f32)
+            self.opt_m = torch.zeros(max(self.n_params, 4), **f32)
+            self.opt_v = torch.zeros(max(self.n_params, 4), **f32)
+            self.workspace = torch.zeros(self.ws_bytes + 256, dtype=torch.uint8, device=self.device)
+            off = (-self.workspace.data_ptr()) % 256
+            self._ws_view = self.workspace[off:off + self.ws_bytes]
+            N.check(self.lib.emb_bind(self._h, _ptr(self.params), _ptr(self.grads), _ptr(self.buffers), _ptr(self.opt_m),
+                                      _ptr(self.opt_v), _ptr(self._ws_view), self.ws_bytes))
+        N.check(self.lib.emb_set_seed(self._h, seed))
+        self.table = []
+        info = N.EmbParamInfo()
+        for i in range(self.lib.emb_num_tensors(self._h)):
+            N.check(self.lib.emb_param_info(self._h, i, C.byref(info)))
+            self.table.append(dict(name=info.name.decode(), offset=info.offset, numel=info.numel,
+                                   shape=tuple(info.shape[:info.ndim]), is_buffer=bool(info.is_buffer)))
+        if tensor_core is None:
+            tensor_core = precision == 'bf16'
+        self.set_tensor_core(tensor_core)
+        self._keep = None
+
+    def __del__(self):
+        try:
+            if getattr(self, '_h', None) and self._h.value:
+                self.lib.emb_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- parameters ------------------------------------------------------------------------------
+    def view(self, entry, which='params'):
+        """Tensor view (reference state_dict shape) of one table entry in the params / grads / buffers arena."""
+        arena = self.buffers if entry['is_buffer'] else getattr(self, which)
+        return arena[entry['offset']:entry['offset'] + entry['numel']].view(entry['shape'])
+
+    def named_views(self, which='params'):
+        return {t['name']: self.view(t, which) for t in self.table if which == 'params' or not t['is_buffer']}
+
+    def load_numpy(self, P):
+        """P: {state_dict key: numpy array}; num_batches_tracked entries are ignored (host-side counter)."""
+        for t in self.table:
+            self.view(t).copy_(torch.from_numpy(np.asarray(P[t['name']], dtype=np.float32)).to(self.device))
+
+    def grads_numpy(self):
+        return {t['name']: self.view(t, 'grads').detach().cpu().numpy().astype(np.float64) for t in self.table if not t['is_buffer']}
+
+    def params_numpy(self):
+        return {t['name']: self.view(t).detach().cpu().numpy().astype(np.float64) for t in self.table}
+
+    def set_tensor_core(self, on):
+        N.check(self.lib.emb_set_tensor_core(self._h, 1 if on else 0))
+        self.tensor_core = bool(on)
+
+    def set_shard(self, row_offset, global_batch):
+        N.check(self.lib.emb_set_shard(self._h, int(row_offset), int(global_batch)))
+
+    # ---- draws -----------------------------------------------------------------------------------
+    def _draws(self, draws):
+        """dict of replayed uniforms (numpy or torch, reference layouts) -> EmbDraws (device pointers)."""
+        if draws is None:
+            self._keep = None
+            return None
+        d = N.EmbDraws()
+        keep = []
+
+        def dev(a, dtype):
+            t = torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a).to(device=self.device, dtype=dtype).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        for key, arr, p_list in (('ffnn_drop', d.ffnn_drop, self.spec.ffnn_dropout), ('cnn_drop', d.cnn_drop, self.spec.cnn_dropout),
+                                 ('post_drop', d.post_drop, self.spec.post_dropout)):
+            for i, u in enumerate(draws.get(key, []) or []):
+                if u is not None and i < len(p_list) and p_list[i] > 0:
+                    arr[i] = dev(u, torch.float32)
+        if draws.get('embrace_u') is not None:
+            d.embrace_u = dev(draws['embrace_u'], torch.float64)
+        if draws.get('modal_rows') is not None:
+            d.modal_rows = dev(draws['modal_rows'], torch.float32)
+        if draws.get('modal_u0') is not None:
+            d.modal_u0 = float(draws['modal_u0'])
+            d.has_modal_u0 = 1
+        self._keep = keep
+        return d
+
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- hot path ----------------------------------------------------------------------------------
+    def _inputs(self, x_ffnn, bases):
+        if x_ffnn is not None:
+            x_ffnn = x_ffnn.to(device=self.device, dtype=torch.float32).contiguous()
+        if bases is not None:
+            bases = bases.to(device=self.device, dtype=torch.uint8).contiguous()
+        return x_ffnn, bases
+
+    def forward(self, x_ffnn, bases, training, draws=None, availabilities=None, want_probs=False):
+        x_ffnn, bases = self._inputs(x_ffnn, bases)
+        B = (x_ffnn if x_ffnn is not None else bases).shape[0]
+        logits = torch.empty(B, 2, dtype=torch.float32, device=self.device)
+        av = availabilities.to(device=self.device, dtype=torch.float32).contiguous() if availabilities is not None else None
+        d = self._draws(draws)
+        dref = C.byref(d) if d is not None else None
+        if training:
+            N.check(self.lib.emb_forward_train(self._h, _ptr(x_ffnn), _ptr(bases), _ptr(av), B, dref, _ptr(logits), self.stream))
+            return logits
+        probs = torch.empty(B, dtype=torch.float32, device=self.device) if want_probs else None
+        N.check(self.lib.emb_forward_infer(self._h, _ptr(x_ffnn), _ptr(bases), _ptr(av), B, dref, _ptr(logits), _ptr(probs), self.stream))
+        return (logits, probs) if want_probs else logits
+
+    def loss(self, logits, labels, want_grad=True):
+        B = logits.shape[0]
+        labels = labels.to(device=self.device, dtype=torch.int32).contiguous().view(-1)
+        dlogits = torch.empty(B, 2, dtype=torch.float32, device=self.device) if want_grad else None
+        N.check(self.lib.emb_loss_ce_weighted(self._h, _ptr(logits.contiguous()), _ptr(labels), B, _ptr(dlogits), self.stream))
+        return dlogits
+
+    def backward(self, dlogits):
+        N.check(self.lib.emb_backward(self._h, _ptr(dlogits.to(torch.float32).contiguous()), self.stream))
+
+    @staticmethod
+    def opt_config(kind='adam', lr=1e-3, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, alpha=0.99, momentum_decay=4e-3):
+        return N.EmbOptConfig(N.OPT[kind], lr, weight_decay, betas[0], betas[1], eps, alpha, momentum_decay)
+
+    def opt_step(self, cfg):
+        N.check(self.lib.emb_opt_step(self._h, C.byref(cfg), self.stream))
+
+    def train_step(self, x_ffnn, bases, labels, cfg, draws=None):
+        x_ffnn, bases = self._inputs(x_ffnn, bases)
+        B = (x_ffnn if x_ffnn is not None else bases).shape[0]
+        labels = labels.to(device=self.device, dtype=torch.int32).contiguous().view(-1)
+        d = self._draws(draws)
+        N.check(self.lib.emb_train_step(self._h, _ptr(x_ffnn), _ptr(bases), _ptr(labels), B, C.byref(d) if d is not None else None,
+                                        C.byref(cfg) if cfg is not None else None, self.stream))
+
+    def train_step_host(self, x_ffnn_host, bases_host, labels_host, cfg):
+        """numpy / pinned-torch host buffers in, one EmbStepMetrics out (copies inside the call)."""
+        m = N.EmbStepMetrics()
+        B = (x_ffnn_host if x_ffnn_host is not None else bases_host).shape[0]
+
+        def hp(a):
+            if a is None:
+                return C.c_void_p(0)
+            return C.c_void_p(a.data_ptr() if torch.is_tensor(a) else a.ctypes.data)
+        N.check(self.lib.emb_train_step_host(self._h, hp(x_ffnn_host), hp(bases_host), hp(labels_host), B, C.byref(cfg), C.byref(m), self.stream))
+        return m
+
+    def predict_host(self, x_ffnn_host, bases_host, availabilities_host=None):
+        B = (x_ffnn_host if x_ffnn_host is not None else bases_host).shape[0]
+        out = np.empty(B, dtype=np.float32)
+
+        def hp(a):
+            if a is None:
+                return C.c_void_p(0)
+            return C.c_void_p(a.data_ptr() if torch.is_tensor(a) else a.ctypes.data)
+        N.check(self.lib.emb_predict_host(self._h, hp(x_ffnn_host), hp(bases_host), hp(availabilities_host), B,
+                                          C.c_void_p(out.ctypes.data), self.stream))
+        return out
+
+    def metrics_reset(self):
+        N.check(self.lib.emb_metrics_reset(self._h, self.stream))
+
+    def metrics_read(self, max_records=65536):
+        buf = (N.EmbStepMetrics * max_records)()
+        n = N.check(self.lib.emb_metrics_read(self._h, buf, max_records, self.stream))
+        return [dict(loss=buf[i].loss, tp=buf[i].tp, fp=buf[i].fp, fn=buf[i].fn, tn=buf[i].tn) for i in range(n)]
+
+    def last_selection(self, B):
+        idx = torch.empty(B, self.spec.embracement_size, dtype=torch.uint8, device=self.device)
+        N.check(self.lib.emb_last_selection(self._h, _ptr(idx), B, self.stream))
+        return idx
+
+    @property
+    def launch_count(self):
+        return self.lib.emb_launch_count(self._h)
