@@ -46,6 +46,39 @@ BN_MOMENTUM = 0.1
 
 
 # --------------------------------------------------------------------------
+# optional storage-precision emulation.  The reference is fp64 throughout; the CUDA engine's bf16
+# precision rounds every STORED activation / gradient and every GEMM weight operand to bf16 (fp32
+# accumulation).  `with quantized(bf16_round):` makes the oracle round at exactly those points, so the
+# bf16 kernels can be checked tightly; without it the oracle is the plain fp64 restatement.
+# --------------------------------------------------------------------------
+import contextlib
+
+_Q = None
+
+
+def bf16_round(x):
+    """Round-to-nearest-even to bfloat16, returned as float64."""
+    x32 = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+    b = x32.view(np.uint32)
+    r = ((b >> np.uint32(16)) & np.uint32(1)) + np.uint32(0x7FFF)
+    return ((b + r) & np.uint32(0xFFFF0000)).view(np.float32).astype(np.float64)
+
+
+@contextlib.contextmanager
+def quantized(fn):
+    global _Q
+    old, _Q = _Q, fn
+    try:
+        yield
+    finally:
+        _Q = old
+
+
+def _q(x):
+    return x if _Q is None else _Q(x)
+
+
+# --------------------------------------------------------------------------
 # shape helpers (utils.py:143-153, :178-202)
 # --------------------------------------------------------------------------
 def size_out_convolution(input_size, kernel, padding, stride):
@@ -240,7 +273,7 @@ def bn_train_bwd(dz, xhat, rstd, gamma):
     n = dz.shape[0] * dz.shape[2]
     dbeta = dz.sum(axis=(0, 2))
     dgamma = (dz * xhat).sum(axis=(0, 2))
-    dy = (gamma * rstd)[None, :, None] * (dz - dbeta[None, :, None] / n - xhat * dgamma[None, :, None] / n)
+    dy = (gamma * rstd)[None, :, None] * (_q(dz) - dbeta[None, :, None] / n - xhat * dgamma[None, :, None] / n)
     return dy, dgamma, dbeta
 
 
@@ -410,14 +443,14 @@ def _keys(spec):
 
 def ffnn_forward(spec, P, x, draws, training, cache):
     _, pre_f, _ = _keys(spec)
-    h = np.asarray(x, dtype=np.float64)
+    h = _q(np.asarray(x, dtype=np.float64))
     cache['ffnn'] = []
     for i, (u, p) in enumerate(zip(spec['ffnn_units'], spec['ffnn_dropout'])):
-        pre = linear_fwd(h, P[f'{pre_f}{3*i}.weight'], P[f'{pre_f}{3*i}.bias'])
+        pre = linear_fwd(h, _q(P[f'{pre_f}{3*i}.weight']), P[f'{pre_f}{3*i}.bias'])
         r = np.maximum(pre, 0.0)
         out, keep = dropout_fwd(r, draws['ffnn_drop'][i] if (training and p > 0) else None, p, training)
         cache['ffnn'].append((h, pre, keep, p))
-        h = out
+        h = _q(out)
     return h
 
 
@@ -427,10 +460,10 @@ def ffnn_backward(spec, P, g, cache, G):
         h, pre, keep, p = cache['ffnn'][i]
         if keep is not None:
             g = g * keep / (1.0 - p)
-        g = g * (pre > 0)
+        g = _q(g * (pre > 0))
         G[f'{pre_f}{3*i}.weight'] = g.T @ h
         G[f'{pre_f}{3*i}.bias'] = g.sum(axis=0)
-        g = g @ P[f'{pre_f}{3*i}.weight']
+        g = g @ _q(P[f'{pre_f}{3*i}.weight'])
     return g
 
 
@@ -442,7 +475,7 @@ def cnn_forward(spec, P, bases, draws, training, cache, new_buffers):
         W, b = P[f'{pre_c}{5*i}.weight'], P[f'{pre_c}{5*i}.bias']
         gamma, beta = P[f'{pre_c}{5*i+1}.weight'], P[f'{pre_c}{5*i+1}.bias']
         rm, rv = P[f'{pre_c}{5*i+1}.running_mean'], P[f'{pre_c}{5*i+1}.running_var']
-        y = onehot_conv_fwd(bases, W, b) if i == 0 else conv1d_fwd(x, W, b)
+        y = _q(onehot_conv_fwd(bases, W, b) if i == 0 else conv1d_fwd(x, _q(W), b))
         if training:
             z, xhat, rstd, nrm, nrv = bn_train_fwd(y, gamma, beta, rm, rv)
             new_buffers[f'{pre_c}{5*i+1}.running_mean'] = nrm
@@ -454,7 +487,7 @@ def cnn_forward(spec, P, bases, draws, training, cache, new_buffers):
         pooled, pos = relu_maxpool_fwd(z)
         out, keep = dropout_fwd(pooled, draws['cnn_drop'][i] if (training and p > 0) else None, p, training)
         cache['cnn'].append((x, z, xhat, rstd, pos, keep, p))
-        x = out
+        x = _q(out)
     return x.reshape(x.shape[0], -1)                  # channel-major flatten: c*L_last + l
 
 
@@ -471,12 +504,15 @@ def cnn_backward(spec, P, g_flat, bases, cache, G):
         dy, dgamma, dbeta = bn_train_bwd(dz, xhat, rstd, P[f'{pre_c}{5*i+1}.weight'])
         G[f'{pre_c}{5*i+1}.weight'] = dgamma
         G[f'{pre_c}{5*i+1}.bias'] = dbeta
+        db = dy.sum(axis=(0, 2))
+        dy = _q(dy)
         W = P[f'{pre_c}{5*i}.weight']
         if i == 0:
-            dW, db = onehot_conv_bwd(bases, dy, W.shape[2])
+            dW, _ = onehot_conv_bwd(bases, dy, W.shape[2])
             g = None
         else:
-            g, dW, db = conv1d_bwd(x, W, dy)
+            g, dW, _ = conv1d_bwd(x, _q(W), dy)
+            g = _q(g)
         G[f'{pre_c}{5*i}.weight'] = dW
         G[f'{pre_c}{5*i}.bias'] = db
 
@@ -493,13 +529,13 @@ def forward(spec, P, x_ffnn, bases, draws=None, training=False, availabilities=N
         h = ffnn_forward(spec, P, x_ffnn, draws, training, cache)
         n = len(spec['ffnn_units'])
         cache['head_in'] = h
-        return linear_fwd(h, P[f'{pre_f}{3*n}.weight'], P[f'{pre_f}{3*n}.bias']), cache
+        return linear_fwd(h, _q(P[f'{pre_f}{3*n}.weight']), P[f'{pre_f}{3*n}.bias']), cache
     if kind == 'cnn':
         f = cnn_forward(spec, P, bases, draws, training, cache, cache['new_buffers'])
-        h1 = linear_fwd(f, P['last_layer1.weight'], P['last_layer1.bias'])
-        h2 = linear_fwd(h1, P['last_layer2.weight'], P['last_layer2.bias'])
+        h1 = _q(linear_fwd(f, _q(P['last_layer1.weight']), P['last_layer1.bias']))
+        h2 = _q(linear_fwd(h1, _q(P['last_layer2.weight']), P['last_layer2.bias']))
         cache['head'] = (f, h1, h2)
-        return linear_fwd(h2, P['last_output.weight'], P['last_output.bias']), cache
+        return linear_fwd(h2, _q(P['last_output.weight']), P['last_output.bias']), cache
 
     B = x_ffnn.shape[0]
     xf = ffnn_forward(spec, P, x_ffnn, draws, training, cache)
@@ -510,23 +546,23 @@ def forward(spec, P, x_ffnn, bases, draws=None, training=False, availabilities=N
             availabilities = av
     p32, cum0 = embrace_probabilities(spec['p_ffnn'], B, availabilities)
     idx = embrace_select(draws['embrace_u'], cum0)
-    pre0 = linear_fwd(xf, P['embracenet.docking_0.weight'], P['embracenet.docking_0.bias'])
-    pre1 = linear_fwd(xc, P['embracenet.docking_1.weight'], P['embracenet.docking_1.bias'])
+    pre0 = linear_fwd(xf, _q(P['embracenet.docking_0.weight']), P['embracenet.docking_0.bias'])
+    pre1 = linear_fwd(xc, _q(P['embracenet.docking_1.weight']), P['embracenet.docking_1.bias'])
     d0, d1 = np.maximum(pre0, 0.0), np.maximum(pre1, 0.0)
-    e = np.where(idx == 1, d1, d0)
+    e = _q(np.where(idx == 1, d1, d0))
     cache.update(xf=xf, xc=xc, pre0=pre0, pre1=pre1, idx=idx, cum0=cum0, p32=p32, e=e,
                  availabilities=availabilities)
     h = e
     cache['post'] = []
     for i, (u, p) in enumerate(zip(spec['post_units'], spec['post_dropout'])):
-        pre = linear_fwd(h, P[f'post.{3*i}.weight'], P[f'post.{3*i}.bias'])
+        pre = linear_fwd(h, _q(P[f'post.{3*i}.weight']), P[f'post.{3*i}.bias'])
         r = np.maximum(pre, 0.0)
         out, keep = dropout_fwd(r, draws['post_drop'][i] if (training and p > 0) else None, p, training)
         cache['post'].append((h, pre, keep, p))
-        h = out
+        h = _q(out)
     n = len(spec['post_units'])
     cache['head_in'] = h
-    logits = linear_fwd(h, P[f'post.{3*n}.weight'], P[f'post.{3*n}.bias'])
+    logits = linear_fwd(h, _q(P[f'post.{3*n}.weight']), P[f'post.{3*n}.bias'])
     return logits, cache
 
 
@@ -539,37 +575,37 @@ def backward(spec, P, dlogits, bases, cache):
         n = len(spec['ffnn_units'])
         G[f'{pre_f}{3*n}.weight'] = g.T @ cache['head_in']
         G[f'{pre_f}{3*n}.bias'] = g.sum(axis=0)
-        ffnn_backward(spec, P, g @ P[f'{pre_f}{3*n}.weight'], cache, G)
+        ffnn_backward(spec, P, g @ _q(P[f'{pre_f}{3*n}.weight']), cache, G)
         return G
     if kind == 'cnn':
         f, h1, h2 = cache['head']
         for name, inp in (('last_output', h2), ('last_layer2', h1), ('last_layer1', f)):
             G[f'{name}.weight'] = g.T @ inp
             G[f'{name}.bias'] = g.sum(axis=0)
-            g = g @ P[f'{name}.weight']
+            g = _q(g @ _q(P[f'{name}.weight']))
         cnn_backward(spec, P, g, bases, cache, G)
         return G
     n = len(spec['post_units'])
     G[f'post.{3*n}.weight'] = g.T @ cache['head_in']
     G[f'post.{3*n}.bias'] = g.sum(axis=0)
-    g = g @ P[f'post.{3*n}.weight']
+    g = g @ _q(P[f'post.{3*n}.weight'])
     for i in reversed(range(n)):
         h, pre, keep, p = cache['post'][i]
         if keep is not None:
             g = g * keep / (1.0 - p)
-        g = g * (pre > 0)
+        g = _q(g * (pre > 0))
         G[f'post.{3*i}.weight'] = g.T @ h
         G[f'post.{3*i}.bias'] = g.sum(axis=0)
-        g = g @ P[f'post.{3*i}.weight']
+        g = g @ _q(P[f'post.{3*i}.weight'])
     idx = cache['idx']
-    dd0 = g * (idx == 0) * (cache['pre0'] > 0)
-    dd1 = g * (idx == 1) * (cache['pre1'] > 0)
+    dd0 = _q(g * (idx == 0) * (cache['pre0'] > 0))
+    dd1 = _q(g * (idx == 1) * (cache['pre1'] > 0))
     G['embracenet.docking_0.weight'] = dd0.T @ cache['xf']
     G['embracenet.docking_0.bias'] = dd0.sum(axis=0)
     G['embracenet.docking_1.weight'] = dd1.T @ cache['xc']
     G['embracenet.docking_1.bias'] = dd1.sum(axis=0)
-    ffnn_backward(spec, P, dd0 @ P['embracenet.docking_0.weight'], cache, G)
-    cnn_backward(spec, P, dd1 @ P['embracenet.docking_1.weight'], bases, cache, G)
+    ffnn_backward(spec, P, dd0 @ _q(P['embracenet.docking_0.weight']), cache, G)
+    cnn_backward(spec, P, _q(dd1 @ _q(P['embracenet.docking_1.weight'])), bases, cache, G)
     return G
 
 

@@ -535,6 +535,11 @@ int forward_impl(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const 
     Act flat;
     if (s.kind != EMB_KIND_FFNN) {
         if (!bases) return set_error(EMB_E_ARG, "bases is NULL");
+        if (training && bases != e->in_bases) {   // backward re-reads the bases: keep a private copy (256 B/row)
+            EMB_CUDA_OK(cudaMemcpyAsync(e->in_bases, bases, (size_t)B * SEQ_LEN, cudaMemcpyDeviceToDevice, st));
+            bases = e->in_bases;
+            e->last_bases = bases;
+        }
         rc = cnn_forward(e, bases, B, training, dr, st);
         if (rc) return rc;
         flat.p = e->cnn.back().a;
