@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- EmbraceNet train samples/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--arch L|S|M|W] [--batch B] [--precision bf16|fp32]
+
+Workload (BASELINE.json configs[2]): full EmbraceNet training, arch "L" (largest point of the
+search space), synthetic HEPG2-promoter shape (F=562, 256-bp bases), GLOBAL batch 8192 split over the N ranks
+(strong scaling), Adam with coupled L2.  A "step" is one pass of the train-step hot path over one batch.
+
+  value   device-resident inputs, emb_train_step (forward + loss + backward + optimizer), CUDA-event timed
+  e2e     the same through emb_train_step_host: pinned HOST buffers in, EmbStepMetrics back, copies inside
+          the timed region
+  roofline  the GEMM kernel class (Conv1d implicit GEMMs, docking, Linear; fwd/dgrad/wgrad), timed per launch
+          with CUDA event pairs inside the timed steps
+  cpu_baseline  oracle/torch_port.py (the reference's own PyTorch-CPU library calls, fp64) on a bounded sample
+
+--impl reference times that CPU port alone, with all host threads, on the same config/metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'embracenet_train_samples_per_sec'
+UNIT = 'samples/s'
+
+
+def arch(name):
+    from tests.golden.cases import ARCH_L, ARCH_S, ARCH_M, ARCH_W
+    return {'L': ARCH_L, 'S': ARCH_S, 'M': ARCH_M, 'W': ARCH_W}[name]
+
+
+def fwd_flops_per_sample(spec):
+    """Dense-equivalent forward FLOPs (2*MAC) per sample of the GEMM-shaped ops; layer 0 counted as a gather."""
+    from oracle.embracenet_oracle import cnn_lengths
+    f, fin = 0, spec['F']
+    for u in spec['ffnn_units']:
+        f += 2 * fin * u
+        fin = u
+    cin, L = 4, 256
+    for i, ((co, k), (Lc, Lp)) in enumerate(zip(zip(spec['cnn_channels'], spec['cnn_kernels']), cnn_lengths(spec['cnn_kernels']))):
+        f += (k * co * Lc) if i == 0 else 2 * cin * k * co * Lc
+        cin, L = co, Lp
+    C = spec['C']
+    f += 2 * (spec['ffnn_units'][-1] + cin * L) * C
+    fin = C
+    for u in spec['post_units']:
+        f += 2 * fin * u
+        fin = u
+    return f + 2 * fin * 2
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md 'clocks' line)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace('.', '').isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def synth_batches(spec, B, n, seed):
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    out = []
+    for _ in range(n):
+        x = rs.random_sample((B, spec['F'])).astype(np.float32)
+        bases = rs.randint(0, 4, size=(B, 256)).astype(np.uint8)
+        # planted signal: logistic on 4 features + base rate ~1/7 (HEPG2 promoters)
+        z = 3.0 * (x[:, :4].sum(1) - 2.0) - 1.9
+        y = (rs.random_sample(B) < 1 / (1 + np.exp(-z))).astype(np.int32)
+        out.append((x, bases, y))
+    return out
+
+
+def run_reference(args, spec, rank, world):
+    """The reference's CPU implementation of the path (PyTorch fp64 library calls, oracle/torch_port.py)."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import torch_port as TP
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    B = args.ref_batch
+    r = TP.time_train(spec, B, args.steps, args.warmup, seed=789)
+    val = r['samples_per_s']
+    sample = f'{args.steps} train steps of batch {B} (arch {args.arch}, fp64, torch {torch.__version__} CPU)'
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * r['seconds'] / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': f'EmbraceNet arch {args.arch} train step, global batch {args.batch} (bounded CPU sample: batch {B})',
+                   'arch': args.arch, 'global_batch': args.batch, 'in_features': spec['F'], 'optimizer': 'adam+L2'},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': r['threads'], 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--arch', default='L')
+    ap.add_argument('--batch', type=int, default=8192, help='GLOBAL batch')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--tensor-core', type=int, default=1)
+    ap.add_argument('--ref-batch', type=int, default=32, help='batch of the bounded CPU sample')
+    ap.add_argument('--cpu-baseline', type=int, default=1)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else max(args.warmup, 1)
+
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    spec = arch(args.arch)
+
+    if args.impl == 'reference':
+        run_reference(args, spec, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import embrace_b200
+    from tests.test_gpu_parity import to_archspec
+    from oracle.embracenet_oracle import init_params
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    if args.batch % world:
+        raise SystemExit('global batch must divide by the number of ranks')
+    B = args.batch // world
+    NBUF = 4
+
+    eng = embrace_b200.Engine(to_archspec(spec), max_batch=B, precision=args.precision, device=dev, seed=789,
+                              tensor_core=bool(args.tensor_core) and args.precision == 'bf16')
+    eng.load_numpy(init_params(spec, 789))                 # same random-init weights on every rank
+    cfg = eng.opt_config('adam', lr=4.1e-5, weight_decay=7.6e-4)
+    glob = synth_batches(spec, args.batch, NBUF, seed=789)   # every rank builds the global batches, keeps its rows
+    lo = rank * B
+    host = [(torch.from_numpy(x[lo:lo + B]).pin_memory(), torch.from_numpy(b[lo:lo + B]).pin_memory(),
+             torch.from_numpy(y[lo:lo + B]).pin_memory()) for x, b, y in glob]
+    devb = [(x.to(dev), b.to(dev), y.to(dev)) for x, b, y in host]
+    npos = [int(y.sum()) for _, _, y in glob]
+    if world > 1:
+        eng.set_shard(lo, args.batch)
+        eng.set_allreduce(lambda t: dist.all_reduce(t))
+
+    def step_device(i):
+        x, b, y = devb[i % NBUF]
+        if world > 1:
+            eng.set_global_positives(npos[i % NBUF])
+            eng.train_step(x, b, y, None)                    # forward + loss + backward
+            dist.all_reduce(eng.grads)                       # the one data-path collective (flat fp32 gradient arena)
+            eng.opt_step(cfg)
+        else:
+            eng.train_step(x, b, y, cfg)
+
+    def step_host(i):
+        x, b, y = host[i % NBUF]
+        if world > 1:
+            eng.set_global_positives(npos[i % NBUF])
+            xd, bd, yd = x.to(dev, non_blocking=True), b.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+            eng.metrics_reset()
+            eng.train_step(xd, bd, yd, None)
+            dist.all_reduce(eng.grads)
+            eng.opt_step(cfg)
+            return eng.metrics_read(1)[0]['loss']
+        return eng.train_step_host(x, b, y, cfg).loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count
+    eng.profile_gemm(True)
+    ms = timed(step_device, args.steps)
+    prof = eng.profile_read()
+    eng.profile_gemm(False)
+    launches = eng.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # second pass without the per-launch events (they serialise nothing, but keep `value` free of them)
+    ms_clean = timed(step_device, args.steps)
+    ms = min(ms, ms_clean)
+
+    for i in range(2):
+        step_host(i)
+    ms_e2e = timed(step_host, args.steps)
+    final = eng.metrics_read(4)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+    peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback (B200_PROFILING.md)'
+    achieved_tf = prof['flops'] / (prof['ms'] * 1e-3) / 1e12 if prof['ms'] > 0 else 0.0
+
+    value = args.batch * args.steps / (ms * 1e-3)
+    e2e = args.batch * args.steps / (ms_e2e * 1e-3)
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+        'config': {'workload': f'EmbraceNet arch {args.arch} full train step (fwd+loss+bwd+Adam), global batch {args.batch}, '
+                               f'F={spec["F"]}, 256-bp bases (BASELINE configs[2])',
+                   'arch': args.arch, 'global_batch': args.batch, 'per_gpu_batch': B, 'in_features': spec['F'],
+                   'optimizer': 'adam+L2', 'precision': args.precision, 'tensor_core': eng.tensor_core,
+                   'parallelism': f'dp{world}' if world > 1 else 'single',
+                   'l2': f'per-step working set (activations+gradients, ~{eng.ws_bytes / 1e9:.1f} GB) >> 126 MB L2; '
+                         f'inputs rotate over {NBUF} resident batches',
+                   'train_flops_per_sample': 3 * fwd_flops_per_sample(spec)},
+        'clocks': clocks,
+        'e2e': {'value': e2e, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
+                'h2d_bytes_per_step': int(args.batch * (spec['F'] * 4 + 256 + 4)), 'd2h_bytes_per_step': 20 * world},
+        'gpu_launches': int(launches),
+        'roofline': {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                     'frac': achieved_tf / peak_tf, 'traffic': None, 'kernel': 'GEMM class (conv implicit GEMM / docking / linear)',
+                     'kernel_ms_per_step': prof['ms'] / args.steps, 'kernel_launches_per_step': prof['launches'] / args.steps,
+                     'kernel_share_of_step': prof['ms'] / max(ms, 1e-9) if ms_clean >= ms else prof['ms'] / max(ms_clean, 1e-9),
+                     'peak_source': peak_src},
+        'final_loss': final[-1]['loss'] if final else None,
+    }
+    if world == 1 and args.cpu_baseline:
+        from oracle import torch_port as TP
+        torch.set_num_threads(os.cpu_count() or 1)
+        r = TP.time_train(spec, args.ref_batch, 2, 1, seed=789)
+        line['cpu_baseline'] = {'value': r['samples_per_s'], 'unit': UNIT, 'cores': r['threads'], 'kind': 'port',
+                                'sample': f'2 train steps of batch {args.ref_batch} after 1 warm-up (arch {args.arch}, fp64 PyTorch CPU '
+                                          f'port of the reference, {r["seconds"]:.1f} s)'}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -142,6 +142,9 @@ int emb_set_seed(EmbEngine* e, uint64_t seed);
  * global batch of global_batch rows (Philox counters, loss weights and BatchNorm n use the
  * global view; the collectives themselves are issued by the host, see emb_bn_partial_*). */
 int emb_set_shard(EmbEngine* e, int64_t row_offset, int64_t global_batch);
+/* number of positive labels in the GLOBAL batch of the next step (get_loss_weights_from_labels, utils.py:121-140,
+ * sees the whole batch; labels are known to the host before the step). -1: use the local count. */
+int emb_set_global_positives(EmbEngine* e, int64_t n_pos_global);
 
 /* ---- the hot path --------------------------------------------------------------------------*/
 /* EmbraceNetMultimodal.forward(..., is_training=True) (EmbraceNetMultimodal.py:159-193), or
@@ -190,6 +193,11 @@ int emb_metrics_read(EmbEngine* e, EmbStepMetrics* out_host, int32_t max_records
 int emb_last_selection(EmbEngine* e, uint8_t* idx_out, int32_t B, void* stream);
 /* number of kernel launches issued by this engine since creation (bench.py's gpu_launches) */
 int64_t emb_launch_count(const EmbEngine* e);
+/* Time every launch of the GEMM kernel class (nn.Linear, docking, Conv1d implicit GEMMs, their dgrad and
+ * wgrad) with CUDA event pairs on the launching stream; emb_profile_read synchronises the device and returns
+ * the summed kernel time, the algorithmic FLOPs (2*M*N*K per launch) and the launch count since enable. */
+int emb_profile_gemm(EmbEngine* e, int32_t enable);
+int emb_profile_read(EmbEngine* e, double* ms_out, double* flops_out, int64_t* launches_out);
 /* select GEMM back end: 0 = SIMT fp32-accumulate kernels only, 1 = tcgen05/TMEM/TMA where the shape
  * allows (bf16 precision only) */
 int emb_set_tensor_core(EmbEngine* e, int32_t on);

@@ -72,6 +72,7 @@ SIGNATURES = {
     'emb_bind': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64]),
     'emb_set_seed': (C.c_int, [_P, C.c_uint64]),
     'emb_set_shard': (C.c_int, [_P, C.c_int64, C.c_int64]),
+    'emb_set_global_positives': (C.c_int, [_P, C.c_int64]),
     'emb_forward_train': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.POINTER(EmbDraws), _P, _P]),
     'emb_forward_infer': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.POINTER(EmbDraws), _P, _P, _P]),
     'emb_loss_ce_weighted': (C.c_int, [_P, _P, _P, C.c_int32, _P, _P]),
@@ -85,6 +86,8 @@ SIGNATURES = {
     'emb_last_selection': (C.c_int, [_P, _P, C.c_int32, _P]),
     'emb_launch_count': (C.c_int64, [_P]),
     'emb_set_tensor_core': (C.c_int, [_P, C.c_int32]),
+    'emb_profile_gemm': (C.c_int, [_P, C.c_int32]),
+    'emb_profile_read': (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     'emb_set_allreduce': (C.c_int, [_P, ALLREDUCE_FN, _P]),
     'emb_k_onehot_conv_fwd': (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     'emb_k_onehot_conv_bwd': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),

@@ -109,11 +109,17 @@ struct EmbEngine {
     // optimizer / shard state
     int64_t opt_t = 0;
     double nadam_mu_product = 1.0;
-    int64_t row_offset = 0, global_batch = -1;
+    int64_t row_offset = 0, global_batch = -1, global_pos = -1;
     uint64_t seed = 0x5EEDull;
     EmbAllreduceFn allreduce = nullptr;
     void* allreduce_user = nullptr;
     int64_t launches = 0;
+    // per-kernel timing of the GEMM class (bench.py roofline): CUDA event pairs around each launch
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    size_t prof_used = 0;
+    double prof_flops = 0;
+    int64_t prof_launches = 0;
 };
 
 namespace {
@@ -332,8 +338,26 @@ Operand input_operand(EmbEngine* e, const LinearLayer& l, const Act& in, int B, 
     return o;
 }
 
+void prof_begin(EmbEngine* e, double flops, cudaStream_t st) {
+    if (!e->prof_on) return;
+    if (e->prof_used + 2 > e->prof_ev.size()) {
+        if (e->prof_ev.size() >= (1u << 16)) return;
+        for (int i = 0; i < 512; ++i) { cudaEvent_t ev; cudaEventCreate(&ev); e->prof_ev.push_back(ev); }
+    }
+    cudaEventRecord(e->prof_ev[e->prof_used], st);
+    e->prof_flops += flops;
+    e->prof_launches += 1;
+}
+void prof_end(EmbEngine* e, cudaStream_t st) {
+    if (!e->prof_on || e->prof_used + 2 > e->prof_ev.size()) return;
+    cudaEventRecord(e->prof_ev[e->prof_used + 1], st);
+    e->prof_used += 2;
+}
+
 int run_gemm(EmbEngine* e, const Operand& A, const Operand& B, const Epilogue& ep, int M, int N, int K, int split_k, cudaStream_t st) {
+    prof_begin(e, 2.0 * M * N * K, st);
     cudaError_t err = launch_gemm_simt(A, B, ep, M, N, K, split_k, st);
+    prof_end(e, st);
     if (err != cudaSuccess) return set_error(EMB_E_CUDA, "gemm launch: %s", cudaGetErrorString(err));
     LAUNCHED(e);
     return EMB_OK;
@@ -764,6 +788,7 @@ int emb_create(const EmbArchSpec* spec, int32_t max_batch, int32_t precision, Em
 
 void emb_destroy(EmbEngine* e) {
     if (!e) return;
+    for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     if (e->owns_memory) {
         cudaFree(e->params); cudaFree(e->grads); cudaFree(e->buffers); cudaFree(e->opt_m); cudaFree(e->opt_v); cudaFree(e->ws);
     }
@@ -839,6 +864,12 @@ int emb_set_shard(EmbEngine* e, int64_t row_offset, int64_t global_batch) {
     return EMB_OK;
 }
 
+int emb_set_global_positives(EmbEngine* e, int64_t n_pos_global) {
+    if (!e) return set_error(EMB_E_ARG, "null engine");
+    e->global_pos = n_pos_global;
+    return EMB_OK;
+}
+
 int emb_set_allreduce(EmbEngine* e, EmbAllreduceFn fn, void* user) {
     if (!e) return set_error(EMB_E_ARG, "null engine");
     e->allreduce = fn;
@@ -854,6 +885,30 @@ int emb_set_tensor_core(EmbEngine* e, int32_t on) {
 }
 
 int64_t emb_launch_count(const EmbEngine* e) { return e ? e->launches : 0; }
+
+int emb_profile_gemm(EmbEngine* e, int32_t enable) {
+    if (!e) return set_error(EMB_E_ARG, "null engine");
+    e->prof_on = enable != 0;
+    e->prof_used = 0;
+    e->prof_flops = 0;
+    e->prof_launches = 0;
+    return EMB_OK;
+}
+
+int emb_profile_read(EmbEngine* e, double* ms_out, double* flops_out, int64_t* launches_out) {
+    if (!e) return set_error(EMB_E_ARG, "null engine");
+    EMB_CUDA_OK(cudaDeviceSynchronize());
+    double ms = 0;
+    for (size_t i = 0; i + 1 < e->prof_used; i += 2) {
+        float t = 0;
+        EMB_CUDA_OK(cudaEventElapsedTime(&t, e->prof_ev[i], e->prof_ev[i + 1]));
+        ms += t;
+    }
+    if (ms_out) *ms_out = ms;
+    if (flops_out) *flops_out = e->prof_flops;
+    if (launches_out) *launches_out = e->prof_launches;
+    return EMB_OK;
+}
 
 int emb_forward_train(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const float* availabilities, int32_t B,
                       const EmbDraws* draws, float* logits_out, void* stream) {
@@ -882,7 +937,9 @@ int emb_loss_ce_weighted(EmbEngine* e, const float* logits, const int32_t* label
     int rc = check_ready(e, B, false);
     if (rc) return rc;
     if (!logits || !labels) return set_error(EMB_E_ARG, "null logits/labels");
-    ce_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, labels, B, -1, -1, dlogits_out, e->rec, e->rec_count, EmbEngine::MAX_REC);
+    const bool sharded = e->global_batch > 0 && e->global_pos >= 0;
+    ce_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, labels, B, sharded ? e->global_pos : -1, sharded ? e->global_batch : -1,
+                                                         dlogits_out, e->rec, e->rec_count, EmbEngine::MAX_REC);
     EMB_CHECK_LAUNCH();
     LAUNCHED(e);
     return EMB_OK;

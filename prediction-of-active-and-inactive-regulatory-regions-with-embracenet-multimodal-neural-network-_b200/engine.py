@@ -94,6 +94,24 @@ class Engine:
     def set_shard(self, row_offset, global_batch):
         N.check(self.lib.emb_set_shard(self._h, int(row_offset), int(global_batch)))
 
+    def set_global_positives(self, n_pos):
+        N.check(self.lib.emb_set_global_positives(self._h, int(n_pos)))
+
+    def set_allreduce(self, fn):
+        """fn(tensor_float64) -> None performs an in-place SUM all-reduce of a device tensor (SyncBN statistics)."""
+        base = self._ws_view.data_ptr()
+
+        def cb(user, ptr, count, stream):
+            try:
+                off = ptr - base
+                fn(self._ws_view[off:off + count * 8].view(torch.float64))
+                return 0
+            except Exception as ex:           # never unwind through C
+                print('allreduce callback failed:', ex)
+                return 1
+        self._allreduce_cb = N.ALLREDUCE_FN(cb) if fn is not None else N.ALLREDUCE_FN()
+        N.check(self.lib.emb_set_allreduce(self._h, self._allreduce_cb, None))
+
     # ---- draws -----------------------------------------------------------------------------------
     def _draws(self, draws):
         """dict of replayed uniforms (numpy or torch, reference layouts) -> EmbDraws (device pointers)."""
@@ -210,6 +228,14 @@ class Engine:
         idx = torch.empty(B, self.spec.embracement_size, dtype=torch.uint8, device=self.device)
         N.check(self.lib.emb_last_selection(self._h, _ptr(idx), B, self.stream))
         return idx
+
+    def profile_gemm(self, enable=True):
+        N.check(self.lib.emb_profile_gemm(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+        N.check(self.lib.emb_profile_read(self._h, C.byref(ms), C.byref(fl), C.byref(n)))
+        return dict(ms=ms.value, flops=fl.value, launches=n.value)
 
     @property
     def launch_count(self):
