@@ -215,9 +215,15 @@ int emb_k_onehot_conv_fwd(const uint8_t* bases, const float* w, const float* bia
                           int32_t k, int32_t precision, void* y, void* stream);
 int emb_k_onehot_conv_bwd(const uint8_t* bases, const void* dy, int32_t B, int32_t C1, int32_t k,
                           int32_t precision, float* dw, float* dbias, void* stream);
-/* out[M,N] = A[M,K] * W[N,K]^T + bias  (nn.Linear), fp32 in/out, via the engine's GEMM back end */
-int emb_k_linear_fwd(const float* a, const float* w, const float* bias, int32_t M, int32_t N, int32_t K,
-                     int32_t relu, int32_t tensor_core, float* out, void* stream);
+/* One GEMM-shaped op of the step on either back end (backend 0 = SIMT fp32-accumulate kernel, 1 = tcgen05/TMEM/TMA
+ * kernel); fp32 in / fp32 out, inputs rounded to bf16 as the bf16 precision does.  kind:
+ *   0 linear fwd   a[M,K] b[N,K] -> out[M,N]       3 conv fwd   a[B,L,Cin]  b=W[Cout,Cin,taps] -> out[B*L,Cout]
+ *   1 linear dgrad a[M,K] b[K,N] -> out[M,N]       4 conv dgrad a[B,L,Cout] b=W[Cout,Cin,taps] -> out[B*L,Cin]
+ *   2 linear wgrad a[K,M] b[K,N] -> out[M,N]       5 conv wgrad a[B,L,Cout] b=act[B,L,Cin]     -> out=dW[Cout,Cin,taps]
+ * (nn.Linear / nn.Conv1d(stride 1, "same" padding) forward and their autograd formulas; all inner widths multiples
+ * of 8).  Synchronises the stream. */
+int emb_k_gemm(int32_t kind, int32_t backend, const float* a, const float* b, float* out, int32_t M, int32_t N, int32_t K,
+               int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t taps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,7 @@ struct Tensor {       // one state_dict entry
 
 struct LinearLayer {
     int in, out;
+    bf16* wc;         // bf16 operand copy [out][round_up(in,8)] (permuted to channels-last order when perm_in)
     int64_t w, b;     // offsets into the params arena
     float drop;
     bool relu;
@@ -52,6 +53,7 @@ struct ConvLayer {
     int64_t w, b, gamma, beta;   // params arena
     int64_t rm, rv;              // buffers arena
     float drop;
+    bf16* wc;                    // bf16 operand copy [k][cout][round_up(cin,8)]
     // workspace
     void *y, *a, *dy, *ga;
     float *scale, *shift, *mean, *rstd;
@@ -234,6 +236,28 @@ Act take_act(Bump& bp, int64_t rows, int width, int esize) {
     return a;
 }
 
+// bf16 GEMM-operand copies of the fp32 master weights, refreshed at the start of every forward
+__global__ void wcache_linear_kernel(const float* __restrict__ w, bf16* __restrict__ out, int N, int K, int ldk, int perm, int L, int C) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * ldk) return;
+    int n = i / ldk, kk = i - (size_t)n * ldk;
+    float v = 0.f;
+    if (kk < K) {
+        int src = kk;
+        if (perm) { int l = kk / C, c = kk - l * C; src = c * L + l; }
+        v = w[(size_t)n * K + src];
+    }
+    out[i] = __float2bfloat16_rn(v);
+}
+__global__ void wcache_conv_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int taps, int ldc) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)taps * Cout * ldc) return;
+    int c = i % ldc;
+    size_t r = i / ldc;
+    int o = r % Cout, tap = r / Cout;
+    out[i] = __float2bfloat16_rn(c < Cin ? w[((size_t)o * Cin + c) * taps + tap] : 0.f);
+}
+
 // carve the workspace; with base == nullptr only the size is computed
 int64_t carve(EmbEngine* e, char* base) {
     Bump bp{base};
@@ -252,6 +276,14 @@ int64_t carve(EmbEngine* e, char* base) {
     e->in_bases = bp.take<uint8_t>(Bm * SEQ_LEN);
     e->in_labels = bp.take<int32_t>(Bm);
     e->in_avail = bp.take<float>(Bm * 2);
+    if (e->prec == EMB_PREC_BF16) {
+        auto wl = [&](LinearLayer& l) { l.wc = bp.take<bf16>((int64_t)l.out * round_up(l.in, 8)); };
+        for (auto& l : e->ffnn) wl(l);
+        for (auto& l : e->post) wl(l);
+        for (auto& l : e->head) wl(l);
+        if (s.kind == EMB_KIND_EMBRACENET) { wl(e->dock0); wl(e->dock1); }
+        for (size_t i = 1; i < e->cnn.size(); ++i) e->cnn[i].wc = bp.take<bf16>((int64_t)e->cnn[i].k * e->cnn[i].cout * round_up(e->cnn[i].cin, 8));
+    }
     if (s.kind != EMB_KIND_CNN) {
         e->x0 = take_act(bp, Bm, s.in_features, es);
         for (auto& l : e->ffnn) {
@@ -370,6 +402,55 @@ int pick_split_k(int M, int N, int K) {
     return std::min(want, maxk);
 }
 
+int run_tc(EmbEngine* e, const TcProblem& pr, const Epilogue& ep, double flops, cudaStream_t st) {
+    prof_begin(e, flops, st);
+    int rc = tc_gemm(pr, ep, st);
+    prof_end(e, st);
+    if (rc) return rc;
+    LAUNCHED(e);
+    return EMB_OK;
+}
+
+bool tc_on(const EmbEngine* e) { return e->use_tc && e->prec == EMB_PREC_BF16; }
+
+// can this Linear layer's GEMMs run on the tensor-core kernel?  (the flattened CNN input must be dense)
+bool tc_linear_ok(const EmbEngine* e, const LinearLayer& l) {
+    if (!tc_on(e) || l.out < 16 || l.in < 16) return false;
+    if (l.perm_in && e->cnn_ld_last != e->cnn_C_last) return false;
+    return true;
+}
+
+int refresh_wcache(EmbEngine* e, cudaStream_t st) {
+    if (!tc_on(e)) return EMB_OK;
+    auto wl = [&](const LinearLayer& l) -> int {
+        if (!l.wc) return EMB_OK;
+        const int ldk = round_up(l.in, 8);
+        size_t tot = (size_t)l.out * ldk;
+        wcache_linear_kernel<<<cdiv(tot, 256), 256, 0, st>>>(e->params + l.w, l.wc, l.out, l.in, ldk, l.perm_in ? 1 : 0, e->cnn_Lp_last, e->cnn_C_last);
+        EMB_CHECK_LAUNCH();
+        LAUNCHED(e);
+        return EMB_OK;
+    };
+    int rc;
+    for (auto& l : e->ffnn) if ((rc = wl(l))) return rc;
+    for (auto& l : e->post) if ((rc = wl(l))) return rc;
+    for (auto& l : e->head) if ((rc = wl(l))) return rc;
+    if (e->spec.kind == EMB_KIND_EMBRACENET) { if ((rc = wl(e->dock0))) return rc; if ((rc = wl(e->dock1))) return rc; }
+    for (size_t i = 1; i < e->cnn.size(); ++i) {
+        ConvLayer& c = e->cnn[i];
+        const int ldc = round_up(c.cin, 8);
+        size_t tot = (size_t)c.k * c.cout * ldc;
+        wcache_conv_kernel<<<cdiv(tot, 256), 256, 0, st>>>(e->params + c.w, c.wc, c.cout, c.cin, c.k, ldc);
+        EMB_CHECK_LAUNCH();
+        LAUNCHED(e);
+    }
+    return EMB_OK;
+}
+
+bool tc_conv_ok(const EmbEngine* e, const ConvLayer& c) {
+    return tc_on(e) && c.Lc <= 128 && c.cin >= 16 && c.cout >= 16 && (c.cin % 8) == 0 && (c.cout % 8) == 0;
+}
+
 // y = [dropout]([relu](x W^T + b))
 int linear_forward(EmbEngine* e, const LinearLayer& l, const Act& in, const Act& out, int B, bool training,
                    const float* drop_u, uint32_t stream_id, cudaStream_t st) {
@@ -379,6 +460,12 @@ int linear_forward(EmbEngine* e, const LinearLayer& l, const Act& in, const Act&
     ep.bias = e->params + l.b;
     ep.relu = l.relu;
     if (training && l.drop > 0.f) { ep.drop_p = l.drop; ep.drop_u = drop_u; ep.rng_stream = stream_id; }
+    if (tc_linear_ok(e, l)) {
+        TcProblem pr = {};
+        pr.kind = TC_LINEAR_FWD; pr.a = (const bf16*)in.p; pr.lda = in.ld; pr.b = l.wc; pr.ldb = round_up(l.in, 8);
+        pr.M = B; pr.N = l.out; pr.K = l.in;
+        return run_tc(e, pr, ep, 2.0 * B * l.out * l.in, st);
+    }
     return run_gemm(e, A, W, ep, B, l.out, l.in, 1, st);
 }
 
@@ -388,7 +475,15 @@ int linear_wgrad(EmbEngine* e, const LinearLayer& l, const void* g, int g_dtype,
     Operand X = input_operand(e, l, in, B, true);
     Epilogue ep = base_epi(e, EPI_ATOMIC, e->grads + l.w, l.in);
     if (l.perm_in) { ep.map = MAP_W_PERM; ep.mapC = e->cnn_C_last; ep.mapL = e->cnn_Lp_last; ep.map_wrows = l.in; }
-    int rc = run_gemm(e, A, X, ep, l.out, l.in, B, pick_split_k(l.out, l.in, B), st);
+    int rc;
+    if (tc_linear_ok(e, l) && g_dtype == 1 && (g_ld % 8) == 0) {
+        TcProblem pr = {};
+        pr.kind = TC_LINEAR_WGRAD; pr.a = (const bf16*)g; pr.lda = g_ld; pr.b = (const bf16*)in.p; pr.ldb = in.ld;
+        pr.M = l.out; pr.N = l.in; pr.K = B;
+        rc = run_tc(e, pr, ep, 2.0 * B * l.out * l.in, st);
+    } else {
+        rc = run_gemm(e, A, X, ep, l.out, l.in, B, pick_split_k(l.out, l.in, B), st);
+    }
     if (rc) return rc;
     dim3 grid(cdiv(l.out, 32), std::min(64, cdiv(B, 8)));
     if (g_dtype) colsum_kernel<bf16><<<grid, dim3(32, 8), 0, st>>>((const bf16*)g, e->grads + l.b, B, l.out, g_ld);
@@ -400,6 +495,12 @@ int linear_wgrad(EmbEngine* e, const LinearLayer& l, const void* g, int g_dtype,
 
 // gradient w.r.t. the layer input: acc = g W, finished by `ep`
 int linear_dgrad(EmbEngine* e, const LinearLayer& l, const void* g, int g_dtype, int g_ld, int B, Epilogue ep, cudaStream_t st) {
+    if (tc_linear_ok(e, l) && g_dtype == 1 && (g_ld % 8) == 0) {
+        TcProblem pr = {};
+        pr.kind = TC_LINEAR_DGRAD; pr.a = (const bf16*)g; pr.lda = g_ld; pr.b = l.wc; pr.ldb = round_up(l.in, 8);
+        pr.M = B; pr.N = l.in; pr.K = l.out;
+        return run_tc(e, pr, ep, 2.0 * B * l.out * l.in, st);
+    }
     Operand A = make_operand(g, g_dtype, OP_ROWMAJOR, g_ld, B, l.out);
     Operand W = weight_operand(e, l, true);
     return run_gemm(e, A, W, ep, B, l.in, l.out, 1, st);
@@ -417,14 +518,22 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
             EMB_CHECK_LAUNCH();
             LAUNCHED(e);
         } else {
-            ConvLayer& pr = e->cnn[i - 1];
-            Operand A = make_operand(pr.a, dt, OP_CONV_SHIFT, pr.ld, B * c.Lc, c.k * c.cin);
+            ConvLayer& pr_ = e->cnn[i - 1];
+            Operand A = make_operand(pr_.a, dt, OP_CONV_SHIFT, pr_.ld, B * c.Lc, c.k * c.cin);
             A.L = c.Lc; A.C = c.cin; A.taps = c.k; A.pad = c.pad; A.sign = 1;
             Operand W = make_operand(e->params + c.w, 0, OP_CONV_W_FWD, 0, c.cout, c.k * c.cin);
             W.C = c.cin; W.taps = c.k; W.round_bf16 = e->prec == EMB_PREC_BF16;
             Epilogue ep = base_epi(e, EPI_LINEAR, c.y, c.ld);
             ep.bias = e->params + c.b;
-            int rc = run_gemm(e, A, W, ep, B * c.Lc, c.cout, c.k * c.cin, 1, st);
+            int rc;
+            if (tc_conv_ok(e, c)) {
+                TcProblem pr = {};
+                pr.kind = TC_CONV_FWD; pr.a = (const bf16*)pr_.a; pr.lda = pr_.ld; pr.b = c.wc; pr.ldb = round_up(c.cin, 8);
+                pr.M = B * c.Lc; pr.N = c.cout; pr.B = B; pr.L = c.Lc; pr.Cin = c.cin; pr.Cout = c.cout; pr.taps = c.k; pr.pad = c.pad;
+                rc = run_tc(e, pr, ep, 2.0 * B * c.Lc * c.cout * c.k * c.cin, st);
+            } else {
+                rc = run_gemm(e, A, W, ep, B * c.Lc, c.cout, c.k * c.cin, 1, st);
+            }
             if (rc) return rc;
         }
         const int64_t R = (int64_t)B * c.Lc;
@@ -498,13 +607,23 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
             LAUNCHED(e);
         } else {
             ConvLayer& pr = e->cnn[i - 1];
+            const bool tc = tc_conv_ok(e, c);
+            const double flops = 2.0 * R * c.cout * c.k * c.cin;
             // wgrad: dW[o][c][tap] = sum_{b,l} dy[b,l,o] * a_prev[b, l+tap-pad, c]
             Operand A = make_operand(c.dy, dt, OP_TRANSPOSED, c.ld, c.cout, (int)R);
             Operand X = make_operand(pr.a, dt, OP_CONV_SHIFT_T, pr.ld, c.k * c.cin, (int)R);
             X.L = c.Lc; X.C = c.cin; X.taps = c.k; X.pad = c.pad; X.sign = 1;
             Epilogue ep = base_epi(e, EPI_ATOMIC, e->grads + c.w, 0);
             ep.map = MAP_CONV_W; ep.mapC = c.cin; ep.map_taps = c.k;
-            int rc = run_gemm(e, A, X, ep, c.cout, c.k * c.cin, (int)R, pick_split_k(c.cout, c.k * c.cin, (int)R), st);
+            int rc;
+            if (tc) {
+                TcProblem tp = {};
+                tp.kind = TC_CONV_WGRAD; tp.a = (const bf16*)c.dy; tp.lda = c.ld; tp.b = (const bf16*)pr.a; tp.ldb = pr.ld;
+                tp.M = c.cout; tp.N = c.cin; tp.B = B; tp.L = c.Lc; tp.Cin = c.cin; tp.Cout = c.cout; tp.taps = c.k; tp.pad = c.pad;
+                rc = run_tc(e, tp, ep, flops, st);
+            } else {
+                rc = run_gemm(e, A, X, ep, c.cout, c.k * c.cin, (int)R, pick_split_k(c.cout, c.k * c.cin, (int)R), st);
+            }
             if (rc) return rc;
             // dgrad: ga_prev[b,l',c] = sum_{tap,o} dy[b, l'-tap+pad, o] * W[o][c][tap]
             Operand G = make_operand(c.dy, dt, OP_CONV_SHIFT, c.ld, (int)R, c.k * c.cout);
@@ -512,7 +631,14 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
             Operand W = make_operand(e->params + c.w, 0, OP_CONV_W_DGRAD, 0, c.cin, c.k * c.cout);
             W.C = c.cout; W.taps = c.k; W.wrows = c.cin; W.round_bf16 = e->prec == EMB_PREC_BF16;
             Epilogue ed = base_epi(e, EPI_LINEAR, pr.ga, pr.ld);
-            rc = run_gemm(e, G, W, ed, (int)R, c.cin, c.k * c.cout, 1, st);
+            if (tc) {
+                TcProblem tp = {};
+                tp.kind = TC_CONV_DGRAD; tp.a = (const bf16*)c.dy; tp.lda = c.ld; tp.b = c.wc; tp.ldb = round_up(c.cin, 8);
+                tp.M = (int)R; tp.N = c.cin; tp.B = B; tp.L = c.Lc; tp.Cin = c.cin; tp.Cout = c.cout; tp.taps = c.k; tp.pad = c.pad;
+                rc = run_tc(e, tp, ed, flops, st);
+            } else {
+                rc = run_gemm(e, G, W, ed, (int)R, c.cin, c.k * c.cout, 1, st);
+            }
             if (rc) return rc;
         }
     }
@@ -539,6 +665,7 @@ int forward_impl(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const 
     e->last_B = B;
     e->last_training = training;
     e->last_bases = bases;
+    if ((rc = refresh_wcache(e, st))) return rc;
     const Act* ffnn_last = nullptr;
     if (s.kind != EMB_KIND_CNN) {
         if (!x_ffnn) return set_error(EMB_E_ARG, "x_ffnn is NULL");
@@ -590,7 +717,14 @@ int forward_impl(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const 
             ep.emb_u = dr ? dr->embrace_u : nullptr;
             ep.cum0 = e->cum0;
             ep.idx_out = e->idx;
-            rc = run_gemm(e, A, W, ep, B, C, e->dock1.in, 1, st);
+            if (tc_linear_ok(e, e->dock1)) {
+                TcProblem pr = {};
+                pr.kind = TC_LINEAR_FWD; pr.a = (const bf16*)flat.p; pr.lda = flat.ld; pr.b = e->dock1.wc; pr.ldb = round_up(e->dock1.in, 8);
+                pr.M = B; pr.N = C; pr.K = e->dock1.in;
+                rc = run_tc(e, pr, ep, 2.0 * B * C * e->dock1.in, st);
+            } else {
+                rc = run_gemm(e, A, W, ep, B, C, e->dock1.in, 1, st);
+            }
             if (rc) return rc;
         }
         const Act* in = &e->e;
@@ -1077,16 +1211,84 @@ int emb_k_onehot_conv_bwd(const uint8_t* bases, const void* dy, int32_t B, int32
     return EMB_OK;
 }
 
-int emb_k_linear_fwd(const float* a, const float* w, const float* bias, int32_t M, int32_t N, int32_t K, int32_t relu, int32_t tensor_core,
-                     float* out, void* stream) {
+// One GEMM-shaped op of the step on either back end (0 = SIMT, 1 = tcgen05), fp32 in / fp32 out; the
+// inputs are rounded to bf16 exactly as the bf16 precision does.  kind = TcKind; shapes as documented at tc_gemm():
+//   0 linear fwd   a[M,K] b[N,K]            -> out[M,N]        3 conv fwd   a[B,L,Cin]  b = W[Cout,Cin,taps] -> out[B*L,Cout]
+//   1 linear dgrad a[M,K] b[K,N]            -> out[M,N]        4 conv dgrad a[B,L,Cout] b = W[Cout,Cin,taps] -> out[B*L,Cin]
+//   2 linear wgrad a[K,M] b[K,N]            -> out[M,N]        5 conv wgrad a[B,L,Cout] b = act[B,L,Cin]     -> out = dW[Cout,Cin,taps]
+// (all inner widths must be multiples of 8).  Synchronises the stream.
+int emb_k_gemm(int32_t kind, int32_t backend, const float* a, const float* b, float* out, int32_t M, int32_t N, int32_t K,
+               int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t taps, void* stream) {
     if (emb_device_count() < 1) return set_error(EMB_E_NO_DEVICE, "no sm_100 device");
-    if (tensor_core) return tc_linear_f32(a, w, bias, M, N, K, relu, out, (cudaStream_t)stream);
-    Operand A = make_operand(a, 0, OP_ROWMAJOR, K, M, K);
-    Operand W = make_operand(w, 0, OP_ROWMAJOR, K, N, K);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool conv = kind >= 3;
+    const int pad = (taps - 1) / 2;
+    size_t na, nb, nout;
+    if (kind == 0) { na = (size_t)M * K; nb = (size_t)N * K; nout = (size_t)M * N; }
+    else if (kind == 1) { na = (size_t)M * K; nb = (size_t)K * N; nout = (size_t)M * N; }
+    else if (kind == 2) { na = (size_t)K * M; nb = (size_t)K * N; nout = (size_t)M * N; }
+    else if (kind == 3) { na = (size_t)B * L * Cin; nb = (size_t)Cout * Cin * taps; nout = (size_t)B * L * Cout; }
+    else if (kind == 4) { na = (size_t)B * L * Cout; nb = (size_t)Cout * Cin * taps; nout = (size_t)B * L * Cin; }
+    else if (kind == 5) { na = (size_t)B * L * Cout; nb = (size_t)B * L * Cin; nout = (size_t)Cout * Cin * taps; }
+    else return set_error(EMB_E_ARG, "bad kind");
+    bf16 *a16 = nullptr, *b16 = nullptr;
+    EMB_CUDA_OK(cudaMalloc(&a16, na * 2 + 16));
+    EMB_CUDA_OK(cudaMalloc(&b16, nb * 2 + 16));
+    cast_f32_kernel<bf16><<<cdiv(na, 256), 256, 0, st>>>(a, a16, na);
+    const bool w_is_b = kind == 3 || kind == 4;
+    if (w_is_b && backend == 1) wcache_conv_kernel<<<cdiv(nb, 256), 256, 0, st>>>(b, b16, Cout, Cin, taps, Cin);
+    else cast_f32_kernel<bf16><<<cdiv(nb, 256), 256, 0, st>>>(b, b16, nb);
+    EMB_CHECK_LAUNCH();
     Epilogue ep = {};
-    ep.mode = EPI_LINEAR; ep.out = out; ep.out_dtype = 0; ep.ldo = N; ep.bias = bias; ep.relu = relu;
-    cudaError_t err = launch_gemm_simt(A, W, ep, M, N, K, 1, (cudaStream_t)stream);
-    if (err != cudaSuccess) return set_error(EMB_E_CUDA, "gemm launch: %s", cudaGetErrorString(err));
+    ep.scale = 1.f;
+    ep.out = out; ep.out_dtype = 0;
+    if (kind == 2 || kind == 5) {
+        EMB_CUDA_OK(cudaMemsetAsync(out, 0, nout * sizeof(float), st));
+        ep.mode = EPI_ATOMIC; ep.ldo = N;
+        if (kind == 5) { ep.map = MAP_CONV_W; ep.mapC = Cin; ep.map_taps = taps; }
+    } else {
+        ep.mode = EPI_LINEAR;
+        ep.ldo = kind == 3 ? Cout : kind == 4 ? Cin : N;
+    }
+    int rc = EMB_OK;
+    if (backend == 1) {
+        TcProblem pr = {};
+        pr.kind = kind; pr.a = a16; pr.b = b16;
+        pr.M = M; pr.N = N; pr.K = K; pr.B = B; pr.L = L; pr.Cin = Cin; pr.Cout = Cout; pr.taps = taps; pr.pad = pad;
+        if (kind == 0) { pr.lda = K; pr.ldb = K; }
+        else if (kind == 1) { pr.lda = K; pr.ldb = N; }
+        else if (kind == 2) { pr.lda = M; pr.ldb = N; }
+        else if (kind == 3) { pr.lda = Cin; pr.ldb = Cin; pr.M = B * L; pr.N = Cout; }
+        else if (kind == 4) { pr.lda = Cout; pr.ldb = Cin; pr.M = B * L; pr.N = Cin; }
+        else { pr.lda = Cout; pr.ldb = Cin; pr.M = Cout; pr.N = Cin; }
+        rc = tc_gemm(pr, ep, st);
+    } else {
+        Operand A, Bo;
+        int gm, gn, gk, split = 1;
+        if (kind == 0) { A = make_operand(a16, 1, OP_ROWMAJOR, K, M, K); Bo = make_operand(b16, 1, OP_ROWMAJOR, K, N, K); gm = M; gn = N; gk = K; }
+        else if (kind == 1) { A = make_operand(a16, 1, OP_ROWMAJOR, K, M, K); Bo = make_operand(b16, 1, OP_TRANSPOSED, N, N, K); gm = M; gn = N; gk = K; }
+        else if (kind == 2) { A = make_operand(a16, 1, OP_TRANSPOSED, M, M, K); Bo = make_operand(b16, 1, OP_TRANSPOSED, N, N, K); gm = M; gn = N; gk = K; split = 8; }
+        else if (kind == 3) {
+            A = make_operand(a16, 1, OP_CONV_SHIFT, Cin, B * L, taps * Cin); A.L = L; A.C = Cin; A.taps = taps; A.pad = pad; A.sign = 1;
+            Bo = make_operand(b16, 1, OP_CONV_W_FWD, 0, Cout, taps * Cin); Bo.C = Cin; Bo.taps = taps;
+            gm = B * L; gn = Cout; gk = taps * Cin;
+        } else if (kind == 4) {
+            A = make_operand(a16, 1, OP_CONV_SHIFT, Cout, B * L, taps * Cout); A.L = L; A.C = Cout; A.taps = taps; A.pad = pad; A.sign = -1;
+            Bo = make_operand(b16, 1, OP_CONV_W_DGRAD, 0, Cin, taps * Cout); Bo.C = Cout; Bo.taps = taps; Bo.wrows = Cin;
+            gm = B * L; gn = Cin; gk = taps * Cout;
+        } else {
+            A = make_operand(a16, 1, OP_TRANSPOSED, Cout, Cout, B * L);
+            Bo = make_operand(b16, 1, OP_CONV_SHIFT_T, Cin, taps * Cin, B * L); Bo.L = L; Bo.C = Cin; Bo.taps = taps; Bo.pad = pad; Bo.sign = 1;
+            gm = Cout; gn = taps * Cin; gk = B * L; split = 8;
+        }
+        cudaError_t err = launch_gemm_simt(A, Bo, ep, gm, gn, gk, split, st);
+        if (err != cudaSuccess) rc = set_error(EMB_E_CUDA, "gemm launch: %s", cudaGetErrorString(err));
+    }
+    cudaError_t serr = cudaStreamSynchronize(st);
+    cudaFree(a16);
+    cudaFree(b16);
+    if (rc) return rc;
+    if (serr != cudaSuccess) return set_error(EMB_E_CUDA, "emb_k_gemm: %s", cudaGetErrorString(serr));
     return EMB_OK;
 }
 

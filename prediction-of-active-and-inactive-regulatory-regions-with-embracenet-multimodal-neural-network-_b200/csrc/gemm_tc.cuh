@@ -1,13 +1,450 @@
-// tcgen05 / TMEM / TMA GEMM back end (bf16 operands, fp32 accumulation in tensor memory).
+// tcgen05 / TMEM / TMA GEMM back end (bf16 operands, fp32 accumulation in tensor memory), sm_100a.
+//
+// One warp-specialised kernel serves every GEMM-shaped op of the step:
+//   nn.Linear fwd / dgrad / wgrad and the Conv1d (layers >= 1) implicit GEMMs fwd / dgrad / wgrad.
+// Nothing is materialised for the convolutions: a 3-D TMA tensor map over the channels-last activation
+// [B, L, C] fetches, for tap t, the box starting at l = t - pad; rows that fall outside [0, L) are zero
+// filled by the TMA unit, which is exactly the "same" zero padding.  Operands that are contiguous along
+// M/N instead of K (weights in dgrad, both operands in wgrad) are consumed in place through MN-major
+// shared-memory descriptors, so no transposed copies exist either.
+//
+//   warp 0     TMA producer   (cp.async.bulk.tensor.3d -> 128B-swizzled smem stages, mbarrier complete_tx)
+//   warp 1     MMA issuer     (tcgen05.mma.cta_group::1.kind::f16, 128 x N x 16, accumulators in TMEM)
+//   warps 2-5  epilogue       (tcgen05.ld 32x32b -> registers -> the same fused epilogues as the SIMT path)
 #pragma once
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include "common.cuh"
+#include "gemm_simt.cuh"
 
 namespace emb {
 
-inline int tc_init() { return 0; }
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-inline int tc_linear_f32(const float*, const float*, const float*, int, int, int, int, float*, cudaStream_t) {
-    return set_error(-5, "tensor-core GEMM not built yet");
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a mis-programmed pipeline traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): SWIZZLE_128B, version 1 (Blackwell)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel parameters
+// ---------------------------------------------------------------------------------------------
+struct TcOperand {
+    int mn_major;       // 0: K-major tile [rows][64 k] ; 1: MN-major blocks of [k rows][64 mn]
+    int boxes;          // TMA boxes per stage (MN-major: one per 64-wide block)
+    int box_bytes;      // bytes one box deposits (expect_tx)
+    int block_bytes;    // smem distance between consecutive boxes of a stage (>= box_bytes, multiple of 1024)
+    int stage_bytes;    // boxes * block_bytes
+    int base[3];        // TMA coordinates = base + tap*ctap + j*cj + tile*ctile + blk*cblk
+    int ctap[3], cj[3], ctile[3], cblk[3];
+    int kstep_bytes;    // descriptor start-address advance per UMMA K step (16 elements)
+    int lbo_bytes;
+};
+
+struct TcParams {
+    TcOperand a, b;
+    int M, N;               // logical output extent (masking)
+    int n_logical;          // N handed to the epilogue (index arithmetic of replayed draws / idx)
+    int n_taps, n_inner;    // K loop = n_taps x n_inner stages (per K split)
+    int j_total;            // wgrad: total row blocks over all splits (guards the last split)
+    int split_k;            // blockIdx.z = tap_z * split_k + ks when tap_in_z
+    int tap_in_z;           // wgrad conv: the tap is a grid coordinate, not a loop
+    int n_off_per_tap;      // wgrad conv: logical n = tap * Cin + n
+    int k_steps;            // UMMA K steps per stage
+    int n_tile;             // UMMA N (multiple of 16, <= 256)
+    int rows_per_group;     // epilogue row mapping: tile row r -> group r / rpg, element r % rpg
+    int groups_per_tile;
+    int stages;
+    int zero_smem;          // MN-major K rows beyond the box must read as zero
+    uint32_t idesc;
+    uint32_t tmem_cols;
+};
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 6;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p,
+               const Epilogue ep) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int stage_bytes = p.a.stage_bytes + p.b.stage_bytes;
+    uint64_t* full_bar = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + TC_MAX_STAGES;
+    uint64_t* accum_bar = empty_bar + TC_MAX_STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+    int tap_z = 0, ks = blockIdx.z;
+    if (p.tap_in_z) { tap_z = blockIdx.z / p.split_k; ks = blockIdx.z - tap_z * p.split_k; }
+    // stages this CTA runs
+    int n_inner = p.n_inner;
+    if (p.j_total > 0) n_inner = max(0, min(p.n_inner, p.j_total - ks * p.n_inner));
+    const int n_iters = (p.tap_in_z ? 1 : p.n_taps) * n_inner;
+
+    if (p.zero_smem) {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < p.stages * stage_bytes / 16; i += TC_THREADS) ((uint4*)smem)[i] = z;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0 && n_iters > 0) {
+            const uint32_t tx = (uint32_t)(p.a.boxes * p.a.box_bytes + p.b.boxes * p.b.box_bytes);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < n_iters; ++it) {
+                const int tap = p.tap_in_z ? tap_z : it / n_inner;
+                const int j = ks * p.n_inner + (p.tap_in_z ? it : it - tap * n_inner);
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_expect_tx(&full_bar[stage], tx);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                uint8_t* sb = sa + p.a.stage_bytes;
+                for (int blk = 0; blk < p.a.boxes; ++blk) {
+                    int c0 = p.a.base[0] + tap * p.a.ctap[0] + j * p.a.cj[0] + tile_m * p.a.ctile[0] + blk * p.a.cblk[0];
+                    int c1 = p.a.base[1] + tap * p.a.ctap[1] + j * p.a.cj[1] + tile_m * p.a.ctile[1] + blk * p.a.cblk[1];
+                    int c2 = p.a.base[2] + tap * p.a.ctap[2] + j * p.a.cj[2] + tile_m * p.a.ctile[2] + blk * p.a.cblk[2];
+                    tma_load_3d(sa + (size_t)blk * p.a.block_bytes, &map_a, &full_bar[stage], c0, c1, c2);
+                }
+                for (int blk = 0; blk < p.b.boxes; ++blk) {
+                    int c0 = p.b.base[0] + tap * p.b.ctap[0] + j * p.b.cj[0] + tile_n * p.b.ctile[0] + blk * p.b.cblk[0];
+                    int c1 = p.b.base[1] + tap * p.b.ctap[1] + j * p.b.cj[1] + tile_n * p.b.ctile[1] + blk * p.b.cblk[1];
+                    int c2 = p.b.base[2] + tap * p.b.ctap[2] + j * p.b.cj[2] + tile_n * p.b.ctile[2] + blk * p.b.cblk[2];
+                    tma_load_3d(sb + (size_t)blk * p.b.block_bytes, &map_b, &full_bar[stage], c0, c1, c2);
+                }
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0 && n_iters > 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < n_iters; ++it) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t sb = sa + p.a.stage_bytes;
+                for (int s = 0; s < p.k_steps; ++s) {
+                    uint64_t da = umma_desc(sa + s * p.a.kstep_bytes, p.a.lbo_bytes, 1024);
+                    uint64_t db = umma_desc(sb + s * p.b.kstep_bytes, p.b.lbo_bytes, 1024);
+                    tc_mma_f16(tmem_base, da, db, p.idesc, (it | s) ? 1u : 0u);
+                }
+                tc_commit(&empty_bar[stage]);          // frees the smem stage when these MMAs retire
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(accum_bar);                      // accumulator complete
+        }
+    } else if (n_iters > 0) {
+        // ================= epilogue (warps 2..5 own TMEM lane quarters warp%4) =================
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int r = q * 32 + lane;                                   // tile row == TMEM lane
+        const int grp = r / p.rows_per_group;
+        const int m = (tile_m * p.groups_per_tile + grp) * p.rows_per_group + (r - grp * p.rows_per_group);
+        const bool row_ok = (r < p.groups_per_tile * p.rows_per_group) && (m < p.M);
+        const int n_base = tile_n * p.n_tile;
+        const int n_off = p.tap_in_z ? tap_z * p.n_off_per_tap : 0;
+        for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+            if (n_base + c0 >= p.N) break;                              // warp-uniform
+            float v[16];
+            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (row_ok) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    int n = n_base + c0 + i;
+                    if (n < p.N) epilogue_apply(ep, m, n_off + n, p.M, p.n_logical, v[i]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn& encode_fn() { static EncodeTiledFn f = nullptr; return f; }
+inline int& tc_max_smem() { static int v = 0; return v; }
+
+inline int tc_init() {
+    if (encode_fn()) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (err != cudaSuccess || !fn) return set_error(-3, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(err));
+    encode_fn() = (EncodeTiledFn)fn;
+    int dev = 0, smem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    tc_max_smem() = smem;
+    err = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return set_error(-3, "cudaFuncSetAttribute(tc_gemm_kernel): %s", cudaGetErrorString(err));
+    return 0;
+}
+
+// bf16 tensor [d2][d1][d0] (d0 contiguous), strides in ELEMENTS for d1 and d2
+inline int make_map(CUtensorMap* m, const void* ptr, int d0, int d1, int d2, int64_t s1, int64_t s2, int b0, int b1, int b2) {
+    cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+    cuuint64_t strides[2] = {(cuuint64_t)s1 * 2, (cuuint64_t)s2 * 2};
+    cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
+    cuuint32_t es[3] = {1, 1, 1};
+    if (((uintptr_t)ptr & 15) || (strides[0] & 15) || (strides[1] & 15)) return set_error(-1, "TMA operand not 16-byte aligned");
+    CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(-3, "cuTensorMapEncodeTiled failed (%d) dims=%d,%d,%d box=%d,%d,%d", (int)r, d0, d1, d2, b0, b1, b2);
+    return 0;
+}
+
+enum TcKind { TC_LINEAR_FWD = 0, TC_LINEAR_DGRAD = 1, TC_LINEAR_WGRAD = 2, TC_CONV_FWD = 3, TC_CONV_DGRAD = 4, TC_CONV_WGRAD = 5 };
+
+struct TcProblem {
+    int kind;
+    const bf16* a; int lda;     // see tc_gemm() for the meaning per kind
+    const bf16* b; int ldb;
+    int M, N, K;                // linear: out[M,N] = A[M,K] B[N,K]^T (fwd); see per-kind notes
+    int B, L, Cin, Cout, taps, pad;   // conv geometry (L = positions of both the conv input and output)
+};
+
+inline uint32_t make_idesc(int a_mn, int b_mn, int n_tile) {
+    uint32_t d = 0;
+    d |= 1u << 4;                    // C format F32
+    d |= 1u << 7;                    // A format BF16
+    d |= 1u << 10;                   // B format BF16
+    d |= (uint32_t)(a_mn ? 1 : 0) << 15;
+    d |= (uint32_t)(b_mn ? 1 : 0) << 16;
+    d |= (uint32_t)(n_tile >> 3) << 17;
+    d |= (uint32_t)(128 >> 4) << 24; // M = 128
+    return d;
+}
+
+inline void kmajor_operand(TcOperand& o, int rows) {
+    o.mn_major = 0; o.boxes = 1; o.box_bytes = rows * 128; o.block_bytes = round_up(rows * 128, 1024);
+    o.stage_bytes = o.block_bytes; o.kstep_bytes = 32; o.lbo_bytes = 16;
+}
+inline void mnmajor_operand(TcOperand& o, int mn_extent, int k_rows_box, int k_rows_stage) {
+    o.mn_major = 1; o.boxes = cdiv(mn_extent, 64); o.box_bytes = k_rows_box * 128; o.block_bytes = k_rows_stage * 128;
+    o.stage_bytes = o.boxes * o.block_bytes; o.kstep_bytes = 16 * 128; o.lbo_bytes = o.block_bytes;
+}
+
+inline bool tc_shape_ok(int n, int k_elems_contig_a, int k_elems_contig_b) {
+    return n >= 16 && (n % 16) == 0 && (k_elems_contig_a % 8) == 0 && (k_elems_contig_b % 8) == 0;
+}
+
+// Launch one GEMM on the tensor cores.  Operand conventions (all bf16, leading dimensions in elements):
+//  TC_LINEAR_FWD    a = X [M, K] (lda), b = W [N, K] (ldb)                       out[m,n] = sum_k X[m,k] W[n,k]
+//  TC_LINEAR_DGRAD  a = G [M, K] (lda; K = out units), b = W [K, N] (ldb; N = in) out[m,n] = sum_k G[m,k] W[k,n]
+//  TC_LINEAR_WGRAD  a = G [K, M] (lda; K = batch rows, M = out), b = X [K, N] (ldb) out[m,n] = sum_k G[k,m] X[k,n]
+//  TC_CONV_FWD      a = act [B, L, Cin] (lda), b = Wf [taps, Cout, Cin] (ldb)     M = B*L rows, N = Cout
+//  TC_CONV_DGRAD    a = dy [B, L, Cout] (lda), b = Wf [taps, Cout, Cin] (ldb)     M = B*L rows, N = Cin
+//  TC_CONV_WGRAD    a = dy [B, L, Cout] (lda), b = act [B, L, Cin] (ldb)          M = Cout, N = Cin per tap (logical n = tap*Cin + c)
+inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int* launches = nullptr) {
+    int rc = tc_init();
+    if (rc) return rc;
+    TcParams p = {};
+    CUtensorMap ma, mb;
+    const int kind = pr.kind;
+    const bool conv = kind >= TC_CONV_FWD;
+    int n_tile, grid_m, grid_n, grid_z = 1;
+    p.split_k = 1;
+    p.rows_per_group = 128; p.groups_per_tile = 1;
+    if (kind == TC_LINEAR_FWD || kind == TC_CONV_FWD || kind == TC_LINEAR_DGRAD || kind == TC_CONV_DGRAD) {
+        const int N = pr.N;
+        n_tile = N <= 256 ? round_up(N, 16) : 256;
+        // balance the N tiles (e.g. N = 1000 -> 4 x 256 rather than 3 x 256 + 232 is the same count; keep 256)
+        grid_n = cdiv(N, n_tile);
+        p.M = pr.M; p.N = N; p.n_logical = N;
+        if (conv) {
+            const int bt = std::max(1, 128 / pr.L);
+            if (pr.L > 128) return set_error(-5, "conv GEMM: L > 128 not supported");
+            p.rows_per_group = pr.L; p.groups_per_tile = bt;
+            grid_m = cdiv(pr.B, bt);
+            const int Ca = kind == TC_CONV_FWD ? pr.Cin : pr.Cout;    // channels of the A activation
+            rc = make_map(&ma, pr.a, Ca, pr.L, pr.B, pr.lda, (int64_t)pr.L * pr.lda, 64, pr.L, bt);
+            if (rc) return rc;
+            kmajor_operand(p.a, bt * pr.L);
+            p.a.block_bytes = p.a.stage_bytes = round_up(128 * 128, 1024);   // UMMA reads 128 rows
+            p.a.cj[0] = 64;
+            p.a.base[1] = kind == TC_CONV_FWD ? -pr.pad : pr.pad;
+            p.a.ctap[1] = kind == TC_CONV_FWD ? 1 : -1;
+            p.a.ctile[2] = bt;
+            p.n_taps = pr.taps;
+            p.n_inner = cdiv(Ca, 64);
+            // weights Wf [taps][Cout][Cin]
+            if (kind == TC_CONV_FWD) {
+                rc = make_map(&mb, pr.b, pr.Cin, pr.Cout, pr.taps, pr.ldb, (int64_t)pr.Cout * pr.ldb, 64, n_tile, 1);
+                if (rc) return rc;
+                kmajor_operand(p.b, n_tile);
+                p.b.cj[0] = 64; p.b.ctile[1] = n_tile; p.b.ctap[2] = 1;
+            } else {
+                rc = make_map(&mb, pr.b, pr.Cin, pr.Cout, pr.taps, pr.ldb, (int64_t)pr.Cout * pr.ldb, 64, 64, 1);
+                if (rc) return rc;
+                mnmajor_operand(p.b, n_tile, 64, 64);
+                p.b.ctile[0] = n_tile; p.b.cblk[0] = 64; p.b.cj[1] = 64; p.b.ctap[2] = 1;
+            }
+            p.k_steps = 4;
+        } else {
+            grid_m = cdiv(pr.M, 128);
+            rc = make_map(&ma, pr.a, pr.K, pr.M, 1, pr.lda, (int64_t)pr.M * pr.lda, 64, 128, 1);
+            if (rc) return rc;
+            kmajor_operand(p.a, 128);
+            p.a.cj[0] = 64; p.a.ctile[1] = 128;
+            p.n_taps = 1;
+            p.n_inner = cdiv(pr.K, 64);
+            if (kind == TC_LINEAR_FWD) {
+                rc = make_map(&mb, pr.b, pr.K, N, 1, pr.ldb, (int64_t)N * pr.ldb, 64, n_tile, 1);
+                if (rc) return rc;
+                kmajor_operand(p.b, n_tile);
+                p.b.cj[0] = 64; p.b.ctile[1] = n_tile;
+            } else {
+                rc = make_map(&mb, pr.b, N, pr.K, 1, pr.ldb, (int64_t)pr.K * pr.ldb, 64, 64, 1);
+                if (rc) return rc;
+                mnmajor_operand(p.b, n_tile, 64, 64);
+                p.b.ctile[0] = n_tile; p.b.cblk[0] = 64; p.b.cj[1] = 64;
+            }
+            p.k_steps = 4;
+        }
+    } else {
+        // wgrad: both operands MN-major, K = rows of the batch
+        const int N = pr.N;                       // Cin (conv) or in-features (linear)
+        n_tile = N <= 128 ? round_up(N, 16) : 128;
+        grid_n = cdiv(N, n_tile);
+        grid_m = cdiv(pr.M, 128);
+        p.M = pr.M; p.N = N;
+        int rows_box, j_total;
+        if (conv) {
+            if (pr.L > 128) return set_error(-5, "conv GEMM: L > 128 not supported");
+            const int bt = std::max(1, 128 / pr.L);
+            rows_box = bt * pr.L;
+            j_total = cdiv(pr.B, bt);
+            rc = make_map(&ma, pr.a, pr.Cout, pr.L, pr.B, pr.lda, (int64_t)pr.L * pr.lda, 64, pr.L, bt);
+            if (rc) return rc;
+            rc = make_map(&mb, pr.b, pr.Cin, pr.L, pr.B, pr.ldb, (int64_t)pr.L * pr.ldb, 64, pr.L, bt);
+            if (rc) return rc;
+            mnmajor_operand(p.a, 128, rows_box, 128);
+            mnmajor_operand(p.b, n_tile, rows_box, 128);
+            p.a.ctile[0] = 128; p.a.cblk[0] = 64; p.a.cj[2] = bt;
+            p.b.ctile[0] = n_tile; p.b.cblk[0] = 64; p.b.cj[2] = bt; p.b.base[1] = -pr.pad; p.b.ctap[1] = 1;
+            p.tap_in_z = 1; p.n_taps = pr.taps; p.n_off_per_tap = pr.Cin;
+            p.n_logical = pr.taps * pr.Cin;
+            p.zero_smem = rows_box < 128;
+        } else {
+            rows_box = 128;
+            j_total = cdiv(pr.K, 128);
+            rc = make_map(&ma, pr.a, pr.M, pr.K, 1, pr.lda, (int64_t)pr.K * pr.lda, 64, 128, 1);
+            if (rc) return rc;
+            rc = make_map(&mb, pr.b, N, pr.K, 1, pr.ldb, (int64_t)pr.K * pr.ldb, 64, 128, 1);
+            if (rc) return rc;
+            mnmajor_operand(p.a, 128, 128, 128);
+            mnmajor_operand(p.b, n_tile, 128, 128);
+            p.a.ctile[0] = 128; p.a.cblk[0] = 64; p.a.cj[1] = 128;
+            p.b.ctile[0] = n_tile; p.b.cblk[0] = 64; p.b.cj[1] = 128;
+            p.n_taps = 1; p.n_logical = N;
+        }
+        p.k_steps = 8;
+        p.j_total = j_total;
+        const int tiles = grid_m * grid_n * (conv ? pr.taps : 1);
+        int split = std::max(1, std::min(j_total, (148 * 2) / std::max(1, tiles)));
+        p.n_inner = cdiv(j_total, split);
+        split = cdiv(j_total, p.n_inner);
+        p.split_k = split;
+        grid_z = split * (conv ? pr.taps : 1);
+    }
+    p.n_tile = n_tile;
+    p.idesc = make_idesc(p.a.mn_major, p.b.mn_major, n_tile);
+    p.tmem_cols = n_tile <= 32 ? 32 : n_tile <= 64 ? 64 : n_tile <= 128 ? 128 : 256;
+    const int stage_bytes = p.a.stage_bytes + p.b.stage_bytes;
+    const int budget = tc_max_smem() - 2048;
+    p.stages = std::min(TC_MAX_STAGES, budget / stage_bytes);
+    if (p.stages < 2) return set_error(-5, "tc_gemm: stage of %d bytes does not fit twice in shared memory", stage_bytes);
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+    dim3 grid(grid_n, grid_m, grid_z);
+    tc_gemm_kernel<<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return set_error(-3, "tc_gemm launch failed: %s", cudaGetErrorString(err));
+    if (launches) ++*launches;
+    return 0;
 }
 
 }  // namespace emb

