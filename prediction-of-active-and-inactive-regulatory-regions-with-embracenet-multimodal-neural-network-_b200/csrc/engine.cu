@@ -15,6 +15,7 @@
 #include "../../include/embrace_b200.h"
 #include "common.cuh"
 #include "kernels.cuh"
+#include "kernels_fast.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 
@@ -511,10 +512,23 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
     const int dt = dtype_of(e);
     for (size_t i = 0; i < e->cnn.size(); ++i) {
         ConvLayer& c = e->cnn[i];
+        bool stats_done = false;
+        const bool even = (c.cout % 2) == 0;
         if (i == 0) {
-            size_t smem = (size_t)(c.k * 4 * c.cout + c.cout) * sizeof(float) + SEQ_LEN + 2 * c.pad + 16;
-            int grid = std::min(B, 148 * 8);
-            onehot_conv_fwd_kernel<T><<<grid, 256, smem, st>>>(bases, e->params + c.w, e->params + c.b, (T*)c.y, B, c.cout, c.k, c.ld, 0);
+            const int groups = c.cout / 8;
+            if ((c.cout % 8) == 0 && (256 % groups) == 0) {
+                // vectorised gather-sum; BatchNorm statistics of layer 0 are accumulated by the same kernel
+                if (training) EMB_CUDA_OK(cudaMemsetAsync(c.stats, 0, 2 * c.cout * sizeof(double), st));
+                size_t smem = (size_t)(c.k * 4 * c.cout + c.cout + 256 * 16) * sizeof(float) + SEQ_LEN + 2 * c.pad + 16;
+                int grid = std::min(B, 148 * 6);
+                onehot_conv_fwd_v8_kernel<T><<<grid, 256, smem, st>>>(bases, e->params + c.w, e->params + c.b, (T*)c.y, training ? c.stats : nullptr,
+                                                                     B, c.cout, c.k, c.ld);
+                stats_done = true;
+            } else {
+                size_t smem = (size_t)(c.k * 4 * c.cout + c.cout) * sizeof(float) + SEQ_LEN + 2 * c.pad + 16;
+                int grid = std::min(B, 148 * 8);
+                onehot_conv_fwd_kernel<T><<<grid, 256, smem, st>>>(bases, e->params + c.w, e->params + c.b, (T*)c.y, B, c.cout, c.k, c.ld, 0);
+            }
             EMB_CHECK_LAUNCH();
             LAUNCHED(e);
         } else {
@@ -538,11 +552,18 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
         }
         const int64_t R = (int64_t)B * c.Lc;
         if (training) {
-            EMB_CUDA_OK(cudaMemsetAsync(c.stats, 0, 2 * c.cout * sizeof(double), st));
-            dim3 grid(cdiv(c.cout, 32), (unsigned)std::min<int64_t>(296, cdiv(R, 8)));
-            bn_stats_kernel<T><<<grid, dim3(32, 8), 0, st>>>((const T*)c.y, c.stats, R, c.cout, c.ld);
-            EMB_CHECK_LAUNCH();
-            LAUNCHED(e);
+            if (!stats_done) {
+                EMB_CUDA_OK(cudaMemsetAsync(c.stats, 0, 2 * c.cout * sizeof(double), st));
+                if (even) {
+                    dim3 grid(cdiv(c.cout / 2, 32), (unsigned)std::min<int64_t>(148 * 8 / std::max(1, cdiv(c.cout / 2, 32)), cdiv(R, 8)));
+                    bn_stats_v2_kernel<T><<<grid, dim3(32, 8), 0, st>>>((const T*)c.y, c.stats, R, c.cout, c.ld);
+                } else {
+                    dim3 grid(cdiv(c.cout, 32), (unsigned)std::min<int64_t>(296, cdiv(R, 8)));
+                    bn_stats_kernel<T><<<grid, dim3(32, 8), 0, st>>>((const T*)c.y, c.stats, R, c.cout, c.ld);
+                }
+                EMB_CHECK_LAUNCH();
+                LAUNCHED(e);
+            }
             if (e->allreduce) {
                 int rc = e->allreduce(e->allreduce_user, c.stats, 2 * c.cout, st);
                 if (rc) return set_error(EMB_E_STATE, "allreduce callback failed (%d)", rc);
@@ -556,8 +577,12 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
         size_t total = (size_t)B * c.Lp * c.cout;
         float p = training ? c.drop : 0.f;
         const float* du = (dr && p > 0.f) ? dr->cnn_drop[i] : nullptr;
-        bn_relu_pool_drop_fwd_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)c.y, c.scale, c.shift, (T*)c.a, B, c.Lc, c.Lp, c.cout, c.ld,
-                                                                           p, du, e->rng, RNG_CNN_DROP + (uint32_t)i, e->row_offset);
+        if (even)
+            bn_relu_pool_drop_fwd_stream_kernel<T><<<cdiv((size_t)B * (c.cout / 2), 256), 256, 0, st>>>(
+                (const T*)c.y, c.scale, c.shift, (T*)c.a, B, c.Lc, c.Lp, c.cout, c.ld, p, du, e->rng, RNG_CNN_DROP + (uint32_t)i, e->row_offset);
+        else
+            bn_relu_pool_drop_fwd_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)c.y, c.scale, c.shift, (T*)c.a, B, c.Lc, c.Lp, c.cout, c.ld,
+                                                                               p, du, e->rng, RNG_CNN_DROP + (uint32_t)i, e->row_offset);
         EMB_CHECK_LAUNCH();
         LAUNCHED(e);
     }
@@ -576,7 +601,14 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
         ConvLayer& c = e->cnn[i];
         const int64_t R = (int64_t)B * c.Lc;
         EMB_CUDA_OK(cudaMemsetAsync(c.bstats, 0, 2 * c.cout * sizeof(double), st));
-        {
+        const bool even = (c.cout % 2) == 0;
+        if (even) {
+            dim3 grid(cdiv(c.cout / 2, 32), cdiv(B, 8));
+            pool_bn_bwd_stream_kernel<T><<<grid, dim3(32, 8), 0, st>>>((const T*)c.y, (const T*)c.a, (const T*)c.ga, c.scale, c.shift, c.mean,
+                                                                       c.rstd, (T*)c.dy, c.bstats, B, c.Lc, c.Lp, c.cout, c.ld, c.drop);
+            EMB_CHECK_LAUNCH();
+            LAUNCHED(e);
+        } else {
             dim3 grid(cdiv(c.cout, 32), B);
             size_t smem = (size_t)2 * c.Lc * 32 * sizeof(float);
             pool_bn_bwd_stage1_kernel<T><<<grid, dim3(32, 8), smem, st>>>((const T*)c.y, (const T*)c.a, (const T*)c.ga, c.scale, c.shift, c.mean,
@@ -592,17 +624,29 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
         EMB_CHECK_LAUNCH();
         LAUNCHED(e);
         double n = (double)(e->global_batch > 0 ? e->global_batch : B) * c.Lc;
-        {
+        if (even) {
+            const int gx = cdiv(c.cout / 2, 32);
+            dim3 grid(gx, (unsigned)std::min<int64_t>(std::max(1, 148 * 8 / gx), cdiv(R, 8)));
+            bn_bwd_apply_v2_kernel<T><<<grid, dim3(32, 8), 0, st>>>((const T*)c.y, (T*)c.dy, c.bstats, e->params + c.gamma, c.mean, c.rstd,
+                                                                    e->grads + c.b, R, c.cout, c.ld, n);
+        } else {
             dim3 grid(cdiv(c.cout, 32), (unsigned)std::min<int64_t>(296, cdiv(R, 8)));
             bn_bwd_apply_kernel<T><<<grid, dim3(32, 8), 0, st>>>((const T*)c.y, (T*)c.dy, c.bstats, e->params + c.gamma, c.mean, c.rstd,
                                                                  e->grads + c.b, R, c.cout, c.ld, n);
-            EMB_CHECK_LAUNCH();
-            LAUNCHED(e);
         }
+        EMB_CHECK_LAUNCH();
+        LAUNCHED(e);
         if (i == 0) {
-            int grid = std::min(B, 148 * 4);
-            // conv-0 dbias was already accumulated by bn_bwd_apply_kernel
-            onehot_conv_bwd_kernel<T><<<grid, 256, 0, st>>>(e->last_bases, (const T*)c.dy, e->grads + c.w, nullptr, B, c.cout, c.k, c.ld);
+            // conv-0 dbias was already accumulated by the bn_bwd_apply kernel
+            if (even && (c.cout / 2) * c.k <= 1024) {
+                const int threads = round_up((c.cout / 2) * c.k, 32);
+                size_t smem = (size_t)SEQ_LEN * c.cout * sizeof(float) + SEQ_LEN + 16;
+                int grid = std::min(B, 148 * 2);
+                onehot_conv_bwd_hist_kernel<T><<<grid, threads, smem, st>>>(e->last_bases, (const T*)c.dy, e->grads + c.w, B, c.cout, c.k, c.ld);
+            } else {
+                int grid = std::min(B, 148 * 4);
+                onehot_conv_bwd_kernel<T><<<grid, 256, 0, st>>>(e->last_bases, (const T*)c.dy, e->grads + c.w, nullptr, B, c.cout, c.k, c.ld);
+            }
             EMB_CHECK_LAUNCH();
             LAUNCHED(e);
         } else {
@@ -976,6 +1020,8 @@ int emb_bind(EmbEngine* e, float* params, float* grads, float* buffers, float* o
     EMB_CUDA_OK(cudaMemset(e->rec_count, 0, sizeof(int)));
     cudaFuncSetAttribute(pool_bn_bwd_stage1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SEQ_LEN * 32 * 4);
     cudaFuncSetAttribute(pool_bn_bwd_stage1_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SEQ_LEN * 32 * 4);
+    cudaFuncSetAttribute(onehot_conv_bwd_hist_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEQ_LEN * 64 * 4 + 512);
+    cudaFuncSetAttribute(onehot_conv_bwd_hist_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEQ_LEN * 64 * 4 + 512);
     int rc = tc_init();
     if (rc) return rc;
     return EMB_OK;

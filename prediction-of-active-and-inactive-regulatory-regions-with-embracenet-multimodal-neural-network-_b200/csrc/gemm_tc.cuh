@@ -115,12 +115,70 @@ struct TcParams {
     int stages;
     int zero_smem;          // MN-major K rows beyond the box must read as zero
     uint32_t idesc;
-    uint32_t tmem_cols;
+    uint32_t tmem_cols;     // total allocation = 2 accumulator stages
+    int acc_stride;         // TMEM columns per accumulator stage
+    int grid_m, grid_n, grid_z, total_tiles;
 };
 
 constexpr int TC_THREADS = 192;
 constexpr int TC_MAX_STAGES = 6;
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// 16 consecutive columns of one output row: vectorised paths for the two epilogues that carry almost all of the
+// traffic (plain bias[+ReLU] store and the ReLU/Dropout mask of a dgrad), generic per-element path otherwise.
+__device__ __forceinline__ void tc_epilogue_row16(const Epilogue& ep, int m, int n0, int n_off, int M, int N, int n_logical, float* v) {
+    const bool full16 = n0 + 16 <= N;
+    const bool vec = full16 && ep.out_dtype == 1 && (ep.ldo & 7) == 0;
+    if (vec && ep.mode == EPI_LINEAR && ep.drop_p == 0.f && ep.flatC == 0) {
+        if (ep.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float4 b = __ldg(b4 + i);
+                v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+        }
+        if (ep.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        uint4* dst = reinterpret_cast<uint4*>((bf16*)ep.out + (size_t)m * ep.ldo + n0);
+        dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        return;
+    }
+    if (vec && ep.mode == EPI_MASKGRAD && (ep.ld_ref & 7) == 0) {
+        const uint4* r4 = reinterpret_cast<const uint4*>((const bf16*)ep.ref + (size_t)m * ep.ld_ref + n0);
+        uint4 ra = r4[0], rb = r4[1];
+        const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+            uint32_t lo = rw[i] & 0xFFFFu, hi = rw[i] >> 16;
+            v[2 * i] = (lo != 0 && !(lo & 0x8000u)) ? v[2 * i] * ep.scale : 0.f;
+            v[2 * i + 1] = (hi != 0 && !(hi & 0x8000u)) ? v[2 * i + 1] * ep.scale : 0.f;
+        }
+        uint4* dst = reinterpret_cast<uint4*>((bf16*)ep.out + (size_t)m * ep.ldo + n0);
+        dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        int n = n0 + i;
+        if (n < N) epilogue_apply(ep, m, n_off + n, M, n_logical, v[i]);
+    }
+}
+
+// Persistent: one CTA per SM walks the tile list; two TMEM accumulator stages let the epilogue of tile i
+// overlap the main loop of tile i+1.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p,
                const Epilogue ep) {
@@ -129,17 +187,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int stage_bytes = p.a.stage_bytes + p.b.stage_bytes;
     uint64_t* full_bar = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
     uint64_t* empty_bar = full_bar + TC_MAX_STAGES;
-    uint64_t* accum_bar = empty_bar + TC_MAX_STAGES;
-    uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+    uint64_t* tfull_bar = empty_bar + TC_MAX_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile_n = blockIdx.x, tile_m = blockIdx.y;
-    int tap_z = 0, ks = blockIdx.z;
-    if (p.tap_in_z) { tap_z = blockIdx.z / p.split_k; ks = blockIdx.z - tap_z * p.split_k; }
-    // stages this CTA runs
-    int n_inner = p.n_inner;
-    if (p.j_total > 0) n_inner = max(0, min(p.n_inner, p.j_total - ks * p.n_inner));
-    const int n_iters = (p.tap_in_z ? 1 : p.n_taps) * n_inner;
 
     if (p.zero_smem) {
         uint4 z = make_uint4(0, 0, 0, 0);
@@ -148,7 +200,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(accum_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -160,78 +212,111 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // tile t -> (tile_n fastest, tile_m, z); z = tap_z * split_k + ks
+#define TC_DECODE_TILE(t)                                                                         \
+    const int tile_n = (t) % p.grid_n;                                                            \
+    const int tile_m = ((t) / p.grid_n) % p.grid_m;                                               \
+    const int zz = (t) / (p.grid_n * p.grid_m);                                                   \
+    const int tap_z = p.tap_in_z ? zz / p.split_k : 0;                                            \
+    const int ks = p.tap_in_z ? zz - tap_z * p.split_k : zz;                                      \
+    const int n_inner = p.j_total > 0 ? max(0, min(p.n_inner, p.j_total - ks * p.n_inner)) : p.n_inner; \
+    const int n_iters = (p.tap_in_z ? 1 : p.n_taps) * n_inner;
+
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0 && n_iters > 0) {
+        if (lane == 0) {
             const uint32_t tx = (uint32_t)(p.a.boxes * p.a.box_bytes + p.b.boxes * p.b.box_bytes);
             int stage = 0;
             uint32_t phase = 0;
-            for (int it = 0; it < n_iters; ++it) {
-                const int tap = p.tap_in_z ? tap_z : it / n_inner;
-                const int j = ks * p.n_inner + (p.tap_in_z ? it : it - tap * n_inner);
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                mbar_expect_tx(&full_bar[stage], tx);
-                uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                uint8_t* sb = sa + p.a.stage_bytes;
-                for (int blk = 0; blk < p.a.boxes; ++blk) {
-                    int c0 = p.a.base[0] + tap * p.a.ctap[0] + j * p.a.cj[0] + tile_m * p.a.ctile[0] + blk * p.a.cblk[0];
-                    int c1 = p.a.base[1] + tap * p.a.ctap[1] + j * p.a.cj[1] + tile_m * p.a.ctile[1] + blk * p.a.cblk[1];
-                    int c2 = p.a.base[2] + tap * p.a.ctap[2] + j * p.a.cj[2] + tile_m * p.a.ctile[2] + blk * p.a.cblk[2];
-                    tma_load_3d(sa + (size_t)blk * p.a.block_bytes, &map_a, &full_bar[stage], c0, c1, c2);
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                TC_DECODE_TILE(t)
+                for (int it = 0; it < n_iters; ++it) {
+                    const int tap = p.tap_in_z ? tap_z : it / n_inner;
+                    const int j = ks * p.n_inner + (p.tap_in_z ? it : it - tap * n_inner);
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], tx);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    uint8_t* sb = sa + p.a.stage_bytes;
+                    for (int blk = 0; blk < p.a.boxes; ++blk) {
+                        int c0 = p.a.base[0] + tap * p.a.ctap[0] + j * p.a.cj[0] + tile_m * p.a.ctile[0] + blk * p.a.cblk[0];
+                        int c1 = p.a.base[1] + tap * p.a.ctap[1] + j * p.a.cj[1] + tile_m * p.a.ctile[1] + blk * p.a.cblk[1];
+                        int c2 = p.a.base[2] + tap * p.a.ctap[2] + j * p.a.cj[2] + tile_m * p.a.ctile[2] + blk * p.a.cblk[2];
+                        tma_load_3d(sa + (size_t)blk * p.a.block_bytes, &map_a, &full_bar[stage], c0, c1, c2);
+                    }
+                    for (int blk = 0; blk < p.b.boxes; ++blk) {
+                        int c0 = p.b.base[0] + tap * p.b.ctap[0] + j * p.b.cj[0] + tile_n * p.b.ctile[0] + blk * p.b.cblk[0];
+                        int c1 = p.b.base[1] + tap * p.b.ctap[1] + j * p.b.cj[1] + tile_n * p.b.ctile[1] + blk * p.b.cblk[1];
+                        int c2 = p.b.base[2] + tap * p.b.ctap[2] + j * p.b.cj[2] + tile_n * p.b.ctile[2] + blk * p.b.cblk[2];
+                        tma_load_3d(sb + (size_t)blk * p.b.block_bytes, &map_b, &full_bar[stage], c0, c1, c2);
+                    }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                for (int blk = 0; blk < p.b.boxes; ++blk) {
-                    int c0 = p.b.base[0] + tap * p.b.ctap[0] + j * p.b.cj[0] + tile_n * p.b.ctile[0] + blk * p.b.cblk[0];
-                    int c1 = p.b.base[1] + tap * p.b.ctap[1] + j * p.b.cj[1] + tile_n * p.b.ctile[1] + blk * p.b.cblk[1];
-                    int c2 = p.b.base[2] + tap * p.b.ctap[2] + j * p.b.cj[2] + tile_n * p.b.ctile[2] + blk * p.b.cblk[2];
-                    tma_load_3d(sb + (size_t)blk * p.b.block_bytes, &map_b, &full_bar[stage], c0, c1, c2);
-                }
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0 && n_iters > 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int it = 0; it < n_iters; ++it) {
-                mbar_wait(&full_bar[stage], phase);
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                TC_DECODE_TILE(t)
+                (void)tile_n; (void)tile_m;
+                if (n_iters == 0) continue;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                const uint32_t sb = sa + p.a.stage_bytes;
-                for (int s = 0; s < p.k_steps; ++s) {
-                    uint64_t da = umma_desc(sa + s * p.a.kstep_bytes, p.a.lbo_bytes, 1024);
-                    uint64_t db = umma_desc(sb + s * p.b.kstep_bytes, p.b.lbo_bytes, 1024);
-                    tc_mma_f16(tmem_base, da, db, p.idesc, (it | s) ? 1u : 0u);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+                for (int it = 0; it < n_iters; ++it) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t sb = sa + p.a.stage_bytes;
+                    for (int s = 0; s < p.k_steps; ++s) {
+                        uint64_t da = umma_desc(sa + s * p.a.kstep_bytes, p.a.lbo_bytes, 1024);
+                        uint64_t db = umma_desc(sb + s * p.b.kstep_bytes, p.b.lbo_bytes, 1024);
+                        tc_mma_f16(d_tmem, da, db, p.idesc, (it | s) ? 1u : 0u);
+                    }
+                    tc_commit(&empty_bar[stage]);          // frees the smem stage when these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&empty_bar[stage]);          // frees the smem stage when these MMAs retire
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                tc_commit(&tfull_bar[acc]);                // accumulator complete
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
             }
-            tc_commit(accum_bar);                      // accumulator complete
         }
-    } else if (n_iters > 0) {
+    } else {
         // ================= epilogue (warps 2..5 own TMEM lane quarters warp%4) =================
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
         const int q = warp & 3;
         const int r = q * 32 + lane;                                   // tile row == TMEM lane
         const int grp = r / p.rows_per_group;
-        const int m = (tile_m * p.groups_per_tile + grp) * p.rows_per_group + (r - grp * p.rows_per_group);
-        const bool row_ok = (r < p.groups_per_tile * p.rows_per_group) && (m < p.M);
-        const int n_base = tile_n * p.n_tile;
-        const int n_off = p.tap_in_z ? tap_z * p.n_off_per_tap : 0;
-        for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-            if (n_base + c0 >= p.N) break;                              // warp-uniform
-            float v[16];
-            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (row_ok) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    int n = n_base + c0 + i;
-                    if (n < p.N) epilogue_apply(ep, m, n_off + n, p.M, p.n_logical, v[i]);
-                }
+        const int r_in = r - grp * p.rows_per_group;
+        const bool r_ok = r < p.groups_per_tile * p.rows_per_group;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            TC_DECODE_TILE(t)
+            (void)ks;
+            if (n_iters == 0) continue;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const int m = (tile_m * p.groups_per_tile + grp) * p.rows_per_group + r_in;
+            const bool row_ok = r_ok && (m < p.M);
+            const int n_base = tile_n * p.n_tile;
+            const int n_off = p.tap_in_z ? tap_z * p.n_off_per_tap : 0;
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+            for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+                if (n_base + c0 >= p.N) break;                          // warp-uniform
+                float v[16];
+                tc_ld16(t_addr + (uint32_t)c0, v);
+                if (row_ok) tc_epilogue_row16(ep, m, n_base + c0, n_off, p.M, p.N, p.n_logical, v);
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // accumulator may be overwritten
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
         }
     }
+#undef TC_DECODE_TILE
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -247,6 +332,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 inline EncodeTiledFn& encode_fn() { static EncodeTiledFn f = nullptr; return f; }
 inline int& tc_max_smem() { static int v = 0; return v; }
+inline int& tc_num_sms() { static int v = 148; return v; }
 
 inline int tc_init() {
     if (encode_fn()) return 0;
@@ -259,6 +345,7 @@ inline int tc_init() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     tc_max_smem() = smem;
+    cudaDeviceGetAttribute(&tc_num_sms(), cudaDevAttrMultiProcessorCount, dev);
     err = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return set_error(-3, "cudaFuncSetAttribute(tc_gemm_kernel): %s", cudaGetErrorString(err));
     return 0;
@@ -433,13 +520,16 @@ inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int
     }
     p.n_tile = n_tile;
     p.idesc = make_idesc(p.a.mn_major, p.b.mn_major, n_tile);
-    p.tmem_cols = n_tile <= 32 ? 32 : n_tile <= 64 ? 64 : n_tile <= 128 ? 128 : 256;
+    p.acc_stride = n_tile <= 16 ? 16 : n_tile <= 32 ? 32 : n_tile <= 64 ? 64 : n_tile <= 128 ? 128 : 256;
+    p.tmem_cols = std::max(32, 2 * p.acc_stride);
+    p.grid_m = grid_m; p.grid_n = grid_n; p.grid_z = grid_z;
+    p.total_tiles = grid_m * grid_n * grid_z;
     const int stage_bytes = p.a.stage_bytes + p.b.stage_bytes;
     const int budget = tc_max_smem() - 2048;
     p.stages = std::min(TC_MAX_STAGES, budget / stage_bytes);
     if (p.stages < 2) return set_error(-5, "tc_gemm: stage of %d bytes does not fit twice in shared memory", stage_bytes);
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
-    dim3 grid(grid_n, grid_m, grid_z);
+    const int grid = std::min(p.total_tiles, tc_num_sms());
     tc_gemm_kernel<<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error(-3, "tc_gemm launch failed: %s", cudaGetErrorString(err));

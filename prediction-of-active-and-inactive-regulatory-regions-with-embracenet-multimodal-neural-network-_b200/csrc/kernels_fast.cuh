@@ -1,0 +1,371 @@
+// Bandwidth-oriented versions of the CNN-stack kernels for even / multiple-of-8 channel counts (every point of
+// the reference's search space: 16..512 channels).  kernels.cuh keeps the shape-generic versions used for odd
+// channel counts.  All activations are channels-last [B, L, C] (leading dimension ld, even).
+#pragma once
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace emb {
+
+// ---- two-channel load/store helpers -----------------------------------------------------------------------
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 ld2(const bf16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
+__device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+__device__ __forceinline__ void st2(bf16* p, float2 v) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y); }
+__device__ __forceinline__ void st8(float* p, const float* v) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8(bf16* p, const float* v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b),
+                                              *reinterpret_cast<uint32_t*>(&c), *reinterpret_cast<uint32_t*>(&d));
+}
+template <typename T> __device__ __forceinline__ float round_like(float v);
+template <> __device__ __forceinline__ float round_like<float>(float v) { return v; }
+template <> __device__ __forceinline__ float round_like<bf16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// ---------------------------------------------------------------------------------------------
+// K1 forward, vectorised: each thread produces 8 consecutive output channels of one position from the
+// shared-memory weight-row table (two 16-byte table reads per tap), stores them as one 16-byte (bf16) or two
+// 16-byte (fp32) words, and keeps the BatchNorm sum / sum-of-squares of its 8 channels in registers, so layer 0
+// needs no separate statistics pass.  Requires C1 % 8 == 0 and 256 % (C1/8) == 0.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+onehot_conv_fwd_v8_kernel(const uint8_t* __restrict__ bases, const float* __restrict__ w, const float* __restrict__ bias,
+                          T* __restrict__ y, double* __restrict__ stats, int B, int C1, int k, int ld) {
+    extern __shared__ float smem[];
+    float* tab = smem;                         // [k][4][C1]
+    float* sb = tab + k * 4 * C1;              // [C1]
+    float* red = sb + C1;                      // [256][16] reduction scratch
+    uint8_t* sbase = (uint8_t*)(red + 256 * 16);
+    const int p = (k - 1) / 2;
+    const int groups = C1 / 8;
+    for (int i = threadIdx.x; i < k * 4 * C1; i += blockDim.x) {
+        int tap = i / (4 * C1), r = i - tap * 4 * C1, c = r / C1, o = r - c * C1;
+        tab[i] = w[((size_t)o * 4 + c) * k + tap];
+    }
+    for (int i = threadIdx.x; i < C1; i += blockDim.x) sb[i] = bias[i];
+    const int og = threadIdx.x % groups;       // constant per thread: 256 % groups == 0
+    float s1[8], s2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < SEQ_LEN + 2 * p; i += blockDim.x) {
+            int l = i - p;
+            sbase[i] = (l >= 0 && l < SEQ_LEN) ? bases[(size_t)b * SEQ_LEN + l] : 4;
+        }
+        __syncthreads();
+        for (int item = threadIdx.x; item < SEQ_LEN * groups; item += 256) {
+            const int l = item / groups;
+            float acc[8];
+            const float4* b4 = reinterpret_cast<const float4*>(sb + og * 8);
+            float4 t0 = b4[0], t1 = b4[1];
+            acc[0] = t0.x; acc[1] = t0.y; acc[2] = t0.z; acc[3] = t0.w; acc[4] = t1.x; acc[5] = t1.y; acc[6] = t1.z; acc[7] = t1.w;
+            for (int tap = 0; tap < k; ++tap) {
+                int c = sbase[l + tap];
+                if (c < 4) {
+                    const float4* r4 = reinterpret_cast<const float4*>(tab + (tap * 4 + c) * C1 + og * 8);
+                    float4 a0 = r4[0], a1 = r4[1];
+                    acc[0] += a0.x; acc[1] += a0.y; acc[2] += a0.z; acc[3] += a0.w;
+                    acc[4] += a1.x; acc[5] += a1.y; acc[6] += a1.z; acc[7] += a1.w;
+                }
+            }
+            st8(y + ((size_t)b * SEQ_LEN + l) * ld + og * 8, acc);
+            if (stats) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { float v = round_like<T>(acc[i]); s1[i] += v; s2[i] += v * v; }
+            }
+        }
+    }
+    if (stats) {   // threads with the same og hold partials of the same 8 channels
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { red[threadIdx.x * 16 + i] = s1[i]; red[threadIdx.x * 16 + 8 + i] = s2[i]; }
+        __syncthreads();
+        for (int i = threadIdx.x; i < groups * 16; i += blockDim.x) {
+            int g = i / 16, j = i - g * 16;
+            double tot = 0;
+            for (int t = g; t < 256; t += groups) tot += red[t * 16 + j];
+            int c = g * 8 + (j & 7);
+            atomicAdd(&stats[(j < 8 ? 0 : C1) + c], tot);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 backward, histogram form: thread = (output channel pair, tap); the loop runs over SOURCE positions l', whose
+// base is the same for the whole CTA, so the per-base accumulator is chosen by a uniform branch instead of four
+// predicated adds.  The sample's dy tile is staged in shared memory once (coalesced) and re-read by the 15 taps
+// from there.  Per-sample fp32 partials are folded into fp64 so that the heavy cancellation BatchNorm induces
+// (sum_l dy = 0 per channel) does not cost accuracy.   Requires C1 even and (C1/2)*k <= 1024.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024)
+onehot_conv_bwd_hist_kernel(const uint8_t* __restrict__ bases, const T* __restrict__ dy, float* __restrict__ dw, int B, int C1, int k, int ld) {
+    extern __shared__ float smem[];
+    float* dys = smem;                                   // [256][C1] fp32
+    uint8_t* sbase = (uint8_t*)(dys + SEQ_LEN * C1);     // [256]
+    const int p = (k - 1) / 2;
+    const int pairs = C1 / 2;
+    const int tap = threadIdx.x / pairs, op = threadIdx.x - tap * pairs;
+    const bool active = tap < k;
+    double d[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) d[i][c] = 0.0;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < SEQ_LEN * pairs; i += blockDim.x) {
+            int l = i / pairs, o2 = i - l * pairs;
+            float2 v = ld2(dy + ((size_t)b * SEQ_LEN + l) * ld + 2 * o2);
+            dys[l * C1 + 2 * o2] = v.x;
+            dys[l * C1 + 2 * o2 + 1] = v.y;
+        }
+        for (int i = threadIdx.x; i < SEQ_LEN; i += blockDim.x) sbase[i] = bases[(size_t)b * SEQ_LEN + i];
+        __syncthreads();
+        if (active) {
+            float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+            // output position l reads source l' = l + tap - p  <=>  source l' feeds output l = l' - tap + p
+            for (int ls = 0; ls < SEQ_LEN; ++ls) {
+                const int c = sbase[ls];                                  // uniform across the CTA
+                const int l = ls - tap + p;
+                if (l < 0 || l >= SEQ_LEN) continue;
+                const float2 v = *reinterpret_cast<const float2*>(dys + l * C1 + 2 * op);
+                switch (c) {
+                    case 0: a0[0] += v.x; a1[0] += v.y; break;
+                    case 1: a0[1] += v.x; a1[1] += v.y; break;
+                    case 2: a0[2] += v.x; a1[2] += v.y; break;
+                    default: a0[3] += v.x; a1[3] += v.y; break;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { d[0][c] += a0[c]; d[1][c] += a1[c]; }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) atomicAdd(&dw[((size_t)(2 * op + i) * 4 + c) * k + tap], (float)d[i][c]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 forward, streaming: thread = (sample, channel pair) walks the positions once.  MaxPool1d(10, 2) over
+// ReLU(BN(y)) is the max of 5 consecutive pair-maxima, kept in a 5-register window: every y element is read
+// exactly once (the generic kernel reads it 5 times through L1).  Requires C even.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_relu_pool_drop_fwd_stream_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                                    T* __restrict__ a, int B, int Lc, int Lp, int C, int ld, float drop_p,
+                                    const float* __restrict__ drop_u, RngState const* rng, uint32_t rng_stream, int64_t row_offset) {
+    const int pairs = C / 2;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)B * pairs) return;
+    const int cp = t % pairs, b = t / pairs;
+    const int c = 2 * cp;
+    const float2 sc = make_float2(scale[c], scale[c + 1]), sh = make_float2(shift[c], shift[c + 1]);
+    const T* src = y + (size_t)b * Lc * ld + c;
+    T* dst = a + (size_t)b * Lp * ld + c;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    float2 w0 = make_float2(0.f, 0.f), w1 = w0, w2 = w0, w3 = w0;   // relu folded in: window values start at 0
+#pragma unroll 4
+    for (int i = 0; i < Lp + 4; ++i) {
+        float2 u0 = ld2(src + (size_t)(2 * i) * ld), u1 = ld2(src + (size_t)(2 * i + 1) * ld);
+        float2 m;
+        m.x = fmaxf(fmaxf(fmaf(u0.x, sc.x, sh.x), fmaf(u1.x, sc.x, sh.x)), 0.f);
+        m.y = fmaxf(fmaxf(fmaf(u0.y, sc.y, sh.y), fmaf(u1.y, sc.y, sh.y)), 0.f);
+        if (i >= 4) {
+            const int j = i - 4;
+            float2 r;
+            r.x = fmaxf(fmaxf(fmaxf(w0.x, w1.x), fmaxf(w2.x, w3.x)), m.x);
+            r.y = fmaxf(fmaxf(fmaxf(w0.y, w1.y), fmaxf(w2.y, w3.y)), m.y);
+            if (drop_p > 0.f) {
+                float ux, uy;
+                if (drop_u) {
+                    ux = drop_u[((size_t)b * C + c) * Lp + j];
+                    uy = drop_u[((size_t)b * C + c + 1) * Lp + j];
+                } else {
+                    ux = rng_uniform_f32(*rng, rng_stream, ((uint64_t)(row_offset + b) * C + c) * Lp + j);
+                    uy = rng_uniform_f32(*rng, rng_stream, ((uint64_t)(row_offset + b) * C + c + 1) * Lp + j);
+                }
+                r.x = (ux >= drop_p) ? r.x * inv_keep : 0.f;
+                r.y = (uy >= drop_p) ? r.y * inv_keep : 0.f;
+            }
+            st2(dst + (size_t)j * ld, r);
+        }
+        w0 = w1; w1 = w2; w2 = w3; w3 = m;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 backward stage 1, streaming: thread = (sample, channel pair).  A 10-position ring of y and of the
+// accumulating dz lives in registers; when pair i arrives window j = i-4 is complete, its gradient goes to the
+// FIRST maximum (strict '>'), and positions 2j, 2j+1 can no longer change, so they are emitted.  y, a and d(a)
+// are each read once, dz written once.  blockDim = (32 channel pairs, 8 samples); per-channel BatchNorm
+// reductions are folded over the 8 samples in shared memory, then one fp64 atomic per channel and CTA.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+pool_bn_bwd_stream_kernel(const T* __restrict__ y, const T* __restrict__ a, const T* __restrict__ ga,
+                          const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                          const float* __restrict__ rstd, T* __restrict__ dz_out, double* __restrict__ bstats, int B, int Lc, int Lp,
+                          int C, int ld, float drop_p) {
+    __shared__ float red[4][8][33];
+    const int pairs = C / 2;
+    const int cp = blockIdx.x * 32 + threadIdx.x;
+    const int b = blockIdx.y * 8 + threadIdx.y;
+    const bool ok = cp < pairs && b < B;
+    float sdz[2] = {0.f, 0.f}, sdzx[2] = {0.f, 0.f};
+    if (ok) {
+        const int c = 2 * cp;
+        const float scx = scale[c], scy = scale[c + 1], shx = shift[c], shy = shift[c + 1];
+        const float mux = mean[c], muy = mean[c + 1], rsx = rstd[c], rsy = rstd[c + 1];
+        const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+        const T* ysrc = y + (size_t)b * Lc * ld + c;
+        const T* asrc = a + (size_t)b * Lp * ld + c;
+        const T* gsrc = ga + (size_t)b * Lp * ld + c;
+        T* dst = dz_out + (size_t)b * Lc * ld + c;
+        float2 yr[10], dr[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) { yr[i] = make_float2(0.f, 0.f); dr[i] = make_float2(0.f, 0.f); }
+        // ring slot s holds position 2*(i-4) + s after pair i has been loaded
+        for (int i = 0; i < Lp + 4; ++i) {
+            yr[8] = ld2(ysrc + (size_t)(2 * i) * ld);
+            yr[9] = ld2(ysrc + (size_t)(2 * i + 1) * ld);
+            dr[8] = make_float2(0.f, 0.f);
+            dr[9] = make_float2(0.f, 0.f);
+            if (i >= 4) {
+                const int j = i - 4;
+                float2 av = ld2(asrc + (size_t)j * ld), gv = ld2(gsrc + (size_t)j * ld);
+                if (av.x > 0.f) {      // kept by dropout and the window maximum was positive
+                    int best = 0;
+                    float bm = -INFINITY;
+#pragma unroll
+                    for (int s = 0; s < 10; ++s) { float z = fmaf(yr[s].x, scx, shx); if (z > bm) { bm = z; best = s; } }
+                    const float g = gv.x * inv_keep;
+#pragma unroll
+                    for (int s = 0; s < 10; ++s) dr[s].x += (s == best) ? g : 0.f;
+                }
+                if (av.y > 0.f) {
+                    int best = 0;
+                    float bm = -INFINITY;
+#pragma unroll
+                    for (int s = 0; s < 10; ++s) { float z = fmaf(yr[s].y, scy, shy); if (z > bm) { bm = z; best = s; } }
+                    const float g = gv.y * inv_keep;
+#pragma unroll
+                    for (int s = 0; s < 10; ++s) dr[s].y += (s == best) ? g : 0.f;
+                }
+                // positions 2j and 2j+1 are final
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    st2(dst + (size_t)(2 * j + s) * ld, dr[s]);
+                    sdz[0] += dr[s].x; sdz[1] += dr[s].y;
+                    sdzx[0] += dr[s].x * (yr[s].x - mux) * rsx;
+                    sdzx[1] += dr[s].y * (yr[s].y - muy) * rsy;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 8; ++s) { yr[s] = yr[s + 2]; dr[s] = dr[s + 2]; }
+        }
+        // after the loop slots 0..7 hold positions 2*Lp .. 2*Lp+7; everything beyond was never inside a window
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const int l = 2 * Lp + s;
+            if (l < Lc) {
+                st2(dst + (size_t)l * ld, dr[s]);
+                sdz[0] += dr[s].x; sdz[1] += dr[s].y;
+                sdzx[0] += dr[s].x * (yr[s].x - mux) * rsx;
+                sdzx[1] += dr[s].y * (yr[s].y - muy) * rsy;
+            }
+        }
+        for (int l = 2 * Lp + 8; l < Lc; ++l) st2(dst + (size_t)l * ld, make_float2(0.f, 0.f));
+    }
+    red[0][threadIdx.y][threadIdx.x] = sdz[0];
+    red[1][threadIdx.y][threadIdx.x] = sdz[1];
+    red[2][threadIdx.y][threadIdx.x] = sdzx[0];
+    red[3][threadIdx.y][threadIdx.x] = sdzx[1];
+    __syncthreads();
+    if (threadIdx.y < 4 && cp < pairs) {
+        double tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += red[threadIdx.y][i][threadIdx.x];
+        const int c = 2 * cp + (threadIdx.y & 1);
+        atomicAdd(&bstats[(threadIdx.y < 2 ? 0 : C) + c], tot);
+    }
+}
+
+// K2 backward stage 2, two channels per thread
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_v2_kernel(const T* __restrict__ y, T* __restrict__ dz, const double* __restrict__ bstats, const float* __restrict__ gamma,
+                       const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dbias, int64_t R, int C,
+                       int ld, double n) {
+    __shared__ float s1[2][8][33];
+    const int pairs = C / 2;
+    const int cp = blockIdx.x * 32 + threadIdx.x;
+    float2 acc = make_float2(0.f, 0.f);
+    if (cp < pairs) {
+        const int c = 2 * cp;
+        const float2 dbn = make_float2((float)(bstats[c] / n), (float)(bstats[c + 1] / n));
+        const float2 dgn = make_float2((float)(bstats[C + c] / n), (float)(bstats[C + c + 1] / n));
+        const float2 mu = make_float2(mean[c], mean[c + 1]), rs = make_float2(rstd[c], rstd[c + 1]);
+        const float2 gs = make_float2(gamma[c] * rs.x, gamma[c + 1] * rs.y);
+#pragma unroll 4
+        for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < R; r += (int64_t)gridDim.y * 8) {
+            float2 yv = ld2(y + r * ld + c), dv = ld2(dz + r * ld + c);
+            float2 v;
+            v.x = gs.x * (dv.x - dbn.x - (yv.x - mu.x) * rs.x * dgn.x);
+            v.y = gs.y * (dv.y - dbn.y - (yv.y - mu.y) * rs.y * dgn.y);
+            st2(dz + r * ld + c, v);
+            acc.x += v.x;
+            acc.y += v.y;
+        }
+    }
+    s1[0][threadIdx.y][threadIdx.x] = acc.x;
+    s1[1][threadIdx.y][threadIdx.x] = acc.y;
+    __syncthreads();
+    if (threadIdx.y < 2 && cp < pairs) {
+        float t = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += s1[threadIdx.y][i][threadIdx.x];
+        atomicAdd(&dbias[2 * cp + threadIdx.y], t);
+    }
+}
+
+// BatchNorm batch statistics, two channels per thread
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_stats_v2_kernel(const T* __restrict__ y, double* __restrict__ stats, int64_t R, int C, int ld) {
+    __shared__ float s[4][8][33];
+    const int pairs = C / 2;
+    const int cp = blockIdx.x * 32 + threadIdx.x;
+    float2 a = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
+    if (cp < pairs) {
+#pragma unroll 4
+        for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < R; r += (int64_t)gridDim.y * 8) {
+            float2 v = ld2(y + r * ld + 2 * cp);
+            a.x += v.x; a.y += v.y;
+            q.x += v.x * v.x; q.y += v.y * v.y;
+        }
+    }
+    s[0][threadIdx.y][threadIdx.x] = a.x;
+    s[1][threadIdx.y][threadIdx.x] = a.y;
+    s[2][threadIdx.y][threadIdx.x] = q.x;
+    s[3][threadIdx.y][threadIdx.x] = q.y;
+    __syncthreads();
+    if (threadIdx.y < 4 && cp < pairs) {
+        double tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += s[threadIdx.y][i][threadIdx.x];
+        atomicAdd(&stats[(threadIdx.y < 2 ? 0 : C) + 2 * cp + (threadIdx.y & 1)], tot);
+    }
+}
+
+}  // namespace emb
