@@ -173,6 +173,10 @@ int emb_backward(EmbEngine* e, const float* dlogits, void* stream);
 /* optimizer.step() over the whole parameter arena (torch.optim.Adam / RMSprop, timm Nadam, all with
  * coupled L2 weight decay; EMB_OPT_ADAMW decoupled). */
 int emb_opt_step(EmbEngine* e, const EmbOptConfig* cfg, void* stream);
+/* The host-visible part of the optimizer state (torch.optim keeps `step` per parameter; the fused kernel keeps one):
+ * number of steps taken and Nadam's running momentum-schedule product.  The moments live in opt_m / opt_v. */
+int emb_opt_state_get(const EmbEngine* e, int64_t* step_out, double* nadam_mu_product_out);
+int emb_opt_state_set(EmbEngine* e, int64_t step, double nadam_mu_product);
 /* One iteration of the loop body at training_models_multimodal.py:132-162: forward, loss,
  * backward, optimizer step, metrics; nothing returns to the host. */
 int emb_train_step(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const int32_t* labels, int32_t B,

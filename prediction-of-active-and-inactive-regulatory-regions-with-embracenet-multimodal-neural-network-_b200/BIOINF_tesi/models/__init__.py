@@ -1,0 +1,9 @@
+"""Mirror of BIOINF_tesi/models/__init__.py:1-15 for the classes on the EmbraceNet hot path."""
+from .CNN_net import CNN
+from .FF_net import FFNN
+from .CNN_pre import CNN_pre, CNN_pre_NoTrain
+from .FFNN_pre import FFNN_pre, FFNN_pre_NoTrain
+from .EmbraceNetMultimodal import EmbraceNet, EmbraceNetMultimodal, EmbraceNetMultimodal_NoTrain
+
+__all__ = ['CNN', 'FFNN', 'CNN_pre', 'FFNN_pre', 'EmbraceNetMultimodal', 'CNN_pre_NoTrain', 'FFNN_pre_NoTrain',
+           'EmbraceNetMultimodal_NoTrain', 'EmbraceNet']

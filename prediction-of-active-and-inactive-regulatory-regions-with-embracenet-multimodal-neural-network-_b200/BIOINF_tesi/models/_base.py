@@ -1,0 +1,216 @@
+"""Shared machinery of the nn.Module mirrors: parameters are views into the engine's flat fp32 arenas."""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from ... import _native as N
+from ...archspec import ArchSpec
+from ...engine import Engine
+
+
+def _resolve_device(device):
+    dev = torch.device(device if device is not None else 'cuda')
+    if dev.type != 'cuda':
+        raise N.EmbError(f"device={device!r}: the B200 engine has no CPU path (the reference's CPU route is the oracle's job)")
+    if dev.index is None:
+        dev = torch.device('cuda', torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    return dev
+
+
+class _EngineFn(torch.autograd.Function):
+    """logits = engine.forward_train(...); backward hands dlogits to emb_backward, which fills the gradient arena."""
+
+    @staticmethod
+    def forward(ctx, anchor, owner, x_ffnn, bases, availabilities, draws):
+        ctx.owner = owner
+        logits = owner._engine_for(x_ffnn, bases).forward(x_ffnn, bases, training=True, draws=draws, availabilities=availabilities)
+        ctx.token = owner._forward_token
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        owner = ctx.owner
+        if ctx.token != owner._forward_token:
+            raise RuntimeError('backward() through a stale forward: the engine keeps the activations of the most recent '
+                               'training forward only')
+        owner._engine.backward(dlogits.contiguous())
+        owner._publish_grads()
+        return (None,) * 6
+
+
+class EngineModule(nn.Module):
+    """Base of the mirrors.  Subclasses build the reference's module tree (same attribute names -> same state_dict
+    keys) out of ordinary torch.nn layers used purely as PARAMETER CONTAINERS; `_adopt()` then re-points every
+    parameter / BatchNorm buffer at its slot in the engine's arenas.  No torch.nn forward is ever executed."""
+
+    precision_default = 'bf16'
+
+    def _adopt(self, spec: ArchSpec, device, precision=None, seed=0x5EED):
+        self.spec = spec
+        self._dev = _resolve_device(device)
+        self._precision = precision or self.precision_default
+        self._seed = seed
+        self._engine = None
+        self._forward_token = 0
+        self._anchor = None
+        lib = N.lib()
+        if not torch.cuda.is_available() or lib.emb_device_count() < 1:
+            raise N.EmbError('no B200 (sm_100) device visible: the EmbraceNet engine has no CPU fallback')
+        # plan the arenas (no device work) and create them on the Python side so that they outlive workspace resizes
+        h = C.c_void_p()
+        N.check(lib.emb_create(C.byref(spec.to_c()), 1, N.PREC[self._precision], C.byref(h)))
+        n_params, n_buffers = lib.emb_param_count(h), lib.emb_buffer_count(h)
+        table, info = [], N.EmbParamInfo()
+        for i in range(lib.emb_num_tensors(h)):
+            N.check(lib.emb_param_info(h, i, C.byref(info)))
+            table.append((info.name.decode(), info.offset, info.numel, tuple(info.shape[:info.ndim]), bool(info.is_buffer)))
+        lib.emb_destroy(h)
+        f32 = dict(dtype=torch.float32, device=self._dev)
+        self._arenas = dict(params=torch.zeros(max(n_params, 4), **f32), grads=torch.zeros(max(n_params, 4), **f32),
+                            buffers=torch.zeros(max(n_buffers, 4), **f32), opt_m=torch.zeros(max(n_params, 4), **f32),
+                            opt_v=torch.zeros(max(n_params, 4), **f32))
+        self._table = table
+        own = dict(self.named_parameters())
+        bufs = dict(self.named_buffers())
+        with torch.no_grad():
+            for name, off, numel, shape, is_buf in table:
+                arena = self._arenas['buffers' if is_buf else 'params']
+                view = arena[off:off + numel].view(shape)
+                src = bufs[name] if is_buf else own[name]
+                assert tuple(src.shape) == shape, (name, tuple(src.shape), shape)
+                view.copy_(src.detach().to(self._dev, torch.float32))
+                if is_buf:
+                    mod, leaf = self._owner_of(name)
+                    mod._buffers[leaf] = view
+                else:
+                    own[name].data = view
+        for b in self.buffers():       # num_batches_tracked counters follow the arenas to the device
+            if b.device != self._dev:
+                b.data = b.data.to(self._dev)
+        self._anchor = torch.zeros((), device=self._dev, requires_grad=True)
+        return self
+
+    def _owner_of(self, dotted):
+        mod = self
+        parts = dotted.split('.')
+        for p in parts[:-1]:
+            mod = getattr(mod, p)
+        return mod, parts[-1]
+
+    # ---- nn.Module API the reference's L3/L4 code uses ---------------------------------------------------------
+    def double(self):
+        """The reference trains `model.double()` on CPU; the engine keeps fp32 master weights and computes in
+        bf16 (or fp32): the call is accepted and ignored (precision contract)."""
+        return self
+
+    def float(self):
+        return self
+
+    def to(self, *args, **kwargs):
+        dev = kwargs.get('device', args[0] if args and not isinstance(args[0], torch.dtype) else None)
+        if dev is not None and torch.device(dev).type != 'cuda':
+            raise N.EmbError('the B200 engine cannot be moved off the GPU')
+        return self
+
+    def cuda(self, device=None):
+        return self
+
+    def _apply(self, fn, recurse=True):
+        # parameters are arena views: dtype / device conversions must not re-allocate them
+        return self
+
+    def _engine_for(self, x_ffnn, bases):
+        B = (x_ffnn if x_ffnn is not None else bases).shape[0]
+        if self._engine is None or B > self._engine.max_batch:
+            cap = max(B, 256)
+            old = self._engine
+            state = old.opt_state() if old is not None else None
+            self._engine = Engine(self.spec, cap, precision=self._precision, device=self._dev, seed=self._seed, arenas=self._arenas)
+            if state is not None:
+                self._engine.set_opt_state(*state)
+            del old
+        return self._engine
+
+    def _publish_grads(self):
+        own = dict(self.named_parameters())
+        for name, off, numel, shape, is_buf in self._table:
+            if not is_buf:
+                own[name].grad = self._arenas['grads'][off:off + numel].view(shape)
+
+    def _bump_batches_tracked(self):
+        for name, b in self.named_buffers():
+            if name.endswith('num_batches_tracked'):
+                b += 1
+
+    @staticmethod
+    def _to_bases(x_cnn, dev):
+        """[B,4,256] one-hot (any float dtype) or [B,256] integer codes (a,c,g,t = 0..3) -> uint8 [B,256] on the device."""
+        x = torch.as_tensor(x_cnn)
+        if x.dim() == 2 and x.shape[1] == 256:
+            return x.to(dev, torch.uint8)
+        if x.dim() == 3 and x.shape[1] == 4 and x.shape[2] == 256:
+            return x.to(dev).argmax(dim=1).to(torch.uint8)
+        raise ValueError(f'sequence input must be one-hot [B,4,256] or base codes [B,256], got {tuple(x.shape)}')
+
+    def _run(self, x_ffnn, x_cnn, availabilities, draws, modality_dropout):
+        dev = self._dev
+        xf = torch.as_tensor(x_ffnn).to(dev, torch.float32).contiguous() if x_ffnn is not None else None
+        if xf is not None and xf.dim() == 1:
+            xf = xf.unsqueeze(0)
+        bases = self._to_bases(x_cnn, dev).contiguous() if x_cnn is not None else None
+        if self.spec.kind == 'embracenet' and not modality_dropout:
+            draws = dict(draws or {})
+            draws.setdefault('modal_u0', 0.0)          # coin < 0.5: EmbraceNetMultimodal.py:179-180 takes no modality away
+        if self.training:
+            self._forward_token += 1
+            if torch.is_grad_enabled():
+                out = _EngineFn.apply(self._anchor, self, xf, bases, availabilities, draws)
+            else:
+                out = self._engine_for(xf, bases).forward(xf, bases, training=True, draws=draws, availabilities=availabilities)
+            self._bump_batches_tracked()
+            return out
+        return self._engine_for(xf, bases).forward(xf, bases, training=False, draws=draws, availabilities=availabilities)
+
+    def _batch_inputs(self, x_ffnn, x_cnn, target):
+        dev = self._dev
+        xf = torch.as_tensor(x_ffnn).to(dev, torch.float32).contiguous() if x_ffnn is not None else None
+        bases = self._to_bases(x_cnn, dev).contiguous() if x_cnn is not None else None
+        y = torch.as_tensor(target).reshape(-1).to(dev, torch.int32).contiguous()
+        return xf, bases, y
+
+    def train_batch(self, x_ffnn, x_cnn, target, opt_cfg, draws=None, reset_metrics=False):
+        """One iteration of the reference's loop body (training_models_multimodal.py:132-162) as a single fused engine
+        call: forward(is_training=True), class-weighted CE, backward, optimizer step; loss and confusion counts are
+        appended to the device-side metric records."""
+        xf, bases, y = self._batch_inputs(x_ffnn, x_cnn, target)
+        eng = self._engine_for(xf, bases)
+        if reset_metrics:
+            eng.metrics_reset()
+        self._forward_token += 1
+        eng.train_step(xf, bases, y, opt_cfg, draws=draws)
+        self._bump_batches_tracked()
+
+    @torch.no_grad()
+    def eval_batch(self, x_ffnn, x_cnn, target, draws=None, reset_metrics=False):
+        """model.eval() forward + the same loss/metric record, no gradient (training_models_multimodal.py:167-192)."""
+        xf, bases, y = self._batch_inputs(x_ffnn, x_cnn, target)
+        eng = self._engine_for(xf, bases)
+        if reset_metrics:
+            eng.metrics_reset()
+        logits = eng.forward(xf, bases, training=False, draws=draws)
+        eng.loss(logits, y, want_grad=False)
+        return logits
+
+    def state_dict(self, *args, **kwargs):
+        """Reference key names; tensors are detached COPIES (the live parameters are views of one flat arena)."""
+        sd = super().state_dict(*args, **kwargs)
+        return type(sd)((k, v.detach().clone()) for k, v in sd.items())
+
+    def __getstate__(self):
+        raise TypeError('pickling a whole engine-backed module is not supported: save model.state_dict() (the reference\'s '
+                        'torch.save(model) of Optuna trials, training_models_multimodal.py:413, is outside the hot path)')
+
+    @property
+    def engine(self):
+        return self._engine

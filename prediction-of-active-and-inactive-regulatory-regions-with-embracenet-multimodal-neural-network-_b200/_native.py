@@ -78,6 +78,8 @@ SIGNATURES = {
     'emb_loss_ce_weighted': (C.c_int, [_P, _P, _P, C.c_int32, _P, _P]),
     'emb_backward': (C.c_int, [_P, _P, _P]),
     'emb_opt_step': (C.c_int, [_P, C.POINTER(EmbOptConfig), _P]),
+    'emb_opt_state_get': (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    'emb_opt_state_set': (C.c_int, [_P, C.c_int64, C.c_double]),
     'emb_train_step': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.POINTER(EmbDraws), C.POINTER(EmbOptConfig), _P]),
     'emb_train_step_host': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.POINTER(EmbOptConfig), C.POINTER(EmbStepMetrics), _P]),
     'emb_predict_host': (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P]),

@@ -1066,6 +1066,20 @@ int emb_set_tensor_core(EmbEngine* e, int32_t on) {
 
 int64_t emb_launch_count(const EmbEngine* e) { return e ? e->launches : 0; }
 
+int emb_opt_state_get(const EmbEngine* e, int64_t* step_out, double* nadam_mu_product_out) {
+    if (!e) return set_error(EMB_E_ARG, "null engine");
+    if (step_out) *step_out = e->opt_t;
+    if (nadam_mu_product_out) *nadam_mu_product_out = e->nadam_mu_product;
+    return EMB_OK;
+}
+
+int emb_opt_state_set(EmbEngine* e, int64_t step, double nadam_mu_product) {
+    if (!e || step < 0) return set_error(EMB_E_ARG, "bad optimizer state");
+    e->opt_t = step;
+    e->nadam_mu_product = nadam_mu_product;
+    return EMB_OK;
+}
+
 int emb_profile_gemm(EmbEngine* e, int32_t enable) {
     if (!e) return set_error(EMB_E_ARG, "null engine");
     e->prof_on = enable != 0;

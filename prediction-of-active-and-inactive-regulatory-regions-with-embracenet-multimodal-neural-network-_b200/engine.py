@@ -19,7 +19,9 @@ def _ptr(t):
 
 class Engine:
     def __init__(self, spec: ArchSpec, max_batch: int, precision: str = 'fp32', device='cuda', seed: int = 0x5EED,
-                 tensor_core: bool = None):
+                 tensor_core: bool = None, arenas=None):
+        """arenas: optional dict(params=, grads=, buffers=, opt_m=, opt_v=) of fp32 CUDA tensors to bind instead of
+        allocating new ones (the nn.Module mirror owns them so that its nn.Parameters survive a workspace resize)."""
         self.lib = N.lib()
         if not torch.cuda.is_available() or self.lib.emb_device_count() < 1:
             raise N.EmbError('no B200 (sm_100) device visible: the EmbraceNet engine has no CPU fallback')
@@ -37,11 +39,16 @@ class Engine:
         self.ws_bytes = self.lib.emb_workspace_bytes(self._h)
         with torch.cuda.device(self.device):
             f32 = dict(dtype=torch.float32, device=self.device)
-            self.params = torch.zeros(max(self.n_params, 4), **f32)
-            self.grads = torch.zeros(max(self.n_params, 4), **f32)
-            self.buffers = torch.zeros(max(self.n_buffers, 4), **f32)
-            self.opt_m = torch.zeros(max(self.n_params, 4), **f32)
-            self.opt_v = torch.zeros(max(self.n_params, 4), **f32)
+            arenas = arenas or {}
+            self.params = arenas.get('params', None)
+            if self.params is None:
+                self.params = torch.zeros(max(self.n_params, 4), **f32)
+            self.grads = arenas['grads'] if 'grads' in arenas else torch.zeros(max(self.n_params, 4), **f32)
+            self.buffers = arenas['buffers'] if 'buffers' in arenas else torch.zeros(max(self.n_buffers, 4), **f32)
+            self.opt_m = arenas['opt_m'] if 'opt_m' in arenas else torch.zeros(max(self.n_params, 4), **f32)
+            self.opt_v = arenas['opt_v'] if 'opt_v' in arenas else torch.zeros(max(self.n_params, 4), **f32)
+            for t in (self.params, self.grads, self.buffers, self.opt_m, self.opt_v):
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
             self.workspace = torch.zeros(self.ws_bytes + 256, dtype=torch.uint8, device=self.device)
             off = (-self.workspace.data_ptr()) % 256
             self._ws_view = self.workspace[off:off + self.ws_bytes]
@@ -183,6 +190,14 @@ class Engine:
 
     def opt_step(self, cfg):
         N.check(self.lib.emb_opt_step(self._h, C.byref(cfg), self.stream))
+
+    def opt_state(self):
+        t, mp = C.c_int64(), C.c_double()
+        N.check(self.lib.emb_opt_state_get(self._h, C.byref(t), C.byref(mp)))
+        return t.value, mp.value
+
+    def set_opt_state(self, step, mu_product=1.0):
+        N.check(self.lib.emb_opt_state_set(self._h, int(step), float(mu_product)))
 
     def train_step(self, x_ffnn, bases, labels, cfg, draws=None):
         x_ffnn, bases = self._inputs(x_ffnn, bases)
