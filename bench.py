@@ -188,29 +188,25 @@ def main():
              torch.from_numpy(y[lo:lo + B]).pin_memory()) for x, b, y in glob]
     devb = [(x.to(dev), b.to(dev), y.to(dev)) for x, b, y in host]
     npos = [int(y.sum()) for _, _, y in glob]
+    dp = None
     if world > 1:
-        eng.set_shard(lo, args.batch)
-        eng.set_allreduce(lambda t: dist.all_reduce(t))
+        from embrace_b200.dp import DataParallel
+        dp = DataParallel(eng, args.batch, rank, world)
+        assert (dp.lo, dp.hi) == (lo, lo + B)
 
     def step_device(i):
         x, b, y = devb[i % NBUF]
-        if world > 1:
-            eng.set_global_positives(npos[i % NBUF])
-            eng.train_step(x, b, y, None)                    # forward + loss + backward
-            dist.all_reduce(eng.grads)                       # the one data-path collective (flat fp32 gradient arena)
-            eng.opt_step(cfg)
+        if dp is not None:
+            dp.train_step(x, b, y, npos[i % NBUF], cfg)      # SyncBN partial sums + ONE gradient all-reduce per step
         else:
             eng.train_step(x, b, y, cfg)
 
     def step_host(i):
         x, b, y = host[i % NBUF]
-        if world > 1:
-            eng.set_global_positives(npos[i % NBUF])
+        if dp is not None:
             xd, bd, yd = x.to(dev, non_blocking=True), b.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
             eng.metrics_reset()
-            eng.train_step(xd, bd, yd, None)
-            dist.all_reduce(eng.grads)
-            eng.opt_step(cfg)
+            dp.train_step(xd, bd, yd, npos[i % NBUF], cfg)
             return eng.metrics_read(1)[0]['loss']
         return eng.train_step_host(x, b, y, cfg).loss
 

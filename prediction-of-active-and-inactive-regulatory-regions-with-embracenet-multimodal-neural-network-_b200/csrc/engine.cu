@@ -620,9 +620,13 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
             int rc = e->allreduce(e->allreduce_user, c.bstats, 2 * c.cout, st);
             if (rc) return set_error(EMB_E_STATE, "allreduce callback failed (%d)", rc);
         }
-        bn_bwd_finalize_kernel<<<cdiv(c.cout, 128), 128, 0, st>>>(c.bstats, e->grads + c.gamma, e->grads + c.beta, c.cout);
-        EMB_CHECK_LAUNCH();
-        LAUNCHED(e);
+        // under data parallelism the all-reduced statistics are already global: only the first shard contributes
+        // them to the gradient arena (which the host then sum-reduces across ranks)
+        if (!e->allreduce || e->row_offset == 0) {
+            bn_bwd_finalize_kernel<<<cdiv(c.cout, 128), 128, 0, st>>>(c.bstats, e->grads + c.gamma, e->grads + c.beta, c.cout);
+            EMB_CHECK_LAUNCH();
+            LAUNCHED(e);
+        }
         double n = (double)(e->global_batch > 0 ? e->global_batch : B) * c.Lc;
         if (even) {
             const int gx = cdiv(c.cout / 2, 32);

@@ -1,0 +1,58 @@
+"""Data-parallel training of one EmbraceNet over the GPUs of a node: one process per GPU,
+`torch.distributed` (NCCL over NVLink) for the plumbing.
+
+The global batch is partitioned by rows.  What couples the rows, and how it is kept equal to the single-GPU
+large-batch step:
+  * BatchNorm batch statistics      -> the engine hands its per-channel partial sums ([sum, sumsq] forward,
+                                       [sum dz, sum dz*xhat] backward; 2*C doubles per conv layer) to an all-reduce
+                                       between its stats and finalize kernels (SyncBN); n is the GLOBAL B*L
+  * per-batch class weights of the loss -> computed from the GLOBAL positive count (labels are known to the host)
+  * random draws                    -> Philox counters are keyed by GLOBAL row, so the partition does not change them
+  * parameter gradients             -> ONE all-reduce (sum) of the flat fp32 gradient arena per step
+No other collective exists on the path.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_rows(global_batch, rank, world):
+    """Contiguous, near-equal row ranges: rank r owns [lo, hi)."""
+    base, rem = divmod(global_batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def merge_step_metrics(records, group=None):
+    """Each rank's EmbStepMetrics hold its share of the (globally normalised) loss and its confusion counts:
+    the global record is their sum.  records: list of dicts; returns the merged list (same on every rank)."""
+    if not records:
+        return records
+    dev = 'cuda' if dist.get_backend(group) == 'nccl' else 'cpu'
+    t = torch.tensor([[r['loss'], r['tp'], r['fp'], r['fn'], r['tn']] for r in records], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, group=group)
+    t = t.cpu()
+    return [dict(loss=float(a[0]), tp=int(a[1]), fp=int(a[2]), fn=int(a[3]), tn=int(a[4])) for a in t]
+
+
+class DataParallel:
+    """Wraps an Engine whose rows are this rank's shard of the global batch."""
+
+    def __init__(self, engine, global_batch, rank=None, world=None, group=None):
+        self.engine, self.group = engine, group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.global_batch = global_batch
+        self.lo, self.hi = shard_rows(global_batch, self.rank, self.world)
+        engine.set_shard(self.lo, global_batch)
+        engine.set_allreduce(lambda t: dist.all_reduce(t, group=group))
+
+    def broadcast_parameters(self, src=0):
+        dist.broadcast(self.engine.params, src, group=self.group)
+        dist.broadcast(self.engine.buffers, src, group=self.group)
+
+    def train_step(self, x_local, bases_local, y_local, n_pos_global, cfg):
+        eng = self.engine
+        eng.set_global_positives(n_pos_global)
+        eng.train_step(x_local, bases_local, y_local, None)       # forward + loss + backward (SyncBN inside)
+        dist.all_reduce(eng.grads, group=self.group)               # the gradient all-reduce
+        eng.opt_step(cfg)
