@@ -85,15 +85,17 @@ __device__ __forceinline__ uint4 rng_raw(const RngState& s, uint32_t stream, uin
     uint2 key = make_uint2((uint32_t)s.seed, (uint32_t)(s.seed >> 32));
     return philox4x32_10(ctr, key);
 }
-// uniform in [0,1), 24 bits
+// Element e of a stream uses word (e & 3) of the Philox block with counter (e >> 2): four draws per block, and the value
+// depends only on (seed, step, stream, e) -- not on tiling, back end or data-parallel partition.
+__device__ __forceinline__ uint32_t rng_word(const uint4& r, uint32_t i) { return i == 0 ? r.x : i == 1 ? r.y : i == 2 ? r.z : r.w; }
+__device__ __forceinline__ float u32_to_unit_f32(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }     // [0,1), 24 bits
+__device__ __forceinline__ double u32_to_unit_f64(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }           // [0,1), 32 bits
 __device__ __forceinline__ float rng_uniform_f32(const RngState& s, uint32_t stream, uint64_t elem) {
-    return (float)(rng_raw(s, stream, elem).x >> 8) * (1.0f / 16777216.0f);
+    return u32_to_unit_f32(rng_word(rng_raw(s, stream, elem >> 2), (uint32_t)elem & 3u));
 }
-// uniform in [0,1), 53 bits (what torch's CPU generator gives torch.multinomial)
+// the modality choice compares in fp64 (EmbraceNetMultimodal.py:84 via torch.multinomial); 32 random bits are ample for it
 __device__ __forceinline__ double rng_uniform_f64(const RngState& s, uint32_t stream, uint64_t elem) {
-    uint4 r = rng_raw(s, stream, elem);
-    uint64_t bits = (((uint64_t)r.x << 32) | r.y) >> 11;
-    return (double)bits * (1.0 / 9007199254740992.0);
+    return u32_to_unit_f64(rng_word(rng_raw(s, stream, elem >> 2), (uint32_t)elem & 3u));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -43,6 +43,7 @@ struct Tensor {       // one state_dict entry
 struct LinearLayer {
     int in, out;
     bf16* wc;         // bf16 operand copy [out][round_up(in,8)] (permuted to channels-last order when perm_in)
+    float* wg_tmp;    // perm_in layers: weight gradient in engine (channels-last) column order before un-permuting
     int64_t w, b;     // offsets into the params arena
     float drop;
     bool relu;
@@ -259,6 +260,17 @@ __global__ void wcache_conv_kernel(const float* __restrict__ w, bf16* __restrict
     out[i] = __float2bfloat16_rn(c < Cin ? w[((size_t)o * Cin + c) * taps + tap] : 0.f);
 }
 
+// dW[n][c*L + l] = tmp[n][l*C + c]: the permuted-input Linear's weight gradient back to the reference's flatten order
+__global__ void unpermute_wgrad_kernel(const float* __restrict__ tmp, float* __restrict__ dw, int N, int L, int C) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t K = (size_t)L * C;
+    if (i >= (size_t)N * K) return;
+    size_t n = i / K;
+    int r = (int)(i - n * K);
+    int c = r / L, l = r - c * L;                        // destination index walks the reference layout (coalesced writes)
+    dw[i] = tmp[n * K + (size_t)l * C + c];
+}
+
 // carve the workspace; with base == nullptr only the size is computed
 int64_t carve(EmbEngine* e, char* base) {
     Bump bp{base};
@@ -278,7 +290,10 @@ int64_t carve(EmbEngine* e, char* base) {
     e->in_labels = bp.take<int32_t>(Bm);
     e->in_avail = bp.take<float>(Bm * 2);
     if (e->prec == EMB_PREC_BF16) {
-        auto wl = [&](LinearLayer& l) { l.wc = bp.take<bf16>((int64_t)l.out * round_up(l.in, 8)); };
+        auto wl = [&](LinearLayer& l) {
+            l.wc = bp.take<bf16>((int64_t)l.out * round_up(l.in, 8));
+            if (l.perm_in) l.wg_tmp = bp.take<float>((int64_t)l.out * l.in);
+        };
         for (auto& l : e->ffnn) wl(l);
         for (auto& l : e->post) wl(l);
         for (auto& l : e->head) wl(l);
@@ -481,7 +496,19 @@ int linear_wgrad(EmbEngine* e, const LinearLayer& l, const void* g, int g_dtype,
         TcProblem pr = {};
         pr.kind = TC_LINEAR_WGRAD; pr.a = (const bf16*)g; pr.lda = g_ld; pr.b = (const bf16*)in.p; pr.ldb = in.ld;
         pr.M = l.out; pr.N = l.in; pr.K = B;
-        rc = run_tc(e, pr, ep, 2.0 * B * l.out * l.in, st);
+        if (l.perm_in && l.wg_tmp) {
+            // accumulate in the engine's column order (coalesced), then un-permute once into the gradient arena
+            EMB_CUDA_OK(cudaMemsetAsync(l.wg_tmp, 0, (size_t)l.out * l.in * sizeof(float), st));
+            Epilogue et = base_epi(e, EPI_ATOMIC, l.wg_tmp, l.in);
+            rc = run_tc(e, pr, et, 2.0 * B * l.out * l.in, st);
+            if (rc) return rc;
+            size_t tot = (size_t)l.out * l.in;
+            unpermute_wgrad_kernel<<<cdiv(tot, 256), 256, 0, st>>>(l.wg_tmp, e->grads + l.w, l.out, e->cnn_Lp_last, e->cnn_C_last);
+            EMB_CHECK_LAUNCH();
+            LAUNCHED(e);
+        } else {
+            rc = run_tc(e, pr, ep, 2.0 * B * l.out * l.in, st);
+        }
     } else {
         rc = run_gemm(e, A, X, ep, l.out, l.in, B, pick_split_k(l.out, l.in, B), st);
     }

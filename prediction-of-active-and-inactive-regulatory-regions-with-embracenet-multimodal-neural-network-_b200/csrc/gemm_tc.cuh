@@ -154,6 +154,96 @@ __device__ __forceinline__ void tc_epilogue_row16(const Epilogue& ep, int m, int
         dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
         return;
     }
+    if (vec && ep.mode == EPI_LINEAR && ep.drop_p > 0.f && ep.flatC == 0 && ep.drop_u == nullptr && (N & 3) == 0) {
+        // nn.Linear -> ReLU -> Dropout with the counter-based generator: 4 Philox blocks cover the 16 columns
+        if (ep.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float4 b = __ldg(b4 + i);
+                v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+        }
+        const float inv_keep = 1.f / (1.f - ep.drop_p);
+        const RngState rs = *ep.rng;
+        const uint64_t e0 = (uint64_t)(ep.row_offset + m) * N + n0;      // multiple of 4
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint4 r = rng_raw(rs, ep.rng_stream, (e0 >> 2) + i);
+            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float x = v[4 * i + j];
+                if (ep.relu) x = fmaxf(x, 0.f);
+                v[4 * i + j] = (u32_to_unit_f32(w[j]) >= ep.drop_p) ? x * inv_keep : 0.f;
+            }
+        }
+        uint4* dst = reinterpret_cast<uint4*>((bf16*)ep.out + (size_t)m * ep.ldo + n0);
+        dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        return;
+    }
+    if (vec && ep.mode == EPI_EMBRACE && ep.emb_u == nullptr && (N & 15) == 0 && (ep.ld_d0 & 7) == 0) {
+        // docking_1 epilogue: d1 = relu(acc + b1); idx = (u > cum0[m]); e = idx ? d1 : d0; idx stored as bytes
+        const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 b = __ldg(b4 + i);
+            v[4 * i] = fmaxf(v[4 * i] + b.x, 0.f); v[4 * i + 1] = fmaxf(v[4 * i + 1] + b.y, 0.f);
+            v[4 * i + 2] = fmaxf(v[4 * i + 2] + b.z, 0.f); v[4 * i + 3] = fmaxf(v[4 * i + 3] + b.w, 0.f);
+        }
+        const uint4* d4 = reinterpret_cast<const uint4*>((const bf16*)ep.d0 + (size_t)m * ep.ld_d0 + n0);
+        const uint4 da = d4[0], db = d4[1];
+        const uint32_t dw[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+        // u = w / 2^32 > cum0  <=>  w > floor(cum0 * 2^32)   (integer compare; cum0 == 1 can never be exceeded)
+        const unsigned long long thr = (unsigned long long)floor(ep.cum0[m] * 4294967296.0);
+        const RngState rs = *ep.rng;
+        const uint64_t e0 = (uint64_t)(ep.row_offset + m) * N + n0;
+        uint32_t idw[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint4 r = rng_raw(rs, RNG_EMBRACE, (e0 >> 2) + i);
+            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = 4 * i + j;
+                const int id = (unsigned long long)w[j] > thr;
+                const uint32_t pair = dw[k >> 1];
+                const float d0v = __uint_as_float((k & 1) ? (pair & 0xFFFF0000u) : (pair << 16));
+                v[k] = id ? v[k] : d0v;
+                idw[i] |= (uint32_t)id << (8 * j);
+            }
+        }
+        uint4* dst = reinterpret_cast<uint4*>((bf16*)ep.out + (size_t)m * ep.ldo + n0);
+        dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        *reinterpret_cast<uint4*>(ep.idx_out + (size_t)m * N + n0) = make_uint4(idw[0], idw[1], idw[2], idw[3]);
+        return;
+    }
+    if (vec && ep.mode == EPI_EMBRACE_BWD && (N & 15) == 0 && (ep.ld_e & 7) == 0) {
+        const uint4* e4 = reinterpret_cast<const uint4*>((const bf16*)ep.e + (size_t)m * ep.ld_e + n0);
+        const uint4 ea = e4[0], eb = e4[1];
+        const uint32_t ew[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+        const uint4 iq = *reinterpret_cast<const uint4*>(ep.idx + (size_t)m * N + n0);
+        const uint32_t iw[4] = {iq.x, iq.y, iq.z, iq.w};
+        float a0[16], a1[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t h = (k & 1) ? (ew[k >> 1] >> 16) : (ew[k >> 1] & 0xFFFFu);
+            const bool pos = h != 0 && !(h & 0x8000u);
+            const int id = (iw[k >> 2] >> (8 * (k & 3))) & 0xFF;
+            const float g = pos ? v[k] : 0.f;
+            a0[k] = id == 0 ? g : 0.f;
+            a1[k] = id == 1 ? g : 0.f;
+        }
+        uint4* d0p = reinterpret_cast<uint4*>((bf16*)ep.out + (size_t)m * ep.ldo + n0);
+        uint4* d1p = reinterpret_cast<uint4*>((bf16*)ep.out2 + (size_t)m * ep.ldo + n0);
+        d0p[0] = make_uint4(pack_bf16x2(a0[0], a0[1]), pack_bf16x2(a0[2], a0[3]), pack_bf16x2(a0[4], a0[5]), pack_bf16x2(a0[6], a0[7]));
+        d0p[1] = make_uint4(pack_bf16x2(a0[8], a0[9]), pack_bf16x2(a0[10], a0[11]), pack_bf16x2(a0[12], a0[13]), pack_bf16x2(a0[14], a0[15]));
+        d1p[0] = make_uint4(pack_bf16x2(a1[0], a1[1]), pack_bf16x2(a1[2], a1[3]), pack_bf16x2(a1[4], a1[5]), pack_bf16x2(a1[6], a1[7]));
+        d1p[1] = make_uint4(pack_bf16x2(a1[8], a1[9]), pack_bf16x2(a1[10], a1[11]), pack_bf16x2(a1[12], a1[13]), pack_bf16x2(a1[14], a1[15]));
+        return;
+    }
     if (vec && ep.mode == EPI_MASKGRAD && (ep.ld_ref & 7) == 0) {
         const uint4* r4 = reinterpret_cast<const uint4*>((const bf16*)ep.ref + (size_t)m * ep.ld_ref + n0);
         uint4 ra = r4[0], rb = r4[1];
