@@ -546,10 +546,11 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
             if ((c.cout % 8) == 0 && (256 % groups) == 0) {
                 // vectorised gather-sum; BatchNorm statistics of layer 0 are accumulated by the same kernel
                 if (training) EMB_CUDA_OK(cudaMemsetAsync(c.stats, 0, 2 * c.cout * sizeof(double), st));
-                size_t smem = (size_t)(c.k * 4 * c.cout + c.cout + 256 * 16) * sizeof(float) + SEQ_LEN + 2 * c.pad + 16;
-                int grid = std::min(B, 148 * 6);
-                onehot_conv_fwd_v8_kernel<T><<<grid, 256, smem, st>>>(bases, e->params + c.w, e->params + c.b, (T*)c.y, training ? c.stats : nullptr,
-                                                                     B, c.cout, c.k, c.ld);
+                const int n_tp = (c.k + 1) / 2;
+                size_t smem = (size_t)(n_tp * 25 * c.cout + c.cout + 256 * 16) * sizeof(float) + SEQ_LEN + 2 * c.pad + 32;
+                int grid = std::min(B, 148 * 3);
+                onehot_conv_fwd_pair_kernel<T><<<grid, 256, smem, st>>>(bases, e->params + c.w, e->params + c.b, (T*)c.y,
+                                                                       training ? c.stats : nullptr, B, c.cout, c.k, c.ld);
                 stats_done = true;
             } else {
                 size_t smem = (size_t)(c.k * 4 * c.cout + c.cout) * sizeof(float) + SEQ_LEN + 2 * c.pad + 16;
@@ -655,7 +656,13 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
             LAUNCHED(e);
         }
         double n = (double)(e->global_batch > 0 ? e->global_batch : B) * c.Lc;
-        if (even) {
+        if ((c.cout % 8) == 0 && c.cout <= 2048) {
+            const int G = c.cout / 8, rpb = std::max(1, 256 / G);
+            dim3 block(G, rpb);
+            const int grid = (int)std::min<int64_t>(148 * 8, cdiv(R, rpb));
+            bn_bwd_apply_v8_kernel<T><<<grid, block, (size_t)rpb * c.cout * sizeof(float), st>>>((const T*)c.y, (T*)c.dy, c.bstats, e->params + c.gamma,
+                                                                                                c.mean, c.rstd, e->grads + c.b, R, c.cout, c.ld, n);
+        } else if (even) {
             const int gx = cdiv(c.cout / 2, 32);
             dim3 grid(gx, (unsigned)std::min<int64_t>(std::max(1, 148 * 8 / gx), cdiv(R, 8)));
             bn_bwd_apply_v2_kernel<T><<<grid, dim3(32, 8), 0, st>>>((const T*)c.y, (T*)c.dy, c.bstats, e->params + c.gamma, c.mean, c.rstd,
@@ -671,9 +678,9 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
             // conv-0 dbias was already accumulated by the bn_bwd_apply kernel
             if (even && (c.cout / 2) * c.k <= 1024) {
                 const int threads = round_up((c.cout / 2) * c.k, 32);
-                size_t smem = (size_t)SEQ_LEN * c.cout * sizeof(float) + SEQ_LEN + 16;
+                size_t smem = (size_t)(SEQ_LEN + 2 * c.pad) * c.cout * sizeof(float) + SEQ_LEN + 16;
                 int grid = std::min(B, 148 * 2);
-                onehot_conv_bwd_hist_kernel<T><<<grid, threads, smem, st>>>(e->last_bases, (const T*)c.dy, e->grads + c.w, B, c.cout, c.k, c.ld);
+                onehot_conv_bwd_lists_kernel<T><<<grid, threads, smem, st>>>(e->last_bases, (const T*)c.dy, e->grads + c.w, B, c.cout, c.k, c.ld);
             } else {
                 int grid = std::min(B, 148 * 4);
                 onehot_conv_bwd_kernel<T><<<grid, 256, 0, st>>>(e->last_bases, (const T*)c.dy, e->grads + c.w, nullptr, B, c.cout, c.k, c.ld);
@@ -890,7 +897,7 @@ int backward_impl(EmbEngine* e, const float* dlogits, cudaStream_t st) {
         if (rc) return rc;
         {
             Epilogue ep = base_epi(e, EPI_LINEAR, e->cnn.back().ga, e->cnn_Lp_last * e->cnn_ld_last);
-            ep.flatC = e->cnn_C_last; ep.flat_ldc = e->cnn_ld_last;
+            if (e->cnn_ld_last != e->cnn_C_last) { ep.flatC = e->cnn_C_last; ep.flat_ldc = e->cnn_ld_last; }   // dense rows need no remap
             rc = linear_dgrad(e, e->dock1, e->dd1.p, dt, e->dd1.ld, B, ep, st);
             if (rc) return rc;
         }
@@ -912,7 +919,7 @@ int backward_impl(EmbEngine* e, const float* dlogits, cudaStream_t st) {
             if (i) ep = base_epi(e, EPI_LINEAR, e->head_g[i - 1].p, e->head_g[i - 1].ld);
             else {
                 ep = base_epi(e, EPI_LINEAR, e->cnn.back().ga, e->cnn_Lp_last * e->cnn_ld_last);
-                ep.flatC = e->cnn_C_last; ep.flat_ldc = e->cnn_ld_last;
+                if (e->cnn_ld_last != e->cnn_C_last) { ep.flatC = e->cnn_C_last; ep.flat_ldc = e->cnn_ld_last; }   // dense rows need no remap
             }
             rc = linear_dgrad(e, e->head[i], g, g_dt, g_ld, B, ep, st);
             if (rc) return rc;
@@ -1051,8 +1058,10 @@ int emb_bind(EmbEngine* e, float* params, float* grads, float* buffers, float* o
     EMB_CUDA_OK(cudaMemset(e->rec_count, 0, sizeof(int)));
     cudaFuncSetAttribute(pool_bn_bwd_stage1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SEQ_LEN * 32 * 4);
     cudaFuncSetAttribute(pool_bn_bwd_stage1_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SEQ_LEN * 32 * 4);
-    cudaFuncSetAttribute(onehot_conv_bwd_hist_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEQ_LEN * 64 * 4 + 512);
-    cudaFuncSetAttribute(onehot_conv_bwd_hist_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEQ_LEN * 64 * 4 + 512);
+    cudaFuncSetAttribute(onehot_conv_bwd_lists_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (SEQ_LEN + 16) * 64 * 4 + 512);
+    cudaFuncSetAttribute(onehot_conv_bwd_lists_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (SEQ_LEN + 16) * 64 * 4 + 512);
+    cudaFuncSetAttribute(onehot_conv_fwd_pair_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 * 25 * 64 + 64 + 4096) * 4 + 512);
+    cudaFuncSetAttribute(onehot_conv_fwd_pair_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 * 25 * 64 + 64 + 4096) * 4 + 512);
     int rc = tc_init();
     if (rc) return rc;
     return EMB_OK;

@@ -602,7 +602,7 @@ inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int
         p.k_steps = 8;
         p.j_total = j_total;
         const int tiles = grid_m * grid_n * (conv ? pr.taps : 1);
-        int split = std::max(1, std::min(j_total, (148 * 2) / std::max(1, tiles)));
+        int split = std::max(1, std::min(j_total, tc_num_sms() / std::max(1, tiles)));   // one wave of CTAs: fewer atomics
         p.n_inner = cdiv(j_total, split);
         split = cdiv(j_total, p.n_inner);
         p.split_k = split;

@@ -175,32 +175,43 @@ bn_relu_pool_drop_fwd_stream_kernel(const T* __restrict__ y, const float* __rest
     T* dst = a + (size_t)b * Lp * ld + c;
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
     float2 w0 = make_float2(0.f, 0.f), w1 = w0, w2 = w0, w3 = w0;   // relu folded in: window values start at 0
-#pragma unroll 4
-    for (int i = 0; i < Lp + 4; ++i) {
-        float2 u0 = ld2(src + (size_t)(2 * i) * ld), u1 = ld2(src + (size_t)(2 * i + 1) * ld);
-        float2 m;
-        m.x = fmaxf(fmaxf(fmaf(u0.x, sc.x, sh.x), fmaf(u1.x, sc.x, sh.x)), 0.f);
-        m.y = fmaxf(fmaxf(fmaf(u0.y, sc.y, sh.y), fmaf(u1.y, sc.y, sh.y)), 0.f);
-        if (i >= 4) {
-            const int j = i - 4;
-            float2 r;
-            r.x = fmaxf(fmaxf(fmaxf(w0.x, w1.x), fmaxf(w2.x, w3.x)), m.x);
-            r.y = fmaxf(fmaxf(fmaxf(w0.y, w1.y), fmaxf(w2.y, w3.y)), m.y);
-            if (drop_p > 0.f) {
-                float ux, uy;
-                if (drop_u) {
-                    ux = drop_u[((size_t)b * C + c) * Lp + j];
-                    uy = drop_u[((size_t)b * C + c + 1) * Lp + j];
-                } else {
-                    ux = rng_uniform_f32(*rng, rng_stream, ((uint64_t)(row_offset + b) * C + c) * Lp + j);
-                    uy = rng_uniform_f32(*rng, rng_stream, ((uint64_t)(row_offset + b) * C + c + 1) * Lp + j);
-                }
-                r.x = (ux >= drop_p) ? r.x * inv_keep : 0.f;
-                r.y = (uy >= drop_p) ? r.y * inv_keep : 0.f;
-            }
-            st2(dst + (size_t)j * ld, r);
+    const int n_pairs = Lp + 4;
+    for (int i0 = 0; i0 < n_pairs; i0 += 4) {
+        // issue the loads of four position pairs before touching any of them (memory-level parallelism)
+        float2 u[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int row = 2 * i0 + q;
+            u[q] = (i0 + (q >> 1) < n_pairs) ? ld2(src + (size_t)row * ld) : make_float2(0.f, 0.f);
         }
-        w0 = w1; w1 = w2; w2 = w3; w3 = m;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q;
+            if (i >= n_pairs) break;
+            float2 m;
+            m.x = fmaxf(fmaxf(fmaf(u[2 * q].x, sc.x, sh.x), fmaf(u[2 * q + 1].x, sc.x, sh.x)), 0.f);
+            m.y = fmaxf(fmaxf(fmaf(u[2 * q].y, sc.y, sh.y), fmaf(u[2 * q + 1].y, sc.y, sh.y)), 0.f);
+            if (i >= 4) {
+                const int j = i - 4;
+                float2 r;
+                r.x = fmaxf(fmaxf(fmaxf(w0.x, w1.x), fmaxf(w2.x, w3.x)), m.x);
+                r.y = fmaxf(fmaxf(fmaxf(w0.y, w1.y), fmaxf(w2.y, w3.y)), m.y);
+                if (drop_p > 0.f) {
+                    float ux, uy;
+                    if (drop_u) {
+                        ux = drop_u[((size_t)b * C + c) * Lp + j];
+                        uy = drop_u[((size_t)b * C + c + 1) * Lp + j];
+                    } else {
+                        ux = rng_uniform_f32(*rng, rng_stream, ((uint64_t)(row_offset + b) * C + c) * Lp + j);
+                        uy = rng_uniform_f32(*rng, rng_stream, ((uint64_t)(row_offset + b) * C + c + 1) * Lp + j);
+                    }
+                    r.x = (ux >= drop_p) ? r.x * inv_keep : 0.f;
+                    r.y = (uy >= drop_p) ? r.y * inv_keep : 0.f;
+                }
+                st2(dst + (size_t)j * ld, r);
+            }
+            w0 = w1; w1 = w2; w2 = w3; w3 = m;
+        }
     }
 }
 
@@ -235,15 +246,39 @@ pool_bn_bwd_stream_kernel(const T* __restrict__ y, const T* __restrict__ a, cons
         float2 yr[10], dr[10];
 #pragma unroll
         for (int i = 0; i < 10; ++i) { yr[i] = make_float2(0.f, 0.f); dr[i] = make_float2(0.f, 0.f); }
-        // ring slot s holds position 2*(i-4) + s after pair i has been loaded
-        for (int i = 0; i < Lp + 4; ++i) {
-            yr[8] = ld2(ysrc + (size_t)(2 * i) * ld);
-            yr[9] = ld2(ysrc + (size_t)(2 * i + 1) * ld);
+        // ring slot s holds position 2*(i-4) + s after pair i has been loaded.  Operands are fetched PF pairs ahead
+        // (software pipeline: the loads of pair i+PF are in flight while pair i is processed).
+        constexpr int PF = 3;
+        float2 py0[PF], py1[PF], pa[PF], pg[PF];
+        const int n_pairs = Lp + 4;
+#pragma unroll
+        for (int q = 0; q < PF; ++q) {
+            py0[q] = ld2(ysrc + (size_t)(2 * q) * ld);
+            py1[q] = ld2(ysrc + (size_t)(2 * q + 1) * ld);
+            pa[q] = make_float2(0.f, 0.f);
+            pg[q] = make_float2(0.f, 0.f);          // windows -4..-2 do not exist
+        }
+        for (int i = 0; i < n_pairs; ++i) {
+            yr[8] = py0[0];
+            yr[9] = py1[0];
+            const float2 av = pa[0], gv = pg[0];
+#pragma unroll
+            for (int q = 0; q + 1 < PF; ++q) { py0[q] = py0[q + 1]; py1[q] = py1[q + 1]; pa[q] = pa[q + 1]; pg[q] = pg[q + 1]; }
+            {
+                const int ip = i + PF;
+                if (ip < n_pairs) {
+                    py0[PF - 1] = ld2(ysrc + (size_t)(2 * ip) * ld);
+                    py1[PF - 1] = ld2(ysrc + (size_t)(2 * ip + 1) * ld);
+                    if (ip >= 4) {
+                        pa[PF - 1] = ld2(asrc + (size_t)(ip - 4) * ld);
+                        pg[PF - 1] = ld2(gsrc + (size_t)(ip - 4) * ld);
+                    }
+                }
+            }
             dr[8] = make_float2(0.f, 0.f);
             dr[9] = make_float2(0.f, 0.f);
             if (i >= 4) {
                 const int j = i - 4;
-                float2 av = ld2(asrc + (size_t)j * ld), gv = ld2(gsrc + (size_t)j * ld);
                 if (av.x > 0.f) {      // kept by dropout and the window maximum was positive
                     int best = 0;
                     float bm = -INFINITY;
@@ -365,6 +400,211 @@ bn_stats_v2_kernel(const T* __restrict__ y, double* __restrict__ stats, int64_t 
 #pragma unroll
         for (int i = 0; i < 8; ++i) tot += s[threadIdx.y][i][threadIdx.x];
         atomicAdd(&stats[(threadIdx.y < 2 ? 0 : C) + 2 * cp + (threadIdx.y & 1)], tot);
+    }
+}
+
+// ---- eight-channel (16-byte) helpers ------------------------------------------------------------------------
+__device__ __forceinline__ void ld8(const float* p, float* v) {
+    float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const bf16* p, float* v) {
+    uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+}
+
+// K2 backward stage 2, eight channels (one 16-byte vector) per thread: block = (C/8 channel groups, rows)
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_v8_kernel(const T* __restrict__ y, T* __restrict__ dz, const double* __restrict__ bstats, const float* __restrict__ gamma,
+                       const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dbias, int64_t R, int C,
+                       int ld, double n) {
+    extern __shared__ float sred[];                 // [blockDim.y][C]
+    const int g = threadIdx.x, c0 = 8 * g;
+    float dbn[8], dgn[8], mu[8], rs[8], gs[8], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        dbn[i] = (float)(bstats[c0 + i] / n);
+        dgn[i] = (float)(bstats[C + c0 + i] / n);
+        mu[i] = mean[c0 + i];
+        rs[i] = rstd[c0 + i];
+        gs[i] = gamma[c0 + i] * rs[i];
+        acc[i] = 0.f;
+    }
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (int64_t)gridDim.x * blockDim.y) {
+        float yv[8], dv[8];
+        ld8(y + r * ld + c0, yv);
+        ld8(dz + r * ld + c0, dv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            dv[i] = gs[i] * (dv[i] - dbn[i] - (yv[i] - mu[i]) * rs[i] * dgn[i]);
+            acc[i] += dv[i];
+        }
+        st8(dz + r * ld + c0, dv);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sred[threadIdx.y * C + c0 + i] = acc[i];
+    __syncthreads();
+    for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < C; c += blockDim.x * blockDim.y) {
+        float t = 0.f;
+        for (int ry = 0; ry < (int)blockDim.y; ++ry) t += sred[ry * C + c];
+        atomicAdd(&dbias[c], t);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 forward with TAP-PAIR tables: two adjacent taps are looked up at once (5x5 base combinations incl. "outside"),
+// which halves the shared-memory reads and adds of the gather-sum.  tab2[(pair*25 + b0*5 + b1)*C1 + o].
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+onehot_conv_fwd_pair_kernel(const uint8_t* __restrict__ bases, const float* __restrict__ w, const float* __restrict__ bias,
+                            T* __restrict__ y, double* __restrict__ stats, int B, int C1, int k, int ld) {
+    extern __shared__ float smem[];
+    const int n_pairs = (k + 1) / 2;               // the last pair of an odd k has an empty second tap
+    float* tab = smem;                             // [n_pairs][25][C1]
+    float* sb = tab + n_pairs * 25 * C1;           // [C1]
+    float* red = sb + C1;                          // [256][16]
+    uint8_t* sbase = (uint8_t*)(red + 256 * 16);   // [256 + 2p + 1]
+    const int p = (k - 1) / 2;
+    const int groups = C1 / 8;
+    for (int i = threadIdx.x; i < n_pairs * 25 * C1; i += blockDim.x) {
+        const int o = i % C1, combo = (i / C1) % 25, pr = i / (25 * C1);
+        const int b0 = combo / 5, b1 = combo % 5, t0 = 2 * pr, t1 = 2 * pr + 1;
+        float v = 0.f;
+        if (b0 < 4) v += w[((size_t)o * 4 + b0) * k + t0];
+        if (b1 < 4 && t1 < k) v += w[((size_t)o * 4 + b1) * k + t1];
+        tab[i] = v;
+    }
+    for (int i = threadIdx.x; i < C1; i += blockDim.x) sb[i] = bias[i];
+    const int og = threadIdx.x % groups;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < SEQ_LEN + 2 * p + 1; i += blockDim.x) {
+            int l = i - p;
+            sbase[i] = (l >= 0 && l < SEQ_LEN) ? bases[(size_t)b * SEQ_LEN + l] : 4;
+        }
+        __syncthreads();
+        for (int item = threadIdx.x; item < SEQ_LEN * groups; item += 256) {
+            const int l = item / groups;
+            float acc[8];
+            const float4* b4 = reinterpret_cast<const float4*>(sb + og * 8);
+            float4 t0 = b4[0], t1 = b4[1];
+            acc[0] = t0.x; acc[1] = t0.y; acc[2] = t0.z; acc[3] = t0.w; acc[4] = t1.x; acc[5] = t1.y; acc[6] = t1.z; acc[7] = t1.w;
+            for (int pr = 0; pr < n_pairs; ++pr) {
+                const int combo = sbase[l + 2 * pr] * 5 + sbase[l + 2 * pr + 1];
+                const float4* r4 = reinterpret_cast<const float4*>(tab + (pr * 25 + combo) * C1 + og * 8);
+                float4 a0 = r4[0], a1 = r4[1];
+                acc[0] += a0.x; acc[1] += a0.y; acc[2] += a0.z; acc[3] += a0.w;
+                acc[4] += a1.x; acc[5] += a1.y; acc[6] += a1.z; acc[7] += a1.w;
+            }
+            st8(y + ((size_t)b * SEQ_LEN + l) * ld + og * 8, acc);
+            if (stats) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { float v = round_like<T>(acc[i]); s1[i] += v; s2[i] += v * v; }
+            }
+        }
+    }
+    if (stats) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { red[threadIdx.x * 16 + i] = s1[i]; red[threadIdx.x * 16 + 8 + i] = s2[i]; }
+        __syncthreads();
+        for (int i = threadIdx.x; i < groups * 16; i += blockDim.x) {
+            int g = i / 16, j = i - g * 16;
+            double tot = 0;
+            for (int t = g; t < 256; t += groups) tot += red[t * 16 + j];
+            int c = g * 8 + (j & 7);
+            atomicAdd(&stats[(j < 8 ? 0 : C1) + c], tot);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 backward with per-base position lists: the 256 positions of a sample are bucketed by base once (counting
+// sort in shared memory); thread (channel pair, tap) then walks the four lists with no branch and no bounds check
+// (the staged dy tile carries p zero rows on both sides).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024)
+onehot_conv_bwd_lists_kernel(const uint8_t* __restrict__ bases, const T* __restrict__ dy, float* __restrict__ dw, int B, int C1, int k, int ld) {
+    extern __shared__ float smem[];
+    const int p = (k - 1) / 2;
+    float* dys = smem;                                           // [256 + 2p][C1] fp32, rows shifted by p
+    uint8_t* plist = (uint8_t*)(dys + (SEQ_LEN + 2 * p) * C1);    // [256] positions grouped by base
+    __shared__ int cnt[4], start[5];
+    const int pairs = C1 / 2;
+    const int tap = threadIdx.x / pairs, op = threadIdx.x - tap * pairs;
+    const bool active = tap < k;
+    double d[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) d[i][c] = 0.0;
+    for (int i = threadIdx.x; i < p * C1; i += blockDim.x) { dys[i] = 0.f; dys[(SEQ_LEN + p) * C1 + i] = 0.f; }
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < 4) cnt[threadIdx.x] = 0;
+        for (int i = threadIdx.x; i < SEQ_LEN * pairs; i += blockDim.x) {
+            int l = i / pairs, o2 = i - l * pairs;
+            float2 v = ld2(dy + ((size_t)b * SEQ_LEN + l) * ld + 2 * o2);
+            *reinterpret_cast<float2*>(dys + (l + p) * C1 + 2 * o2) = v;
+        }
+        __syncthreads();
+        // counting sort of the positions by base (warp 0: ballot-based, keeps ascending position order per base)
+        if (threadIdx.x < 32) {
+            int base_cnt[4] = {0, 0, 0, 0};
+            uint8_t mine[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                mine[q] = bases[(size_t)b * SEQ_LEN + q * 32 + threadIdx.x];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) base_cnt[c] += __popc(__ballot_sync(0xffffffffu, mine[q] == c));
+            }
+            int st[5];
+            st[0] = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) st[c + 1] = st[c] + base_cnt[c];
+            if (threadIdx.x < 5) start[threadIdx.x] = st[threadIdx.x];
+            int run[4] = {st[0], st[1], st[2], st[3]};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    unsigned m = __ballot_sync(0xffffffffu, mine[q] == c);
+                    if (mine[q] == c) plist[run[c] + __popc(m & ((1u << threadIdx.x) - 1))] = (uint8_t)(q * 32 + threadIdx.x);
+                    run[c] += __popc(m);
+                }
+            }
+        }
+        __syncthreads();
+        if (active) {
+            // source position ls feeds output l = ls - tap + p, stored at row l + p = ls - tap + 2p of dys
+            const float* col = dys + (2 * p - tap) * C1 + 2 * op;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float a0 = 0.f, a1 = 0.f;
+                const int e = start[c + 1];
+                for (int i = start[c]; i < e; ++i) {
+                    const float2 v = *reinterpret_cast<const float2*>(col + (int)plist[i] * C1);
+                    a0 += v.x;
+                    a1 += v.y;
+                }
+                d[0][c] += a0;
+                d[1][c] += a1;
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) atomicAdd(&dw[((size_t)(2 * op + i) * 4 + c) * k + tap], (float)d[i][c]);
     }
 }
 
