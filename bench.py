@@ -147,7 +147,7 @@ def main():
     ap.add_argument('--batch', type=int, default=8192, help='GLOBAL batch')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--tensor-core', type=int, default=1)
-    ap.add_argument('--ref-batch', type=int, default=32, help='batch of the bounded CPU sample')
+    ap.add_argument('--ref-batch', type=int, default=256, help='batch of the bounded CPU sample')
     ap.add_argument('--cpu-baseline', type=int, default=1)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else max(args.warmup, 1)

@@ -18,6 +18,7 @@
 #include "kernels_fast.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "probe.cuh"
 
 namespace emb {
 
@@ -123,6 +124,7 @@ struct EmbEngine {
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
     double prof_flops = 0;
+    std::vector<double> prof_flops_each;
     int64_t prof_launches = 0;
 };
 
@@ -394,6 +396,7 @@ void prof_begin(EmbEngine* e, double flops, cudaStream_t st) {
     }
     cudaEventRecord(e->prof_ev[e->prof_used], st);
     e->prof_flops += flops;
+    e->prof_flops_each.push_back(flops);
     e->prof_launches += 1;
 }
 void prof_end(EmbEngine* e, cudaStream_t st) {
@@ -1125,6 +1128,7 @@ int emb_profile_gemm(EmbEngine* e, int32_t enable) {
     e->prof_on = enable != 0;
     e->prof_used = 0;
     e->prof_flops = 0;
+    e->prof_flops_each.clear();
     e->prof_launches = 0;
     return EMB_OK;
 }
@@ -1137,6 +1141,9 @@ int emb_profile_read(EmbEngine* e, double* ms_out, double* flops_out, int64_t* l
         float t = 0;
         EMB_CUDA_OK(cudaEventElapsedTime(&t, e->prof_ev[i], e->prof_ev[i + 1]));
         ms += t;
+        if (getenv("EMB_PROF_DUMP") && i / 2 < e->prof_flops_each.size())
+            fprintf(stderr, "gemm %3zu  %9.1f us  %8.2f GFLOP  %7.1f TFLOP/s\n", i / 2, t * 1e3, e->prof_flops_each[i / 2] / 1e9,
+                    e->prof_flops_each[i / 2] / (t * 1e-3) / 1e12);
     }
     if (ms_out) *ms_out = ms;
     if (flops_out) *flops_out = e->prof_flops;
@@ -1389,6 +1396,37 @@ int emb_k_gemm(int32_t kind, int32_t backend, const float* a, const float* b, fl
     cudaFree(b16);
     if (rc) return rc;
     if (serr != cudaSuccess) return set_error(EMB_E_CUDA, "emb_k_gemm: %s", cudaGetErrorString(serr));
+    return EMB_OK;
+}
+
+// test-only: UMMA descriptor row-shift probe (csrc/probe.cuh).  a, b fp32 host-visible device arrays:
+//   mode 0: a [144,64], b [64,64] -> out[128,64] = a[shift:shift+128] @ b^T
+//   mode 1: a [128,128] (k,m), b [144,64] (k,n) -> out[128,64] = sum_k a[k,m] * b[k+shift,n]
+int emb_k_umma_shift_probe(int32_t mode, int32_t shift, int32_t use_base_offset, const float* a, const float* b, float* out, void* stream) {
+    if (emb_device_count() < 1) return set_error(EMB_E_NO_DEVICE, "no sm_100 device");
+    int rc = tc_init();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t na = mode == 0 ? 144 * 64 : 128 * 128, nb = mode == 0 ? 64 * 64 : 144 * 64;
+    bf16 *a16, *b16;
+    EMB_CUDA_OK(cudaMalloc(&a16, na * 2));
+    EMB_CUDA_OK(cudaMalloc(&b16, nb * 2));
+    cast_f32_kernel<bf16><<<cdiv(na, 256), 256, 0, st>>>(a, a16, na);
+    cast_f32_kernel<bf16><<<cdiv(nb, 256), 256, 0, st>>>(b, b16, nb);
+    CUtensorMap ma, mb;
+    if (mode == 0) {
+        if ((rc = make_map(&ma, a16, 64, 144, 1, 64, 144 * 64, 64, 144, 1))) return rc;
+        if ((rc = make_map(&mb, b16, 64, 64, 1, 64, 64 * 64, 64, 64, 1))) return rc;
+    } else {
+        if ((rc = make_map(&ma, a16, 128, 128, 1, 128, 128 * 128, 64, 128, 1))) return rc;
+        if ((rc = make_map(&mb, b16, 64, 144, 1, 64, 144 * 64, 64, 144, 1))) return rc;
+    }
+    cudaFuncSetAttribute(umma_shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 70000);
+    umma_shift_probe_kernel<<<1, 128, 68000, st>>>(ma, mb, mode, shift, use_base_offset, out);
+    cudaError_t err = cudaStreamSynchronize(st);
+    cudaFree(a16);
+    cudaFree(b16);
+    if (err != cudaSuccess) return set_error(EMB_E_CUDA, "probe: %s", cudaGetErrorString(err));
     return EMB_OK;
 }
 

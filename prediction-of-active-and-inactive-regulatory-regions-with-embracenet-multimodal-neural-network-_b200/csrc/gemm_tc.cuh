@@ -97,6 +97,7 @@ struct TcOperand {
     int ctap[3], cj[3], ctile[3], cblk[3];
     int kstep_bytes;    // descriptor start-address advance per UMMA K step (16 elements)
     int lbo_bytes;
+    int dst_off;        // byte offset of the TMA destination inside a block (guard rows in front of a tap-shifted tile)
 };
 
 struct TcParams {
@@ -117,6 +118,10 @@ struct TcParams {
     uint32_t idesc;
     uint32_t tmem_cols;     // total allocation = 2 accumulator stages
     int acc_stride;         // TMEM columns per accumulator stage
+    int acc_stages;         // 2: epilogue of tile i overlaps the main loop of tile i+1; 1: all of TMEM is one tile's
+    int taps_per_cta;       // multi-tap wgrad: this many taps accumulate side by side in TMEM from ONE staged operand pair;
+                            // tap t reads the B tile through a descriptor shifted by (tap - pad) rows of 128 bytes
+    int tap_pad;
     int grid_m, grid_n, grid_z, total_tiles;
 };
 
@@ -331,13 +336,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         int c0 = p.a.base[0] + tap * p.a.ctap[0] + j * p.a.cj[0] + tile_m * p.a.ctile[0] + blk * p.a.cblk[0];
                         int c1 = p.a.base[1] + tap * p.a.ctap[1] + j * p.a.cj[1] + tile_m * p.a.ctile[1] + blk * p.a.cblk[1];
                         int c2 = p.a.base[2] + tap * p.a.ctap[2] + j * p.a.cj[2] + tile_m * p.a.ctile[2] + blk * p.a.cblk[2];
-                        tma_load_3d(sa + (size_t)blk * p.a.block_bytes, &map_a, &full_bar[stage], c0, c1, c2);
+                        tma_load_3d(sa + (size_t)blk * p.a.block_bytes + p.a.dst_off, &map_a, &full_bar[stage], c0, c1, c2);
                     }
                     for (int blk = 0; blk < p.b.boxes; ++blk) {
                         int c0 = p.b.base[0] + tap * p.b.ctap[0] + j * p.b.cj[0] + tile_n * p.b.ctile[0] + blk * p.b.cblk[0];
                         int c1 = p.b.base[1] + tap * p.b.ctap[1] + j * p.b.cj[1] + tile_n * p.b.ctile[1] + blk * p.b.cblk[1];
                         int c2 = p.b.base[2] + tap * p.b.ctap[2] + j * p.b.cj[2] + tile_n * p.b.ctile[2] + blk * p.b.cblk[2];
-                        tma_load_3d(sb + (size_t)blk * p.b.block_bytes, &map_b, &full_bar[stage], c0, c1, c2);
+                        tma_load_3d(sb + (size_t)blk * p.b.block_bytes + p.b.dst_off, &map_b, &full_bar[stage], c0, c1, c2);
                     }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -360,17 +365,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint32_t sb = sa + p.a.stage_bytes;
-                    for (int s = 0; s < p.k_steps; ++s) {
-                        uint64_t da = umma_desc(sa + s * p.a.kstep_bytes, p.a.lbo_bytes, 1024);
-                        uint64_t db = umma_desc(sb + s * p.b.kstep_bytes, p.b.lbo_bytes, 1024);
-                        tc_mma_f16(d_tmem, da, db, p.idesc, (it | s) ? 1u : 0u);
+                    if (p.taps_per_cta > 1) {
+                        // all taps of this CTA's group from one staged (dy, x) pair: x is read through row-shifted descriptors
+                        const int tap0 = tap_z * p.taps_per_cta;
+                        const int nt = min(p.taps_per_cta, p.n_taps - tap0);
+                        for (int t = 0; t < nt; ++t) {
+                            const uint32_t sbt = sb + p.b.dst_off + (tap0 + t - p.tap_pad) * 128;
+                            for (int s = 0; s < p.k_steps; ++s) {
+                                uint64_t da = umma_desc(sa + s * p.a.kstep_bytes, p.a.lbo_bytes, 1024);
+                                uint64_t db = umma_desc(sbt + s * p.b.kstep_bytes, p.b.lbo_bytes, 1024);
+                                tc_mma_f16(d_tmem + (uint32_t)(t * p.n_tile), da, db, p.idesc, (it | s) ? 1u : 0u);
+                            }
+                        }
+                    } else {
+                        for (int s = 0; s < p.k_steps; ++s) {
+                            uint64_t da = umma_desc(sa + s * p.a.kstep_bytes, p.a.lbo_bytes, 1024);
+                            uint64_t db = umma_desc(sb + s * p.b.kstep_bytes, p.b.lbo_bytes, 1024);
+                            tc_mma_f16(d_tmem, da, db, p.idesc, (it | s) ? 1u : 0u);
+                        }
                     }
                     tc_commit(&empty_bar[stage]);          // frees the smem stage when these MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&tfull_bar[acc]);                // accumulator complete
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -391,19 +409,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int m = (tile_m * p.groups_per_tile + grp) * p.rows_per_group + r_in;
             const bool row_ok = r_ok && (m < p.M);
             const int n_base = tile_n * p.n_tile;
-            const int n_off = p.tap_in_z ? tap_z * p.n_off_per_tap : 0;
+            const int tpc = p.taps_per_cta > 1 ? p.taps_per_cta : 1;
+            const int tap0 = p.tap_in_z ? tap_z * tpc : 0;
+            const int nt = p.tap_in_z ? min(tpc, p.n_taps - tap0) : 1;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
-            for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-                if (n_base + c0 >= p.N) break;                          // warp-uniform
-                float v[16];
-                tc_ld16(t_addr + (uint32_t)c0, v);
-                if (row_ok) tc_epilogue_row16(ep, m, n_base + c0, n_off, p.M, p.N, p.n_logical, v);
+            for (int t = 0; t < nt; ++t) {
+                const int n_off = p.tap_in_z ? (tap0 + t) * p.n_off_per_tap : 0;
+                for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+                    if (n_base + c0 >= p.N) break;                          // warp-uniform
+                    float v[16];
+                    tc_ld16(t_addr + (uint32_t)(t * p.n_tile + c0), v);
+                    if (row_ok) tc_epilogue_row16(ep, m, n_base + c0, n_off, p.M, p.N, p.n_logical, v);
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // accumulator may be overwritten
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
         }
     }
 #undef TC_DECODE_TILE
@@ -423,6 +445,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 inline EncodeTiledFn& encode_fn() { static EncodeTiledFn f = nullptr; return f; }
 inline int& tc_max_smem() { static int v = 0; return v; }
 inline int& tc_num_sms() { static int v = 148; return v; }
+// conv wgrad tiling (tunable for experiments): taps accumulated per CTA (<=1: one tap per CTA) and the N tile
+inline int tc_wgrad_taps() { static int v = getenv("EMB_WGRAD_TAPS") ? atoi(getenv("EMB_WGRAD_TAPS")) : 0; return v; }
+inline int tc_wgrad_ntile() { static int v = getenv("EMB_WGRAD_NT") ? atoi(getenv("EMB_WGRAD_NT")) : 128; return v; }
 
 inline int tc_init() {
     if (encode_fn()) return 0;
@@ -463,6 +488,11 @@ struct TcProblem {
     int M, N, K;                // linear: out[M,N] = A[M,K] B[N,K]^T (fwd); see per-kind notes
     int B, L, Cin, Cout, taps, pad;   // conv geometry (L = positions of both the conv input and output)
 };
+
+__host__ __device__ inline uint32_t make_idesc_dev(int a_mn, int b_mn, int n_tile) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a_mn ? 1 : 0) << 15) | ((uint32_t)(b_mn ? 1 : 0) << 16) |
+           ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
 
 inline uint32_t make_idesc(int a_mn, int b_mn, int n_tile) {
     uint32_t d = 0;
@@ -569,8 +599,9 @@ inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int
         grid_n = cdiv(N, n_tile);
         grid_m = cdiv(pr.M, 128);
         p.M = pr.M; p.N = N;
-        int rows_box, j_total;
-        if (conv) {
+        int rows_box, j_total, conv_tap_groups = 1;
+        (void)rows_box;
+        if (conv && tc_wgrad_taps() <= 1) {
             if (pr.L > 128) return set_error(-5, "conv GEMM: L > 128 not supported");
             const int bt = std::max(1, 128 / pr.L);
             rows_box = bt * pr.L;
@@ -586,6 +617,37 @@ inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int
             p.tap_in_z = 1; p.n_taps = pr.taps; p.n_off_per_tap = pr.Cin;
             p.n_logical = pr.taps * pr.Cin;
             p.zero_smem = rows_box < 128;
+            p.k_steps = 8;
+            conv_tap_groups = pr.taps;
+        } else if (conv) {
+            // Multi-tap wgrad: one CTA = (128 output channels) x (n_tile input channels) x (a group of up to 8 taps).
+            // Both operands are staged with their zero halo (rows l = -pad .. L+pad-1 of each sample, filled by TMA),
+            // so tap t is the SAME dy tile against the x tile shifted by (t - pad) rows: one descriptor offset, no reload.
+            const int S = pr.L + 2 * pr.pad;                 // rows per sample incl. halo
+            if (S > 256) return set_error(-5, "conv wgrad: L + 2*pad > 256 not supported");
+            const int bt = std::max(1, 160 / S);             // whole samples per K block
+            const int R = round_up(bt * S, 16);              // K rows per stage (rows beyond the box stay zero)
+            rows_box = bt * S;
+            j_total = cdiv(pr.B, bt);
+            const int nt_max = tc_wgrad_ntile();
+            n_tile = N <= nt_max ? round_up(N, 16) : nt_max;
+            grid_n = cdiv(N, n_tile);
+            rc = make_map(&ma, pr.a, pr.Cout, pr.L, pr.B, pr.lda, (int64_t)pr.L * pr.lda, 64, S, bt);
+            if (rc) return rc;
+            rc = make_map(&mb, pr.b, pr.Cin, pr.L, pr.B, pr.ldb, (int64_t)pr.L * pr.ldb, 64, S, bt);
+            if (rc) return rc;
+            mnmajor_operand(p.a, 128, rows_box, R);
+            mnmajor_operand(p.b, n_tile, rows_box, R + 16);   // 8 guard rows before and after the tile
+            p.b.dst_off = 1024;
+            p.a.ctile[0] = 128; p.a.cblk[0] = 64; p.a.cj[2] = bt; p.a.base[1] = -pr.pad;
+            p.b.ctile[0] = n_tile; p.b.cblk[0] = 64; p.b.cj[2] = bt; p.b.base[1] = -pr.pad;
+            p.taps_per_cta = std::max(1, std::min(std::min(pr.taps, tc_wgrad_taps()), 512 / n_tile));
+            p.tap_pad = pr.pad;
+            p.tap_in_z = 1; p.n_taps = pr.taps; p.n_off_per_tap = pr.Cin;
+            p.n_logical = pr.taps * pr.Cin;
+            p.zero_smem = 1;
+            p.k_steps = R / 16;
+            conv_tap_groups = cdiv(pr.taps, p.taps_per_cta);
         } else {
             rows_box = 128;
             j_total = cdiv(pr.K, 128);
@@ -599,19 +661,25 @@ inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int
             p.b.ctile[0] = n_tile; p.b.cblk[0] = 64; p.b.cj[1] = 128;
             p.n_taps = 1; p.n_logical = N;
         }
-        p.k_steps = 8;
+        if (!conv) p.k_steps = 8;
         p.j_total = j_total;
-        const int tiles = grid_m * grid_n * (conv ? pr.taps : 1);
+        const int tiles = grid_m * grid_n * (conv ? conv_tap_groups : 1);
         int split = std::max(1, std::min(j_total, tc_num_sms() / std::max(1, tiles)));   // one wave of CTAs: fewer atomics
         p.n_inner = cdiv(j_total, split);
         split = cdiv(j_total, p.n_inner);
         p.split_k = split;
-        grid_z = split * (conv ? pr.taps : 1);
+        grid_z = split * (conv ? conv_tap_groups : 1);
     }
     p.n_tile = n_tile;
     p.idesc = make_idesc(p.a.mn_major, p.b.mn_major, n_tile);
     p.acc_stride = n_tile <= 16 ? 16 : n_tile <= 32 ? 32 : n_tile <= 64 ? 64 : n_tile <= 128 ? 128 : 256;
-    p.tmem_cols = std::max(32, 2 * p.acc_stride);
+    p.acc_stages = 2;
+    if (p.taps_per_cta > 1) {
+        const int cols = p.taps_per_cta * n_tile;
+        p.acc_stride = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+        p.acc_stages = p.acc_stride <= 256 ? 2 : 1;
+    }
+    p.tmem_cols = std::max(32, p.acc_stages * p.acc_stride);
     p.grid_m = grid_m; p.grid_n = grid_n; p.grid_z = grid_z;
     p.total_tiles = grid_m * grid_n * grid_z;
     const int stage_bytes = p.a.stage_bytes + p.b.stage_bytes;

@@ -175,43 +175,32 @@ bn_relu_pool_drop_fwd_stream_kernel(const T* __restrict__ y, const float* __rest
     T* dst = a + (size_t)b * Lp * ld + c;
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
     float2 w0 = make_float2(0.f, 0.f), w1 = w0, w2 = w0, w3 = w0;   // relu folded in: window values start at 0
-    const int n_pairs = Lp + 4;
-    for (int i0 = 0; i0 < n_pairs; i0 += 4) {
-        // issue the loads of four position pairs before touching any of them (memory-level parallelism)
-        float2 u[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int row = 2 * i0 + q;
-            u[q] = (i0 + (q >> 1) < n_pairs) ? ld2(src + (size_t)row * ld) : make_float2(0.f, 0.f);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int i = i0 + q;
-            if (i >= n_pairs) break;
-            float2 m;
-            m.x = fmaxf(fmaxf(fmaf(u[2 * q].x, sc.x, sh.x), fmaf(u[2 * q + 1].x, sc.x, sh.x)), 0.f);
-            m.y = fmaxf(fmaxf(fmaf(u[2 * q].y, sc.y, sh.y), fmaf(u[2 * q + 1].y, sc.y, sh.y)), 0.f);
-            if (i >= 4) {
-                const int j = i - 4;
-                float2 r;
-                r.x = fmaxf(fmaxf(fmaxf(w0.x, w1.x), fmaxf(w2.x, w3.x)), m.x);
-                r.y = fmaxf(fmaxf(fmaxf(w0.y, w1.y), fmaxf(w2.y, w3.y)), m.y);
-                if (drop_p > 0.f) {
-                    float ux, uy;
-                    if (drop_u) {
-                        ux = drop_u[((size_t)b * C + c) * Lp + j];
-                        uy = drop_u[((size_t)b * C + c + 1) * Lp + j];
-                    } else {
-                        ux = rng_uniform_f32(*rng, rng_stream, ((uint64_t)(row_offset + b) * C + c) * Lp + j);
-                        uy = rng_uniform_f32(*rng, rng_stream, ((uint64_t)(row_offset + b) * C + c + 1) * Lp + j);
-                    }
-                    r.x = (ux >= drop_p) ? r.x * inv_keep : 0.f;
-                    r.y = (uy >= drop_p) ? r.y * inv_keep : 0.f;
+#pragma unroll 4
+    for (int i = 0; i < Lp + 4; ++i) {
+        float2 u0 = ld2(src + (size_t)(2 * i) * ld), u1 = ld2(src + (size_t)(2 * i + 1) * ld);
+        float2 m;
+        m.x = fmaxf(fmaxf(fmaf(u0.x, sc.x, sh.x), fmaf(u1.x, sc.x, sh.x)), 0.f);
+        m.y = fmaxf(fmaxf(fmaf(u0.y, sc.y, sh.y), fmaf(u1.y, sc.y, sh.y)), 0.f);
+        if (i >= 4) {
+            const int j = i - 4;
+            float2 r;
+            r.x = fmaxf(fmaxf(fmaxf(w0.x, w1.x), fmaxf(w2.x, w3.x)), m.x);
+            r.y = fmaxf(fmaxf(fmaxf(w0.y, w1.y), fmaxf(w2.y, w3.y)), m.y);
+            if (drop_p > 0.f) {
+                float ux, uy;
+                if (drop_u) {
+                    ux = drop_u[((size_t)b * C + c) * Lp + j];
+                    uy = drop_u[((size_t)b * C + c + 1) * Lp + j];
+                } else {
+                    ux = rng_uniform_f32(*rng, rng_stream, ((uint64_t)(row_offset + b) * C + c) * Lp + j);
+                    uy = rng_uniform_f32(*rng, rng_stream, ((uint64_t)(row_offset + b) * C + c + 1) * Lp + j);
                 }
-                st2(dst + (size_t)j * ld, r);
+                r.x = (ux >= drop_p) ? r.x * inv_keep : 0.f;
+                r.y = (uy >= drop_p) ? r.y * inv_keep : 0.f;
             }
-            w0 = w1; w1 = w2; w2 = w3; w3 = m;
+            st2(dst + (size_t)j * ld, r);
         }
+        w0 = w1; w1 = w2; w2 = w3; w3 = m;
     }
 }
 
@@ -246,39 +235,15 @@ pool_bn_bwd_stream_kernel(const T* __restrict__ y, const T* __restrict__ a, cons
         float2 yr[10], dr[10];
 #pragma unroll
         for (int i = 0; i < 10; ++i) { yr[i] = make_float2(0.f, 0.f); dr[i] = make_float2(0.f, 0.f); }
-        // ring slot s holds position 2*(i-4) + s after pair i has been loaded.  Operands are fetched PF pairs ahead
-        // (software pipeline: the loads of pair i+PF are in flight while pair i is processed).
-        constexpr int PF = 3;
-        float2 py0[PF], py1[PF], pa[PF], pg[PF];
-        const int n_pairs = Lp + 4;
-#pragma unroll
-        for (int q = 0; q < PF; ++q) {
-            py0[q] = ld2(ysrc + (size_t)(2 * q) * ld);
-            py1[q] = ld2(ysrc + (size_t)(2 * q + 1) * ld);
-            pa[q] = make_float2(0.f, 0.f);
-            pg[q] = make_float2(0.f, 0.f);          // windows -4..-2 do not exist
-        }
-        for (int i = 0; i < n_pairs; ++i) {
-            yr[8] = py0[0];
-            yr[9] = py1[0];
-            const float2 av = pa[0], gv = pg[0];
-#pragma unroll
-            for (int q = 0; q + 1 < PF; ++q) { py0[q] = py0[q + 1]; py1[q] = py1[q + 1]; pa[q] = pa[q + 1]; pg[q] = pg[q + 1]; }
-            {
-                const int ip = i + PF;
-                if (ip < n_pairs) {
-                    py0[PF - 1] = ld2(ysrc + (size_t)(2 * ip) * ld);
-                    py1[PF - 1] = ld2(ysrc + (size_t)(2 * ip + 1) * ld);
-                    if (ip >= 4) {
-                        pa[PF - 1] = ld2(asrc + (size_t)(ip - 4) * ld);
-                        pg[PF - 1] = ld2(gsrc + (size_t)(ip - 4) * ld);
-                    }
-                }
-            }
+        // ring slot s holds position 2*(i-4) + s after pair i has been loaded
+        for (int i = 0; i < Lp + 4; ++i) {
+            yr[8] = ld2(ysrc + (size_t)(2 * i) * ld);
+            yr[9] = ld2(ysrc + (size_t)(2 * i + 1) * ld);
             dr[8] = make_float2(0.f, 0.f);
             dr[9] = make_float2(0.f, 0.f);
             if (i >= 4) {
                 const int j = i - 4;
+                float2 av = ld2(asrc + (size_t)j * ld), gv = ld2(gsrc + (size_t)j * ld);
                 if (av.x > 0.f) {      // kept by dropout and the window maximum was positive
                     int best = 0;
                     float bm = -INFINITY;
