@@ -98,6 +98,16 @@ __device__ __forceinline__ double rng_uniform_f64(const RngState& s, uint32_t st
     return u32_to_unit_f64(rng_word(rng_raw(s, stream, elem >> 2), (uint32_t)elem & 3u));
 }
 
+// Dropout draws of the CNN stack ([B, C, Lpool] in the reference's layout): one Philox block serves the four pooled
+// positions j = 4q .. 4q+3 of a (row, channel), so a thread walking j refreshes its block every fourth step.
+__device__ __forceinline__ uint4 rng_cnn_block(const RngState& s, uint32_t stream, uint64_t global_row, int C, int c, int Lp, int jq) {
+    const uint64_t q_per_row = (uint64_t)((Lp + 3) >> 2);
+    return rng_raw(s, stream, (global_row * C + c) * q_per_row + jq);
+}
+__device__ __forceinline__ float rng_cnn_uniform(const RngState& s, uint32_t stream, uint64_t global_row, int C, int c, int Lp, int j) {
+    return u32_to_unit_f32(rng_word(rng_cnn_block(s, stream, global_row, C, c, Lp, j >> 2), (uint32_t)j & 3u));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -608,9 +608,16 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
         size_t total = (size_t)B * c.Lp * c.cout;
         float p = training ? c.drop : 0.f;
         const float* du = (dr && p > 0.f) ? dr->cnn_drop[i] : nullptr;
-        if (even)
-            bn_relu_pool_drop_fwd_stream_kernel<T><<<cdiv((size_t)B * (c.cout / 2), 256), 256, 0, st>>>(
-                (const T*)c.y, c.scale, c.shift, (T*)c.a, B, c.Lc, c.Lp, c.cout, c.ld, p, du, e->rng, RNG_CNN_DROP + (uint32_t)i, e->row_offset);
+        if (even) {
+            const int blocks = cdiv((size_t)B * (c.cout / 2), 256);
+#define EMB_K2_FWD(MODE)                                                                                                          \
+            bn_relu_pool_drop_fwd_stream_kernel<T, MODE><<<blocks, 256, 0, st>>>((const T*)c.y, c.scale, c.shift, (T*)c.a, B, c.Lc, c.Lp, \
+                                                                                c.cout, c.ld, p, du, e->rng, RNG_CNN_DROP + (uint32_t)i, e->row_offset)
+            if (p <= 0.f) EMB_K2_FWD(0);
+            else if (du) EMB_K2_FWD(1);
+            else EMB_K2_FWD(2);
+#undef EMB_K2_FWD
+        }
         else
             bn_relu_pool_drop_fwd_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)c.y, c.scale, c.shift, (T*)c.a, B, c.Lc, c.Lp, c.cout, c.ld,
                                                                                p, du, e->rng, RNG_CNN_DROP + (uint32_t)i, e->row_offset);

@@ -192,7 +192,7 @@ bn_relu_pool_drop_fwd_kernel(const T* __restrict__ y, const float* __restrict__ 
     if (drop_p > 0.f) {
         size_t ref_idx = ((size_t)b * C + c) * Lp + j;            // reference layout [B,C,Lp]
         float u = drop_u ? drop_u[ref_idx]
-                         : rng_uniform_f32(*rng, rng_stream, ((uint64_t)(row_offset + b) * C + c) * Lp + j);
+                         : rng_cnn_uniform(*rng, rng_stream, (uint64_t)(row_offset + b), C, c, Lp, j);
         m = (u >= drop_p) ? m / (1.f - drop_p) : 0.f;
     }
     a[((size_t)b * Lp + j) * ld + c] = from_f<T>(m);

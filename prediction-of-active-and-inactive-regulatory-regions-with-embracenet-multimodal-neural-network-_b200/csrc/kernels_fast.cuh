@@ -157,10 +157,12 @@ onehot_conv_bwd_hist_kernel(const uint8_t* __restrict__ bases, const T* __restri
 
 // ---------------------------------------------------------------------------------------------
 // K2 forward, streaming: thread = (sample, channel pair) walks the positions once.  MaxPool1d(10, 2) over
-// ReLU(BN(y)) is the max of 5 consecutive pair-maxima, kept in a 5-register window: every y element is read
-// exactly once (the generic kernel reads it 5 times through L1).  Requires C even.
+// ReLU(BN(y)) is the max of 5 consecutive pair-maxima, kept in a 4-register window: every y element is read
+// exactly once (the generic kernel reads it 5 times through L1).  Four position pairs (8 rows) are loaded per trip
+// before any is used, so each thread keeps 8 independent 4-byte loads in flight.  DROP: 0 none, 1 replayed
+// uniforms, 2 Philox.  Requires C even.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int DROP>
 __global__ void __launch_bounds__(256)
 bn_relu_pool_drop_fwd_stream_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                                     T* __restrict__ a, int B, int Lc, int Lp, int C, int ld, float drop_p,
@@ -173,11 +175,14 @@ bn_relu_pool_drop_fwd_stream_kernel(const T* __restrict__ y, const float* __rest
     const float2 sc = make_float2(scale[c], scale[c + 1]), sh = make_float2(shift[c], shift[c + 1]);
     const T* src = y + (size_t)b * Lc * ld + c;
     T* dst = a + (size_t)b * Lp * ld + c;
-    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const float inv_keep = DROP ? 1.f / (1.f - drop_p) : 1.f;
+    RngState rs = {0, 0};
+    if (DROP == 2) rs = *rng;
+    uint4 blk0 = make_uint4(0, 0, 0, 0), blk1 = blk0;        // current Philox blocks of the two channels
     float2 w0 = make_float2(0.f, 0.f), w1 = w0, w2 = w0, w3 = w0;   // relu folded in: window values start at 0
-#pragma unroll 4
-    for (int i = 0; i < Lp + 4; ++i) {
-        float2 u0 = ld2(src + (size_t)(2 * i) * ld), u1 = ld2(src + (size_t)(2 * i + 1) * ld);
+    const int n_pairs = Lp + 4;
+
+    auto step = [&](int i, float2 u0, float2 u1) {
         float2 m;
         m.x = fmaxf(fmaxf(fmaf(u0.x, sc.x, sh.x), fmaf(u1.x, sc.x, sh.x)), 0.f);
         m.y = fmaxf(fmaxf(fmaf(u0.y, sc.y, sh.y), fmaf(u1.y, sc.y, sh.y)), 0.f);
@@ -186,14 +191,18 @@ bn_relu_pool_drop_fwd_stream_kernel(const T* __restrict__ y, const float* __rest
             float2 r;
             r.x = fmaxf(fmaxf(fmaxf(w0.x, w1.x), fmaxf(w2.x, w3.x)), m.x);
             r.y = fmaxf(fmaxf(fmaxf(w0.y, w1.y), fmaxf(w2.y, w3.y)), m.y);
-            if (drop_p > 0.f) {
+            if (DROP) {
                 float ux, uy;
-                if (drop_u) {
+                if (DROP == 1) {
                     ux = drop_u[((size_t)b * C + c) * Lp + j];
                     uy = drop_u[((size_t)b * C + c + 1) * Lp + j];
                 } else {
-                    ux = rng_uniform_f32(*rng, rng_stream, ((uint64_t)(row_offset + b) * C + c) * Lp + j);
-                    uy = rng_uniform_f32(*rng, rng_stream, ((uint64_t)(row_offset + b) * C + c + 1) * Lp + j);
+                    if ((j & 3) == 0) {                       // uniform across the warp: every thread refreshes at the same j
+                        blk0 = rng_cnn_block(rs, rng_stream, (uint64_t)(row_offset + b), C, c, Lp, j >> 2);
+                        blk1 = rng_cnn_block(rs, rng_stream, (uint64_t)(row_offset + b), C, c + 1, Lp, j >> 2);
+                    }
+                    ux = u32_to_unit_f32(rng_word(blk0, (uint32_t)j & 3u));
+                    uy = u32_to_unit_f32(rng_word(blk1, (uint32_t)j & 3u));
                 }
                 r.x = (ux >= drop_p) ? r.x * inv_keep : 0.f;
                 r.y = (uy >= drop_p) ? r.y * inv_keep : 0.f;
@@ -201,7 +210,17 @@ bn_relu_pool_drop_fwd_stream_kernel(const T* __restrict__ y, const float* __rest
             st2(dst + (size_t)j * ld, r);
         }
         w0 = w1; w1 = w2; w2 = w3; w3 = m;
+    };
+
+    int i = 0;
+    for (; i + 4 <= n_pairs; i += 4) {
+        float2 u[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) u[q] = ld2(src + (size_t)(2 * i + q) * ld);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) step(i + q, u[2 * q], u[2 * q + 1]);
     }
+    for (; i < n_pairs; ++i) step(i, ld2(src + (size_t)(2 * i) * ld), ld2(src + (size_t)(2 * i + 1) * ld));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -236,14 +255,13 @@ pool_bn_bwd_stream_kernel(const T* __restrict__ y, const T* __restrict__ a, cons
 #pragma unroll
         for (int i = 0; i < 10; ++i) { yr[i] = make_float2(0.f, 0.f); dr[i] = make_float2(0.f, 0.f); }
         // ring slot s holds position 2*(i-4) + s after pair i has been loaded
-        for (int i = 0; i < Lp + 4; ++i) {
-            yr[8] = ld2(ysrc + (size_t)(2 * i) * ld);
-            yr[9] = ld2(ysrc + (size_t)(2 * i + 1) * ld);
+        auto step = [&](int i, float2 y0, float2 y1, float2 av, float2 gv) {
+            yr[8] = y0;
+            yr[9] = y1;
             dr[8] = make_float2(0.f, 0.f);
             dr[9] = make_float2(0.f, 0.f);
             if (i >= 4) {
                 const int j = i - 4;
-                float2 av = ld2(asrc + (size_t)j * ld), gv = ld2(gsrc + (size_t)j * ld);
                 if (av.x > 0.f) {      // kept by dropout and the window maximum was positive
                     int best = 0;
                     float bm = -INFINITY;
@@ -273,7 +291,22 @@ pool_bn_bwd_stream_kernel(const T* __restrict__ y, const T* __restrict__ a, cons
             }
 #pragma unroll
             for (int s = 0; s < 8; ++s) { yr[s] = yr[s + 2]; dr[s] = dr[s + 2]; }
+        };
+        const int n_pairs = Lp + 4;
+        const float2 zero2 = make_float2(0.f, 0.f);
+        int i = 0;
+        for (; i < 4 && i < n_pairs; ++i) step(i, ld2(ysrc + (size_t)(2 * i) * ld), ld2(ysrc + (size_t)(2 * i + 1) * ld), zero2, zero2);
+        for (; i + 2 <= n_pairs; i += 2) {
+            // all eight loads of two pairs are issued before the first is consumed
+            const float2 ya = ld2(ysrc + (size_t)(2 * i) * ld), yb = ld2(ysrc + (size_t)(2 * i + 1) * ld);
+            const float2 yc = ld2(ysrc + (size_t)(2 * i + 2) * ld), yd = ld2(ysrc + (size_t)(2 * i + 3) * ld);
+            const float2 a0 = ld2(asrc + (size_t)(i - 4) * ld), g0 = ld2(gsrc + (size_t)(i - 4) * ld);
+            const float2 a1 = ld2(asrc + (size_t)(i - 3) * ld), g1 = ld2(gsrc + (size_t)(i - 3) * ld);
+            step(i, ya, yb, a0, g0);
+            step(i + 1, yc, yd, a1, g1);
         }
+        for (; i < n_pairs; ++i)
+            step(i, ld2(ysrc + (size_t)(2 * i) * ld), ld2(ysrc + (size_t)(2 * i + 1) * ld), ld2(asrc + (size_t)(i - 4) * ld), ld2(gsrc + (size_t)(i - 4) * ld));
         // after the loop slots 0..7 hold positions 2*Lp .. 2*Lp+7; everything beyond was never inside a window
 #pragma unroll
         for (int s = 0; s < 8; ++s) {

@@ -225,12 +225,12 @@ def test_fused_train_step_and_host_entry():
     x, bases, y = make_inputs(spec, B, 8)
     eng = Engine(to_archspec(spec), max_batch=B, precision='fp32', tensor_core=False)
     eng.load_numpy(P)
-    cfg = eng.opt_config('adam', lr=1e-3, weight_decay=1e-4)
+    cfg = eng.opt_config('adam', lr=2e-3, weight_decay=1e-4)
     xs = np.ascontiguousarray(x.astype(np.float32))
     ys = np.ascontiguousarray(y.astype(np.int32))
-    losses = [eng.train_step_host(xs, bases, ys, cfg).loss for _ in range(12)]
+    losses = [eng.train_step_host(xs, bases, ys, cfg).loss for _ in range(40)]
     assert np.isfinite(losses).all()
-    assert min(losses[-3:]) < losses[0]
+    assert np.mean(losses[-8:]) < np.mean(losses[:8])        # stochastic (dropout, modality choice): compare averages
     probs = eng.predict_host(xs, bases)
     assert probs.shape == (B,) and np.isfinite(probs).all() and (probs >= 0).all() and (probs <= 1).all()
     assert eng.launch_count > 0
