@@ -320,37 +320,64 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
+            // The producer is ONE thread: its per-stage instruction count bounds small-tile GEMMs (measured ~900 cycles per
+            // stage with coordinates recomputed from the parameter block), so everything loop-invariant lives in
+            // registers and TMA coordinates advance by deltas.
             const uint32_t tx = (uint32_t)(p.a.boxes * p.a.box_bytes + p.b.boxes * p.b.box_bytes);
+            const int a_boxes = p.a.boxes, b_boxes = p.b.boxes;
+            const uint32_t a_block = p.a.block_bytes, b_block = p.b.block_bytes;
+            const int acj0 = p.a.cj[0], acj1 = p.a.cj[1], acj2 = p.a.cj[2], act0 = p.a.ctap[0], act1 = p.a.ctap[1], act2 = p.a.ctap[2];
+            const int bcj0 = p.b.cj[0], bcj1 = p.b.cj[1], bcj2 = p.b.cj[2], bct0 = p.b.ctap[0], bct1 = p.b.ctap[1], bct2 = p.b.ctap[2];
+            const int acb0 = p.a.cblk[0], acb1 = p.a.cblk[1], acb2 = p.a.cblk[2], bcb0 = p.b.cblk[0], bcb1 = p.b.cblk[1], bcb2 = p.b.cblk[2];
+            const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full_bar), a_stage = p.a.stage_bytes;
+            const uint32_t a_off = p.a.dst_off, b_off = p.b.dst_off;
+            const uint64_t ma = (uint64_t)&map_a, mb = (uint64_t)&map_b;
+            const int n_stages = p.stages;
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 TC_DECODE_TILE(t)
+                const int tap_first = p.tap_in_z ? tap_z : 0;
+                const int j_first = ks * p.n_inner;
+                int a0 = p.a.base[0] + tap_first * act0 + j_first * acj0 + tile_m * p.a.ctile[0];
+                int a1 = p.a.base[1] + tap_first * act1 + j_first * acj1 + tile_m * p.a.ctile[1];
+                int a2 = p.a.base[2] + tap_first * act2 + j_first * acj2 + tile_m * p.a.ctile[2];
+                int b0 = p.b.base[0] + tap_first * bct0 + j_first * bcj0 + tile_n * p.b.ctile[0];
+                int b1 = p.b.base[1] + tap_first * bct1 + j_first * bcj1 + tile_n * p.b.ctile[1];
+                int b2 = p.b.base[2] + tap_first * bct2 + j_first * bcj2 + tile_n * p.b.ctile[2];
+                int jj = 0;
                 for (int it = 0; it < n_iters; ++it) {
-                    const int tap = p.tap_in_z ? tap_z : it / n_inner;
-                    const int j = ks * p.n_inner + (p.tap_in_z ? it : it - tap * n_inner);
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], tx);
-                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                    uint8_t* sb = sa + p.a.stage_bytes;
-                    for (int blk = 0; blk < p.a.boxes; ++blk) {
-                        int c0 = p.a.base[0] + tap * p.a.ctap[0] + j * p.a.cj[0] + tile_m * p.a.ctile[0] + blk * p.a.cblk[0];
-                        int c1 = p.a.base[1] + tap * p.a.ctap[1] + j * p.a.cj[1] + tile_m * p.a.ctile[1] + blk * p.a.cblk[1];
-                        int c2 = p.a.base[2] + tap * p.a.ctap[2] + j * p.a.cj[2] + tile_m * p.a.ctile[2] + blk * p.a.cblk[2];
-                        tma_load_3d(sa + (size_t)blk * p.a.block_bytes + p.a.dst_off, &map_a, &full_bar[stage], c0, c1, c2);
+                    const uint32_t bar = full0 + 8u * stage;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+                    const uint32_t sa = smem0 + (uint32_t)stage * (uint32_t)stage_bytes + a_off;
+                    const uint32_t sb = smem0 + (uint32_t)stage * (uint32_t)stage_bytes + a_stage + b_off;
+                    for (int blk = 0; blk < a_boxes; ++blk)
+                        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                                     ::"r"(sa + blk * a_block), "l"(ma), "r"(bar), "r"(a0 + blk * acb0), "r"(a1 + blk * acb1), "r"(a2 + blk * acb2) : "memory");
+                    for (int blk = 0; blk < b_boxes; ++blk)
+                        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                                     ::"r"(sb + blk * b_block), "l"(mb), "r"(bar), "r"(b0 + blk * bcb0), "r"(b1 + blk * bcb1), "r"(b2 + blk * bcb2) : "memory");
+                    if (++jj == n_inner) {          // next tap: rewind the chunk coordinate, step the tap coordinate
+                        jj = 0;
+                        a0 += act0 - (n_inner - 1) * acj0; a1 += act1 - (n_inner - 1) * acj1; a2 += act2 - (n_inner - 1) * acj2;
+                        b0 += bct0 - (n_inner - 1) * bcj0; b1 += bct1 - (n_inner - 1) * bcj1; b2 += bct2 - (n_inner - 1) * bcj2;
+                    } else {
+                        a0 += acj0; a1 += acj1; a2 += acj2;
+                        b0 += bcj0; b1 += bcj1; b2 += bcj2;
                     }
-                    for (int blk = 0; blk < p.b.boxes; ++blk) {
-                        int c0 = p.b.base[0] + tap * p.b.ctap[0] + j * p.b.cj[0] + tile_n * p.b.ctile[0] + blk * p.b.cblk[0];
-                        int c1 = p.b.base[1] + tap * p.b.ctap[1] + j * p.b.cj[1] + tile_n * p.b.ctile[1] + blk * p.b.cblk[1];
-                        int c2 = p.b.base[2] + tap * p.b.ctap[2] + j * p.b.cj[2] + tile_n * p.b.ctile[2] + blk * p.b.cblk[2];
-                        tma_load_3d(sb + (size_t)blk * p.b.block_bytes + p.b.dst_off, &map_b, &full_bar[stage], c0, c1, c2);
-                    }
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
+            // single issuing thread: descriptors are (constant high part) + (start address >> 4); only the low word moves
+            const uint64_t da_hi = umma_desc(0, p.a.lbo_bytes, 1024), db_hi = umma_desc(0, p.b.lbo_bytes, 1024);
+            const uint32_t a_kstep = (uint32_t)p.a.kstep_bytes >> 4, b_kstep = (uint32_t)p.b.kstep_bytes >> 4;
+            const uint32_t smem0 = smem_u32(smem), a_stage = p.a.stage_bytes, idesc = p.idesc;
+            const int k_steps = p.k_steps, n_stages = p.stages, multi = p.taps_per_cta;
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -363,29 +390,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int it = 0; it < n_iters; ++it) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t sb = sa + p.a.stage_bytes;
-                    if (p.taps_per_cta > 1) {
+                    const uint32_t sa = smem0 + (uint32_t)stage * (uint32_t)stage_bytes;
+                    const uint32_t sb = sa + a_stage;
+                    if (multi > 1) {
                         // all taps of this CTA's group from one staged (dy, x) pair: x is read through row-shifted descriptors
-                        const int tap0 = tap_z * p.taps_per_cta;
-                        const int nt = min(p.taps_per_cta, p.n_taps - tap0);
-                        for (int t = 0; t < nt; ++t) {
-                            const uint32_t sbt = sb + p.b.dst_off + (tap0 + t - p.tap_pad) * 128;
-                            for (int s = 0; s < p.k_steps; ++s) {
-                                uint64_t da = umma_desc(sa + s * p.a.kstep_bytes, p.a.lbo_bytes, 1024);
-                                uint64_t db = umma_desc(sbt + s * p.b.kstep_bytes, p.b.lbo_bytes, 1024);
-                                tc_mma_f16(d_tmem + (uint32_t)(t * p.n_tile), da, db, p.idesc, (it | s) ? 1u : 0u);
-                            }
+                        const int tap0 = tap_z * multi;
+                        const int nt = min(multi, p.n_taps - tap0);
+                        for (int tt = 0; tt < nt; ++tt) {
+                            const uint64_t da0 = da_hi | (uint64_t)((sa & 0x3FFFFu) >> 4);
+                            const uint64_t db0 = db_hi | (uint64_t)(((sb + p.b.dst_off + (tap0 + tt - p.tap_pad) * 128) & 0x3FFFFu) >> 4);
+                            for (int s2 = 0; s2 < k_steps; ++s2)
+                                tc_mma_f16(d_tmem + (uint32_t)(tt * p.n_tile), da0 + (uint64_t)(s2 * a_kstep), db0 + (uint64_t)(s2 * b_kstep), idesc,
+                                           (it | s2) ? 1u : 0u);
                         }
                     } else {
-                        for (int s = 0; s < p.k_steps; ++s) {
-                            uint64_t da = umma_desc(sa + s * p.a.kstep_bytes, p.a.lbo_bytes, 1024);
-                            uint64_t db = umma_desc(sb + s * p.b.kstep_bytes, p.b.lbo_bytes, 1024);
-                            tc_mma_f16(d_tmem, da, db, p.idesc, (it | s) ? 1u : 0u);
-                        }
+                        const uint64_t da0 = da_hi | (uint64_t)((sa & 0x3FFFFu) >> 4);
+                        const uint64_t db0 = db_hi | (uint64_t)((sb & 0x3FFFFu) >> 4);
+                        tc_mma_f16(d_tmem, da0, db0, idesc, it ? 1u : 0u);
+#pragma unroll 4
+                        for (int s2 = 1; s2 < k_steps; ++s2)
+                            tc_mma_f16(d_tmem, da0 + (uint64_t)(s2 * a_kstep), db0 + (uint64_t)(s2 * b_kstep), idesc, 1u);
                     }
                     tc_commit(&empty_bar[stage]);          // frees the smem stage when these MMAs retire
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&tfull_bar[acc]);                // accumulator complete
                 if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
@@ -446,6 +473,7 @@ inline EncodeTiledFn& encode_fn() { static EncodeTiledFn f = nullptr; return f; 
 inline int& tc_max_smem() { static int v = 0; return v; }
 inline int& tc_num_sms() { static int v = 148; return v; }
 // conv wgrad tiling (tunable for experiments): taps accumulated per CTA (<=1: one tap per CTA) and the N tile
+inline int tc_min_kiters() { static int v = getenv("EMB_MIN_KITERS") ? atoi(getenv("EMB_MIN_KITERS")) : 8; return v; }
 inline int tc_wgrad_taps() { static int v = getenv("EMB_WGRAD_TAPS") ? atoi(getenv("EMB_WGRAD_TAPS")) : 0; return v; }
 inline int tc_wgrad_ntile() { static int v = getenv("EMB_WGRAD_NT") ? atoi(getenv("EMB_WGRAD_NT")) : 128; return v; }
 
@@ -664,7 +692,8 @@ inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int
         if (!conv) p.k_steps = 8;
         p.j_total = j_total;
         const int tiles = grid_m * grid_n * (conv ? conv_tap_groups : 1);
-        int split = std::max(1, std::min(j_total, tc_num_sms() / std::max(1, tiles)));   // one wave of CTAs: fewer atomics
+        // split-K: every split adds a full tile of fp32 atomics, so keep at least tc_min_kiters() K blocks per CTA
+        int split = std::max(1, std::min(std::max(1, j_total / tc_min_kiters()), tc_num_sms() / std::max(1, tiles)));
         p.n_inner = cdiv(j_total, split);
         split = cdiv(j_total, p.n_inner);
         p.split_k = split;
