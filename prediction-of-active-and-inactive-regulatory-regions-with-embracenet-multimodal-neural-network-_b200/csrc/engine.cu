@@ -18,6 +18,7 @@
 #include "kernels_fast.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "conv_tc.cuh"
 #include "probe.cuh"
 
 namespace emb {
@@ -423,7 +424,7 @@ int pick_split_k(int M, int N, int K) {
 
 int run_tc(EmbEngine* e, const TcProblem& pr, const Epilogue& ep, double flops, cudaStream_t st) {
     prof_begin(e, flops, st);
-    int rc = tc_gemm(pr, ep, st);
+    int rc = tc_dispatch(pr, ep, st);
     prof_end(e, st);
     if (rc) return rc;
     LAUNCHED(e);
@@ -1375,7 +1376,7 @@ int emb_k_gemm(int32_t kind, int32_t backend, const float* a, const float* b, fl
         else if (kind == 3) { pr.lda = Cin; pr.ldb = Cin; pr.M = B * L; pr.N = Cout; }
         else if (kind == 4) { pr.lda = Cout; pr.ldb = Cin; pr.M = B * L; pr.N = Cin; }
         else { pr.lda = Cout; pr.ldb = Cin; pr.M = Cout; pr.N = Cin; }
-        rc = tc_gemm(pr, ep, st);
+        rc = tc_dispatch(pr, ep, st);
     } else {
         Operand A, Bo;
         int gm, gn, gk, split = 1;

@@ -49,6 +49,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
+// cute::elect_one_sync(): exactly one lane of the (converged) warp gets a non-zero result
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, %1;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred) : "r"(0xFFFFFFFFu));
+    return pred;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
