@@ -296,7 +296,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     if (p.zero_smem) {
         uint4 z = make_uint4(0, 0, 0, 0);
@@ -382,51 +382,64 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            // single issuing thread: descriptors are (constant high part) + (start address >> 4); only the low word moves
-            const uint64_t da_hi = umma_desc(0, p.a.lbo_bytes, 1024), db_hi = umma_desc(0, p.b.lbo_bytes, 1024);
-            const uint32_t a_kstep = (uint32_t)p.a.kstep_bytes >> 4, b_kstep = (uint32_t)p.b.kstep_bytes >> 4;
-            const uint32_t smem0 = smem_u32(smem), a_stage = p.a.stage_bytes, idesc = p.idesc;
-            const int k_steps = p.k_steps, n_stages = p.stages, multi = p.taps_per_cta;
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                TC_DECODE_TILE(t)
-                (void)tile_n; (void)tile_m;
-                if (n_iters == 0) continue;
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
+        // The whole warp walks the loop (uniform control flow keeps the descriptors in uniform registers) and ONE elected
+        // lane issues: inside a divergent `if (lane == 0)` every tcgen05.mma cost an ELECT / R2UR / BRA.U.ANY waterfall
+        // (~25 SASS instructions, ~150 cycles), which made N <= 128 tiles issue-bound.
+        const uint64_t da_desc = umma_desc(0, p.a.lbo_bytes, 1024), db_desc = umma_desc(0, p.b.lbo_bytes, 1024);
+        const uint32_t da_hi = (uint32_t)(da_desc >> 32), db_hi = (uint32_t)(db_desc >> 32);
+        const uint32_t da_lbo = (uint32_t)da_desc, db_lbo = (uint32_t)db_desc;         // LBO field, bits 16-29
+        const uint32_t a_kstep = (uint32_t)p.a.kstep_bytes >> 4, b_kstep = (uint32_t)p.b.kstep_bytes >> 4;
+        const uint32_t smem0 = smem_u32(smem), a_stage = p.a.stage_bytes, idesc = p.idesc;
+        const int k_steps = p.k_steps, n_stages = p.stages, multi = p.taps_per_cta;
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            TC_DECODE_TILE(t)
+            (void)tile_n; (void)tile_m;
+            if (n_iters == 0) continue;
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+            for (int it = 0; it < n_iters; ++it) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
-                for (int it = 0; it < n_iters; ++it) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem0 + (uint32_t)stage * (uint32_t)stage_bytes;
-                    const uint32_t sb = sa + a_stage;
+                const uint32_t sa = smem0 + (uint32_t)stage * (uint32_t)stage_bytes;
+                const uint32_t sb = sa + a_stage;
+                if (elect_one_sync()) {
                     if (multi > 1) {
                         // all taps of this CTA's group from one staged (dy, x) pair: x is read through row-shifted descriptors
                         const int tap0 = tap_z * multi;
                         const int nt = min(multi, p.n_taps - tap0);
+                        const uint64_t da0 = ((uint64_t)da_hi << 32) | (da_lbo | ((sa & 0x3FFFFu) >> 4));
                         for (int tt = 0; tt < nt; ++tt) {
-                            const uint64_t da0 = da_hi | (uint64_t)((sa & 0x3FFFFu) >> 4);
-                            const uint64_t db0 = db_hi | (uint64_t)(((sb + p.b.dst_off + (tap0 + tt - p.tap_pad) * 128) & 0x3FFFFu) >> 4);
+                            const uint32_t sbt = sb + p.b.dst_off + (uint32_t)((tap0 + tt - p.tap_pad) * 128);
+                            const uint64_t db0 = ((uint64_t)db_hi << 32) | (db_lbo | ((sbt & 0x3FFFFu) >> 4));
+                            const uint32_t d_t = d_tmem + (uint32_t)(tt * p.n_tile);
                             for (int s2 = 0; s2 < k_steps; ++s2)
-                                tc_mma_f16(d_tmem + (uint32_t)(tt * p.n_tile), da0 + (uint64_t)(s2 * a_kstep), db0 + (uint64_t)(s2 * b_kstep), idesc,
-                                           (it | s2) ? 1u : 0u);
+                                tc_mma_f16(d_t, da0 + (uint64_t)(s2 * a_kstep), db0 + (uint64_t)(s2 * b_kstep), idesc, (it | s2) ? 1u : 0u);
                         }
                     } else {
-                        const uint64_t da0 = da_hi | (uint64_t)((sa & 0x3FFFFu) >> 4);
-                        const uint64_t db0 = db_hi | (uint64_t)((sb & 0x3FFFFu) >> 4);
+                        const uint64_t da0 = ((uint64_t)da_hi << 32) | (da_lbo | ((sa & 0x3FFFFu) >> 4));
+                        const uint64_t db0 = ((uint64_t)db_hi << 32) | (db_lbo | ((sb & 0x3FFFFu) >> 4));
                         tc_mma_f16(d_tmem, da0, db0, idesc, it ? 1u : 0u);
+                        if (k_steps == 4) {
+                            tc_mma_f16(d_tmem, da0 + a_kstep, db0 + b_kstep, idesc, 1u);
+                            tc_mma_f16(d_tmem, da0 + 2 * a_kstep, db0 + 2 * b_kstep, idesc, 1u);
+                            tc_mma_f16(d_tmem, da0 + 3 * a_kstep, db0 + 3 * b_kstep, idesc, 1u);
+                        } else {
 #pragma unroll 4
-                        for (int s2 = 1; s2 < k_steps; ++s2)
-                            tc_mma_f16(d_tmem, da0 + (uint64_t)(s2 * a_kstep), db0 + (uint64_t)(s2 * b_kstep), idesc, 1u);
+                            for (int s2 = 1; s2 < k_steps; ++s2)
+                                tc_mma_f16(d_tmem, da0 + (uint64_t)(s2 * a_kstep), db0 + (uint64_t)(s2 * b_kstep), idesc, 1u);
+                        }
                     }
                     tc_commit(&empty_bar[stage]);          // frees the smem stage when these MMAs retire
-                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tfull_bar[acc]);                // accumulator complete
-                if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
+            if (elect_one_sync()) tc_commit(&tfull_bar[acc]);                // accumulator complete
+            __syncwarp();
+            if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ================= epilogue (warps 2..5 own TMEM lane quarters warp%4) =================
