@@ -229,6 +229,10 @@ int emb_k_onehot_conv_bwd(const uint8_t* bases, const void* dy, int32_t B, int32
 int emb_k_gemm(int32_t kind, int32_t backend, const float* a, const float* b, float* out, int32_t M, int32_t N, int32_t K,
                int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t taps, void* stream);
 
+/* the same GEMM launched `reps` times (first = warm-up); *ms_out = average device milliseconds per launch (kernel tuning) */
+int emb_k_gemm_time(int32_t kind, int32_t backend, const float* a, const float* b, float* out, int32_t M, int32_t N, int32_t K,
+                    int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t taps, int32_t reps, float* ms_out, void* stream);
+
 /* test-only hardware probe: UMMA shared-memory descriptors with a start address shifted by whole 128-byte rows
  * (csrc/probe.cuh); decides how multi-tap convolution tiles may be addressed. */
 int emb_k_umma_shift_probe(int32_t mode, int32_t shift, int32_t use_base_offset, const float* a, const float* b, float* out, void* stream);

@@ -58,6 +58,7 @@ struct ConvLayer {
     int64_t rm, rv;              // buffers arena
     float drop;
     bf16* wc;                    // bf16 operand copy [k][cout][round_up(cin,8)]
+    float* wg_tmp;               // weight gradient accumulated as [k][cout][cin] (coalesced atomics) before the permuted write-back
     // workspace
     void *y, *a, *dy, *ga;
     float *scale, *shift, *mean, *rstd;
@@ -274,6 +275,16 @@ __global__ void unpermute_wgrad_kernel(const float* __restrict__ tmp, float* __r
     dw[i] = tmp[n * K + (size_t)l * C + c];
 }
 
+// dW[o][c][tap] = tmp[tap][o][c]: the conv weight gradient back to the reference's [Cout, Cin, k] layout
+__global__ void unpermute_conv_wgrad_kernel(const float* __restrict__ tmp, float* __restrict__ dw, int Cout, int Cin, int taps) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t oc = (size_t)Cout * Cin;
+    if (i >= oc * taps) return;
+    const size_t r = i / taps;                           // (o, c); destination index walks the reference layout
+    const int tap = (int)(i - r * taps);
+    dw[i] = tmp[(size_t)tap * oc + r];
+}
+
 // carve the workspace; with base == nullptr only the size is computed
 int64_t carve(EmbEngine* e, char* base) {
     Bump bp{base};
@@ -301,7 +312,10 @@ int64_t carve(EmbEngine* e, char* base) {
         for (auto& l : e->post) wl(l);
         for (auto& l : e->head) wl(l);
         if (s.kind == EMB_KIND_EMBRACENET) { wl(e->dock0); wl(e->dock1); }
-        for (size_t i = 1; i < e->cnn.size(); ++i) e->cnn[i].wc = bp.take<bf16>((int64_t)e->cnn[i].k * e->cnn[i].cout * round_up(e->cnn[i].cin, 8));
+        for (size_t i = 1; i < e->cnn.size(); ++i) {
+            e->cnn[i].wc = bp.take<bf16>((int64_t)e->cnn[i].k * e->cnn[i].cout * round_up(e->cnn[i].cin, 8));
+            e->cnn[i].wg_tmp = bp.take<float>((int64_t)e->cnn[i].k * e->cnn[i].cout * e->cnn[i].cin);
+        }
     }
     if (s.kind != EMB_KIND_CNN) {
         e->x0 = take_act(bp, Bm, s.in_features, es);
@@ -713,7 +727,16 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
                 TcProblem tp = {};
                 tp.kind = TC_CONV_WGRAD; tp.a = (const bf16*)c.dy; tp.lda = c.ld; tp.b = (const bf16*)pr.a; tp.ldb = pr.ld;
                 tp.M = c.cout; tp.N = c.cin; tp.B = B; tp.L = c.Lc; tp.Cin = c.cin; tp.Cout = c.cout; tp.taps = c.k; tp.pad = c.pad;
-                rc = run_tc(e, tp, ep, flops, st);
+                // accumulate as [tap][Cout][Cin] (coalesced atomics), then one permuted write-back into the gradient arena
+                const size_t wn = (size_t)c.k * c.cout * c.cin;
+                EMB_CUDA_OK(cudaMemsetAsync(c.wg_tmp, 0, wn * sizeof(float), st));
+                tp.wgrad_tap_stride = c.cout * c.cin;
+                Epilogue et = base_epi(e, EPI_ATOMIC, c.wg_tmp, c.cin);
+                rc = run_tc(e, tp, et, flops, st);
+                if (rc) return rc;
+                unpermute_conv_wgrad_kernel<<<cdiv(wn, 256), 256, 0, st>>>(c.wg_tmp, e->grads + c.w, c.cout, c.cin, c.k);
+                EMB_CHECK_LAUNCH();
+                LAUNCHED(e);
             } else {
                 rc = run_gemm(e, A, X, ep, c.cout, c.k * c.cin, (int)R, pick_split_k(c.cout, c.k * c.cin, (int)R), st);
             }
@@ -1332,8 +1355,8 @@ int emb_k_onehot_conv_bwd(const uint8_t* bases, const void* dy, int32_t B, int32
 //   1 linear dgrad a[M,K] b[K,N]            -> out[M,N]        4 conv dgrad a[B,L,Cout] b = W[Cout,Cin,taps] -> out[B*L,Cin]
 //   2 linear wgrad a[K,M] b[K,N]            -> out[M,N]        5 conv wgrad a[B,L,Cout] b = act[B,L,Cin]     -> out = dW[Cout,Cin,taps]
 // (all inner widths must be multiples of 8).  Synchronises the stream.
-int emb_k_gemm(int32_t kind, int32_t backend, const float* a, const float* b, float* out, int32_t M, int32_t N, int32_t K,
-               int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t taps, void* stream) {
+static int k_gemm_impl(int32_t kind, int32_t backend, const float* a, const float* b, float* out, int32_t M, int32_t N, int32_t K,
+                       int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t taps, void* stream, int reps, float* ms_out) {
     if (emb_device_count() < 1) return set_error(EMB_E_NO_DEVICE, "no sm_100 device");
     cudaStream_t st = (cudaStream_t)stream;
     const bool conv = kind >= 3;
@@ -1366,6 +1389,10 @@ int emb_k_gemm(int32_t kind, int32_t backend, const float* a, const float* b, fl
         ep.ldo = kind == 3 ? Cout : kind == 4 ? Cin : N;
     }
     int rc = EMB_OK;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ms_out) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); }
+    for (int rep = 0; rep < reps && rc == EMB_OK; ++rep) {
+    if (ms_out && rep == 1) cudaEventRecord(ev0, st);      // rep 0 is the warm-up
     if (backend == 1) {
         TcProblem pr = {};
         pr.kind = kind; pr.a = a16; pr.b = b16;
@@ -1399,12 +1426,33 @@ int emb_k_gemm(int32_t kind, int32_t backend, const float* a, const float* b, fl
         cudaError_t err = launch_gemm_simt(A, Bo, ep, gm, gn, gk, split, st);
         if (err != cudaSuccess) rc = set_error(EMB_E_CUDA, "gemm launch: %s", cudaGetErrorString(err));
     }
+    }
+    if (ms_out) cudaEventRecord(ev1, st);
     cudaError_t serr = cudaStreamSynchronize(st);
+    if (ms_out) {
+        float ms = 0.f;
+        if (serr == cudaSuccess && reps > 1) cudaEventElapsedTime(&ms, ev0, ev1);
+        *ms_out = reps > 1 ? ms / (reps - 1) : 0.f;
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    }
     cudaFree(a16);
     cudaFree(b16);
     if (rc) return rc;
     if (serr != cudaSuccess) return set_error(EMB_E_CUDA, "emb_k_gemm: %s", cudaGetErrorString(serr));
     return EMB_OK;
+}
+
+int emb_k_gemm(int32_t kind, int32_t backend, const float* a, const float* b, float* out, int32_t M, int32_t N, int32_t K,
+               int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t taps, void* stream) {
+    return k_gemm_impl(kind, backend, a, b, out, M, N, K, B, L, Cin, Cout, taps, stream, 1, nullptr);
+}
+
+// the same launch repeated `reps` times (the first is a warm-up), average device time per launch in *ms_out
+// (CUDA events on `stream`); wgrad kinds keep accumulating into `out`, which is only meaningful for reps == 1
+int emb_k_gemm_time(int32_t kind, int32_t backend, const float* a, const float* b, float* out, int32_t M, int32_t N, int32_t K,
+                    int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t taps, int32_t reps, float* ms_out, void* stream) {
+    if (reps < 2 || !ms_out) return set_error(EMB_E_ARG, "reps >= 2 and ms_out required");
+    return k_gemm_impl(kind, backend, a, b, out, M, N, K, B, L, Cin, Cout, taps, stream, reps, ms_out);
 }
 
 // test-only: UMMA descriptor row-shift probe (csrc/probe.cuh).  a, b fp32 host-visible device arrays:

@@ -295,6 +295,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* tfull_bar = empty_bar + TC_MAX_STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+    float* epi_scratch = (float*)((uint8_t*)full_bar + 256);      // [4 warps][32][33] transpose tiles of the atomic epilogue
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
@@ -463,8 +464,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int tap0 = p.tap_in_z ? tap_z * tpc : 0;
             const int nt = p.tap_in_z ? min(tpc, p.n_taps - tap0) : 1;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+            const bool coalesced_atomics = ep.mode == EPI_ATOMIC && ep.map == MAP_ROWMAJOR && p.rows_per_group == 128;
             for (int t = 0; t < nt; ++t) {
                 const int n_off = p.tap_in_z ? (tap0 + t) * p.n_off_per_tap : 0;
+                if (coalesced_atomics) {
+                    // Split-K / wgrad accumulation.  A thread owns one output ROW of the accumulator, so a direct atomicAdd makes
+                    // every warp instruction touch 32 different rows (32 L2 transactions; measured ~45 us per 128 x 128 tile,
+                    // independent of K).  The 32 x 32 block is transposed through shared memory instead, so that one
+                    // instruction adds 32 consecutive columns of one row: a single 128-byte transaction.
+                    float* sc = epi_scratch + q * (32 * 33);
+                    const int m0 = tile_m * 128 + q * 32;
+                    for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+                        if (n_base + c0 >= p.N) break;                      // warp-uniform
+                        float v[32];
+                        tc_ld16(t_addr + (uint32_t)(t * p.n_tile + c0), v);
+                        if (c0 + 16 < p.n_tile) tc_ld16(t_addr + (uint32_t)(t * p.n_tile + c0 + 16), v + 16);
+                        else {
+#pragma unroll
+                            for (int i = 16; i < 32; ++i) v[i] = 0.f;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sc[lane * 33 + i] = v[i];
+                        __syncwarp();
+                        const int n = n_base + c0 + lane;
+                        const bool n_ok = n < p.N && c0 + lane < p.n_tile;
+                        float* dst = (float*)ep.out + (size_t)m0 * ep.ldo + n_off + n;
+                        const int rows = min(32, p.M - m0);
+                        for (int rr = 0; rr < rows; ++rr)
+                            if (n_ok) atomicAdd(dst + (size_t)rr * ep.ldo, sc[rr * 33 + lane]);
+                        __syncwarp();
+                    }
+                    continue;
+                }
                 for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
                     if (n_base + c0 >= p.N) break;                          // warp-uniform
                     float v[16];
@@ -538,6 +569,7 @@ struct TcProblem {
     const bf16* b; int ldb;
     int M, N, K;                // linear: out[M,N] = A[M,K] B[N,K]^T (fwd); see per-kind notes
     int B, L, Cin, Cout, taps, pad;   // conv geometry (L = positions of both the conv input and output)
+    int wgrad_tap_stride;             // TC_CONV_WGRAD: > 0 -> the target is [taps][Cout][Cin] (coalesced atomics), else dW[Cout][Cin][taps] via ep.map
 };
 
 __host__ __device__ inline uint32_t make_idesc_dev(int a_mn, int b_mn, int n_tile) {
@@ -665,7 +697,7 @@ inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int
             mnmajor_operand(p.b, n_tile, rows_box, 128);
             p.a.ctile[0] = 128; p.a.cblk[0] = 64; p.a.cj[2] = bt;
             p.b.ctile[0] = n_tile; p.b.cblk[0] = 64; p.b.cj[2] = bt; p.b.base[1] = -pr.pad; p.b.ctap[1] = 1;
-            p.tap_in_z = 1; p.n_taps = pr.taps; p.n_off_per_tap = pr.Cin;
+            p.tap_in_z = 1; p.n_taps = pr.taps; p.n_off_per_tap = pr.wgrad_tap_stride > 0 ? pr.wgrad_tap_stride : pr.Cin;
             p.n_logical = pr.taps * pr.Cin;
             p.zero_smem = rows_box < 128;
             p.k_steps = 8;
@@ -694,7 +726,7 @@ inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int
             p.b.ctile[0] = n_tile; p.b.cblk[0] = 64; p.b.cj[2] = bt; p.b.base[1] = -pr.pad;
             p.taps_per_cta = std::max(1, std::min(std::min(pr.taps, tc_wgrad_taps()), 512 / n_tile));
             p.tap_pad = pr.pad;
-            p.tap_in_z = 1; p.n_taps = pr.taps; p.n_off_per_tap = pr.Cin;
+            p.tap_in_z = 1; p.n_taps = pr.taps; p.n_off_per_tap = pr.wgrad_tap_stride > 0 ? pr.wgrad_tap_stride : pr.Cin;
             p.n_logical = pr.taps * pr.Cin;
             p.zero_smem = 1;
             p.k_steps = R / 16;
@@ -735,10 +767,11 @@ inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int
     p.grid_m = grid_m; p.grid_n = grid_n; p.grid_z = grid_z;
     p.total_tiles = grid_m * grid_n * grid_z;
     const int stage_bytes = p.a.stage_bytes + p.b.stage_bytes;
-    const int budget = tc_max_smem() - 2048;
+    const int epi_scratch_bytes = 4 * 32 * 33 * 4;
+    const int budget = tc_max_smem() - 2048 - epi_scratch_bytes;
     p.stages = std::min(TC_MAX_STAGES, budget / stage_bytes);
     if (p.stages < 2) return set_error(-5, "tc_gemm: stage of %d bytes does not fit twice in shared memory", stage_bytes);
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256 + epi_scratch_bytes;
     const int grid = std::min(p.total_tiles, tc_num_sms());
     tc_gemm_kernel<<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep);
     cudaError_t err = cudaGetLastError();
