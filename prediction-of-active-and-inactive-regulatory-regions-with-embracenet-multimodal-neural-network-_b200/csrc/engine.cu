@@ -10,12 +10,14 @@
 #include <cstring>
 #include <cmath>
 #include <vector>
+#include <type_traits>
 #include <string>
 
 #include "../../include/embrace_b200.h"
 #include "common.cuh"
 #include "kernels.cuh"
 #include "kernels_fast.cuh"
+#include "kernels_tma.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "conv_tc.cuh"
@@ -623,7 +625,19 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
         size_t total = (size_t)B * c.Lp * c.cout;
         float p = training ? c.drop : 0.f;
         const float* du = (dr && p > 0.f) ? dr->cnn_drop[i] : nullptr;
-        if (even) {
+        const bool kt = std::is_same<T, bf16>::value && kt_ok(c.cout, c.ld) && !du && kt_fwd_smem(c.Lc, c.cout) <= (size_t)kt_max_smem() &&
+                        getenv("EMB_TMA_K2_FWD");     // instruction-bound on the Philox draws either way: the streaming kernel is faster
+        if (kt) {
+            // whole samples staged by bulk copies two ahead of the arithmetic (kernels_tma.cuh)
+            PoolFwdArgs a = {};
+            a.y = (const bf16*)c.y; a.scale = c.scale; a.shift = c.shift; a.a = (bf16*)c.a; a.rng = e->rng; a.row_offset = e->row_offset;
+            a.rng_stream = RNG_CNN_DROP + (uint32_t)i; a.B = B; a.Lc = c.Lc; a.Lp = c.Lp; a.C = c.cout; a.drop_p = p;
+            kt_segments(c.cout, c.Lp, 4, &a.nseg, &a.P);
+            const size_t smem = kt_fwd_smem(c.Lc, c.cout);
+            const int grid = std::min(B, tc_num_sms() * kt_ctas_per_sm(smem, 4));
+            if (p > 0.f) bn_relu_pool_drop_fwd_tma_kernel<2><<<grid, KT_THREADS, smem, st>>>(a);
+            else bn_relu_pool_drop_fwd_tma_kernel<0><<<grid, KT_THREADS, smem, st>>>(a);
+        } else if (even) {
             const int blocks = cdiv((size_t)B * (c.cout / 2), 256);
 #define EMB_K2_FWD(MODE)                                                                                                          \
             bn_relu_pool_drop_fwd_stream_kernel<T, MODE><<<blocks, 256, 0, st>>>((const T*)c.y, c.scale, c.shift, (T*)c.a, B, c.Lc, c.Lp, \
@@ -655,7 +669,21 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
         const int64_t R = (int64_t)B * c.Lc;
         EMB_CUDA_OK(cudaMemsetAsync(c.bstats, 0, 2 * c.cout * sizeof(double), st));
         const bool even = (c.cout % 2) == 0;
-        if (even) {
+        const bool kt = std::is_same<T, bf16>::value && kt_ok(c.cout, c.ld) && kt_bwd_smem(c.Lc, c.Lp, c.cout) <= (size_t)kt_max_smem() &&
+                        !getenv("EMB_NO_TMA_K2");
+        PoolBwdArgs ka = {};
+        if (kt) {
+            // pass 1 of 2: the BatchNorm reductions only; dz is recomputed (not stored) by pass 2 below
+            ka.y = (const bf16*)c.y; ka.a = (const bf16*)c.a; ka.ga = (const bf16*)c.ga; ka.scale = c.scale; ka.shift = c.shift;
+            ka.mean = c.mean; ka.rstd = c.rstd; ka.gamma = e->params + c.gamma; ka.bstats_in = c.bstats; ka.bstats_out = c.bstats;
+            ka.dy = (bf16*)c.dy; ka.dbias = e->grads + c.b; ka.B = B; ka.Lc = c.Lc; ka.Lp = c.Lp; ka.C = c.cout; ka.drop_p = c.drop;
+            ka.n = (double)(e->global_batch > 0 ? e->global_batch : B) * c.Lc;
+            kt_segments(c.cout, c.Lc, 2, &ka.nseg, &ka.P);
+            const size_t ksm = kt_bwd_smem(c.Lc, c.Lp, c.cout);
+            pool_bn_bwd_tma_kernel<0><<<std::min(B, tc_num_sms() * kt_ctas_per_sm(ksm, 3)), KT_THREADS, ksm, st>>>(ka);
+            EMB_CHECK_LAUNCH();
+            LAUNCHED(e);
+        } else if (even) {
             dim3 grid(cdiv(c.cout / 2, 32), cdiv(B, 8));
             pool_bn_bwd_stream_kernel<T><<<grid, dim3(32, 8), 0, st>>>((const T*)c.y, (const T*)c.a, (const T*)c.ga, c.scale, c.shift, c.mean,
                                                                        c.rstd, (T*)c.dy, c.bstats, B, c.Lc, c.Lp, c.cout, c.ld, c.drop);
@@ -681,7 +709,10 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
             LAUNCHED(e);
         }
         double n = (double)(e->global_batch > 0 ? e->global_batch : B) * c.Lc;
-        if ((c.cout % 8) == 0 && c.cout <= 2048) {
+        if (kt) {
+            const size_t ksm = kt_bwd_smem(c.Lc, c.Lp, c.cout);
+            pool_bn_bwd_tma_kernel<1><<<std::min(B, tc_num_sms() * kt_ctas_per_sm(ksm, 3)), KT_THREADS, ksm, st>>>(ka);
+        } else if ((c.cout % 8) == 0 && c.cout <= 2048) {
             const int G = c.cout / 8, rpb = std::max(1, 256 / G);
             dim3 block(G, rpb);
             const int grid = (int)std::min<int64_t>(148 * 8, cdiv(R, rpb));
@@ -1098,6 +1129,10 @@ int emb_bind(EmbEngine* e, float* params, float* grads, float* buffers, float* o
     cudaFuncSetAttribute(onehot_conv_fwd_pair_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 * 25 * 64 + 64 + 4096) * 4 + 512);
     int rc = tc_init();
     if (rc) return rc;
+    EMB_CUDA_OK(cudaFuncSetAttribute(pool_bn_bwd_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kt_max_smem()));
+    EMB_CUDA_OK(cudaFuncSetAttribute(pool_bn_bwd_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kt_max_smem()));
+    EMB_CUDA_OK(cudaFuncSetAttribute(bn_relu_pool_drop_fwd_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kt_max_smem()));
+    EMB_CUDA_OK(cudaFuncSetAttribute(bn_relu_pool_drop_fwd_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kt_max_smem()));
     return EMB_OK;
 }
 
