@@ -287,6 +287,67 @@ __global__ void unpermute_conv_wgrad_kernel(const float* __restrict__ tmp, float
     dw[i] = tmp[(size_t)tap * oc + r];
 }
 
+// ---------------------------------------------------------------------------------------------
+// The 2-logit head (post.N / FFNN final Linear / CNN last_output: nn.Linear(K -> 2)).  A [B, K] x [K, 2] product is a
+// pair of dot products per row -- far below any GEMM tile -- so it gets three small bandwidth-shaped kernels instead of
+// the generic SIMT GEMM (which took 25-55 us per call at batch 8192).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const T* __restrict__ x, int ld, const float* __restrict__ w, const float* __restrict__ bias, int round_w,
+                float* __restrict__ logits, int B, int K) {
+    extern __shared__ float hw[];                       // [2][K]
+    for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) hw[i] = round_w ? __bfloat162float(__float2bfloat16_rn(w[i])) : w[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b = blockIdx.x * 8 + warp; b < B; b += gridDim.x * 8) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int k = lane; k < K; k += 32) {
+            const float v = to_f(x[(size_t)b * ld + k]);
+            a0 = fmaf(v, hw[k], a0);
+            a1 = fmaf(v, hw[K + k], a1);
+        }
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        if (lane == 0) { logits[2 * b] = a0 + bias[0]; logits[2 * b + 1] = a1 + bias[1]; }
+    }
+}
+
+// dW[j][k] += sum_b dl[b][j] * x[b][k],  db[j] += sum_b dl[b][j]        (dl fp32 [B, 2])
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_wgrad_kernel(const float* __restrict__ dl, const T* __restrict__ x, int ld, float* __restrict__ dw, float* __restrict__ db, int B, int K,
+                  int rows_per_block) {
+    const int b0 = blockIdx.x * rows_per_block, b1 = min(B, b0 + rows_per_block);
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int b = b0; b < b1; ++b) {
+            const float v = to_f(x[(size_t)b * ld + k]);
+            const float2 d = *reinterpret_cast<const float2*>(dl + 2 * b);
+            a0 = fmaf(d.x, v, a0);
+            a1 = fmaf(d.y, v, a1);
+        }
+        atomicAdd(&dw[k], a0);
+        atomicAdd(&dw[K + k], a1);
+    }
+    if (threadIdx.x < 2) {
+        float a = 0.f;
+        for (int b = b0; b < b1; ++b) a += dl[2 * b + threadIdx.x];
+        atomicAdd(&db[threadIdx.x], a);
+    }
+}
+
+// acc[b][k] = dl[b][0] * W[0][k] + dl[b][1] * W[1][k], finished by the usual epilogue functor
+__global__ void __launch_bounds__(256)
+head_dgrad_kernel(const float* __restrict__ dl, const float* __restrict__ w, int round_w, Epilogue ep, int B, int K) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * K) return;
+    const int b = (int)(i / K), k = (int)(i - (size_t)b * K);
+    float w0 = w[k], w1 = w[K + k];
+    if (round_w) { w0 = __bfloat162float(__float2bfloat16_rn(w0)); w1 = __bfloat162float(__float2bfloat16_rn(w1)); }
+    epilogue_apply(ep, b, k, B, K, fmaf(dl[2 * b], w0, dl[2 * b + 1] * w1));
+}
+
 // carve the workspace; with base == nullptr only the size is computed
 int64_t carve(EmbEngine* e, char* base) {
     Bump bp{base};
@@ -512,6 +573,15 @@ int linear_wgrad(EmbEngine* e, const LinearLayer& l, const void* g, int g_dtype,
     Epilogue ep = base_epi(e, EPI_ATOMIC, e->grads + l.w, l.in);
     if (l.perm_in) { ep.map = MAP_W_PERM; ep.mapC = e->cnn_C_last; ep.mapL = e->cnn_Lp_last; ep.map_wrows = l.in; }
     int rc;
+    if (l.out == 2 && g_dtype == 0 && g_ld == 2 && !l.perm_in) {
+        // the 2-logit head: weight and bias gradient in one small kernel
+        const int rpb = 64;
+        if (dtype_of(e)) head_wgrad_kernel<bf16><<<cdiv(B, rpb), 256, 0, st>>>((const float*)g, (const bf16*)in.p, in.ld, e->grads + l.w, e->grads + l.b, B, l.in, rpb);
+        else head_wgrad_kernel<float><<<cdiv(B, rpb), 256, 0, st>>>((const float*)g, (const float*)in.p, in.ld, e->grads + l.w, e->grads + l.b, B, l.in, rpb);
+        EMB_CHECK_LAUNCH();
+        LAUNCHED(e);
+        return EMB_OK;
+    }
     if (tc_linear_ok(e, l) && g_dtype == 1 && (g_ld % 8) == 0) {
         TcProblem pr = {};
         pr.kind = TC_LINEAR_WGRAD; pr.a = (const bf16*)g; pr.lda = g_ld; pr.b = (const bf16*)in.p; pr.ldb = in.ld;
@@ -543,6 +613,13 @@ int linear_wgrad(EmbEngine* e, const LinearLayer& l, const void* g, int g_dtype,
 
 // gradient w.r.t. the layer input: acc = g W, finished by `ep`
 int linear_dgrad(EmbEngine* e, const LinearLayer& l, const void* g, int g_dtype, int g_ld, int B, Epilogue ep, cudaStream_t st) {
+    if (l.out == 2 && g_dtype == 0 && g_ld == 2 && !l.perm_in) {
+        const size_t tot = (size_t)B * l.in;
+        head_dgrad_kernel<<<cdiv(tot, 256), 256, 0, st>>>((const float*)g, e->params + l.w, e->prec == EMB_PREC_BF16 ? 1 : 0, ep, B, l.in);
+        EMB_CHECK_LAUNCH();
+        LAUNCHED(e);
+        return EMB_OK;
+    }
     if (tc_linear_ok(e, l) && g_dtype == 1 && (g_ld % 8) == 0) {
         TcProblem pr = {};
         pr.kind = TC_LINEAR_DGRAD; pr.a = (const bf16*)g; pr.lda = g_ld; pr.b = l.wc; pr.ldb = round_up(l.in, 8);
@@ -900,8 +977,17 @@ int forward_impl(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const 
         Epilogue ep = base_epi(e, EPI_LINEAR, logits, 2);
         ep.out_dtype = 0;
         ep.bias = e->params + l.b;
-        rc = run_gemm(e, A, W, ep, B, 2, l.in, 1, st);
-        if (rc) return rc;
+        if (l.out == 2 && !l.perm_in && l.in <= 4096) {
+            const int grid = std::min(cdiv(B, 8), 148 * 8);
+            const size_t smem = (size_t)2 * l.in * sizeof(float);
+            if (dt) head_fwd_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)head_in->p, head_in->ld, e->params + l.w, e->params + l.b, 1, logits, B, l.in);
+            else head_fwd_kernel<float><<<grid, 256, smem, st>>>((const float*)head_in->p, head_in->ld, e->params + l.w, e->params + l.b, 0, logits, B, l.in);
+            EMB_CHECK_LAUNCH();
+            LAUNCHED(e);
+        } else {
+            rc = run_gemm(e, A, W, ep, B, 2, l.in, 1, st);
+            if (rc) return rc;
+        }
     }
     rng_advance_kernel<<<1, 1, 0, st>>>(e->rng);   // next forward (train or eval: multinomial is sampled in both) draws afresh
     EMB_CHECK_LAUNCH();

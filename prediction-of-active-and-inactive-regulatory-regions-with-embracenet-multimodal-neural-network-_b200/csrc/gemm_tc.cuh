@@ -528,7 +528,7 @@ inline int& tc_max_smem() { static int v = 0; return v; }
 inline int& tc_num_sms() { static int v = 148; return v; }
 // conv wgrad tiling (tunable for experiments): taps accumulated per CTA (<=1: one tap per CTA) and the N tile
 inline int tc_min_kiters() { static int v = getenv("EMB_MIN_KITERS") ? atoi(getenv("EMB_MIN_KITERS")) : 8; return v; }
-inline int tc_wgrad_taps() { static int v = getenv("EMB_WGRAD_TAPS") ? atoi(getenv("EMB_WGRAD_TAPS")) : 0; return v; }
+inline int tc_wgrad_taps() { static int v = getenv("EMB_WGRAD_TAPS") ? atoi(getenv("EMB_WGRAD_TAPS")) : 0; return v; }   // 0: as many taps as TMEM holds; 1: per-tap kernel
 inline int tc_wgrad_ntile() { static int v = getenv("EMB_WGRAD_NT") ? atoi(getenv("EMB_WGRAD_NT")) : 128; return v; }
 
 inline int tc_init() {
@@ -684,7 +684,7 @@ inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int
         p.M = pr.M; p.N = N;
         int rows_box, j_total, conv_tap_groups = 1;
         (void)rows_box;
-        if (conv && tc_wgrad_taps() <= 1) {
+        if (conv && (tc_wgrad_taps() == 1 || pr.taps < 2 || pr.pad > 7)) {
             if (pr.L > 128) return set_error(-5, "conv GEMM: L > 128 not supported");
             const int bt = std::max(1, 128 / pr.L);
             rows_box = bt * pr.L;
@@ -703,13 +703,16 @@ inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int
             p.k_steps = 8;
             conv_tap_groups = pr.taps;
         } else if (conv) {
-            // Multi-tap wgrad: one CTA = (128 output channels) x (n_tile input channels) x (a group of up to 8 taps).
-            // Both operands are staged with their zero halo (rows l = -pad .. L+pad-1 of each sample, filled by TMA),
-            // so tap t is the SAME dy tile against the x tile shifted by (t - pad) rows: one descriptor offset, no reload.
-            const int S = pr.L + 2 * pr.pad;                 // rows per sample incl. halo
-            if (S > 256) return set_error(-5, "conv wgrad: L + 2*pad > 256 not supported");
-            const int bt = std::max(1, 160 / S);             // whole samples per K block
-            const int R = round_up(bt * S, 16);              // K rows per stage (rows beyond the box stay zero)
+            // Multi-tap wgrad: one CTA = (128 output channels) x (n_tile input channels) x (a group of T taps, T * n_tile <= 512
+            // TMEM columns).  The per-tap kernel above is bound by L2 -> SM operand traffic (it re-fetches dy and x for each
+            // of the 15 taps); here ONE staged (dy, x) pair feeds T taps.  K rows of a stage, S = L + pad per sample:
+            //   dy_s[g*S + l]       = dy[g, l]   (box starts at l = 0; rows L..S-1 are out of bounds -> zero-filled)
+            //   x_s [g*S + pad + l] = x[g, l]    (box starts at l = -pad; the zero halo is SHARED by consecutive samples)
+            // so tap t is dy_s against x_s shifted by t rows: one descriptor offset, no reload.
+            const int S = pr.L + pr.pad;
+            if (S > 240) return set_error(-5, "conv wgrad: L + pad > 240 not supported");
+            const int bt = std::max(1, 144 / S);              // whole samples per K block
+            const int R = round_up(bt * S, 16);               // K rows per stage (rows beyond the box stay zero)
             rows_box = bt * S;
             j_total = cdiv(pr.B, bt);
             const int nt_max = tc_wgrad_ntile();
@@ -720,12 +723,12 @@ inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int
             rc = make_map(&mb, pr.b, pr.Cin, pr.L, pr.B, pr.ldb, (int64_t)pr.L * pr.ldb, 64, S, bt);
             if (rc) return rc;
             mnmajor_operand(p.a, 128, rows_box, R);
-            mnmajor_operand(p.b, n_tile, rows_box, R + 16);   // 8 guard rows before and after the tile
-            p.b.dst_off = 1024;
-            p.a.ctile[0] = 128; p.a.cblk[0] = 64; p.a.cj[2] = bt; p.a.base[1] = -pr.pad;
+            mnmajor_operand(p.b, n_tile, rows_box, R + 16);   // tap t reads rows t .. t + R - 1 (t <= 2 * pad <= 14)
+            p.a.ctile[0] = 128; p.a.cblk[0] = 64; p.a.cj[2] = bt; p.a.base[1] = 0;
             p.b.ctile[0] = n_tile; p.b.cblk[0] = 64; p.b.cj[2] = bt; p.b.base[1] = -pr.pad;
-            p.taps_per_cta = std::max(1, std::min(std::min(pr.taps, tc_wgrad_taps()), 512 / n_tile));
-            p.tap_pad = pr.pad;
+            const int want = tc_wgrad_taps() > 1 ? tc_wgrad_taps() : 512 / n_tile;
+            p.taps_per_cta = std::max(1, std::min(std::min(pr.taps, want), 512 / n_tile));
+            p.tap_pad = 0;
             p.tap_in_z = 1; p.n_taps = pr.taps; p.n_off_per_tap = pr.wgrad_tap_stride > 0 ? pr.wgrad_tap_stride : pr.Cin;
             p.n_logical = pr.taps * pr.Cin;
             p.zero_smem = 1;
