@@ -813,6 +813,10 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
                 const int threads = round_up((c.cout / 2) * c.k, 32);
                 size_t smem = (size_t)(SEQ_LEN + 2 * c.pad) * c.cout * sizeof(float) + SEQ_LEN + 16;
                 int grid = std::min(B, 148 * 2);
+                if (std::is_same<T, bf16>::value && (c.cout % 8) == 0) {
+                    const size_t smem16 = (size_t)(SEQ_LEN + 2 * c.pad) * c.cout * sizeof(bf16) + SEQ_LEN + 16;
+                    onehot_conv_bwd_lists16_kernel<<<std::min(B, 148 * 2), threads, smem16, st>>>(e->last_bases, (const bf16*)c.dy, e->grads + c.w, B, c.cout, c.k, c.ld);
+                } else
                 onehot_conv_bwd_lists_kernel<T><<<grid, threads, smem, st>>>(e->last_bases, (const T*)c.dy, e->grads + c.w, B, c.cout, c.k, c.ld);
             } else {
                 int grid = std::min(B, 148 * 4);

@@ -606,4 +606,90 @@ onehot_conv_bwd_lists_kernel(const uint8_t* __restrict__ bases, const T* __restr
     }
 }
 
+// bf16 variant of the per-base-list K1 backward: the staged dy tile stays in bf16 (half the shared-memory bytes of the
+// fp32 tile: the kernel is bound by shared-memory reads), 16-byte coalesced global loads.  Requires C1 % 8 == 0.
+__global__ void __launch_bounds__(1024)
+onehot_conv_bwd_lists16_kernel(const uint8_t* __restrict__ bases, const bf16* __restrict__ dy, float* __restrict__ dw, int B, int C1, int k, int ld) {
+    extern __shared__ float smem[];
+    const int p = (k - 1) / 2;
+    bf16* dys = (bf16*)smem;                                      // [256 + 2p][C1] bf16, rows shifted by p
+    uint8_t* plist = (uint8_t*)(dys + (SEQ_LEN + 2 * p) * C1);    // [256] positions grouped by base
+    __shared__ int start[5];
+    const int pairs = C1 / 2;
+    const int tap = threadIdx.x / pairs, op = threadIdx.x - tap * pairs;
+    const bool active = tap < k;
+    double d[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) d[i][c] = 0.0;
+    for (int i = threadIdx.x; i < p * C1 / 2; i += blockDim.x) {
+        ((uint32_t*)dys)[i] = 0u;
+        ((uint32_t*)(dys + (SEQ_LEN + p) * C1))[i] = 0u;
+    }
+    const int vec_per_row = C1 / 8;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < SEQ_LEN * vec_per_row; i += blockDim.x) {
+            const int l = i / vec_per_row, v = i - l * vec_per_row;
+            *reinterpret_cast<uint4*>(dys + (l + p) * C1 + 8 * v) = *reinterpret_cast<const uint4*>(dy + ((size_t)b * SEQ_LEN + l) * ld + 8 * v);
+        }
+        // counting sort of the positions by base (warp 0: ballot-based, keeps ascending position order per base)
+        if (threadIdx.x < 32) {
+            int base_cnt[4] = {0, 0, 0, 0};
+            uint8_t mine[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                mine[q] = bases[(size_t)b * SEQ_LEN + q * 32 + threadIdx.x];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) base_cnt[c] += __popc(__ballot_sync(0xffffffffu, mine[q] == c));
+            }
+            int st[5];
+            st[0] = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) st[c + 1] = st[c] + base_cnt[c];
+            if (threadIdx.x < 5) start[threadIdx.x] = st[threadIdx.x];
+            int run[4] = {st[0], st[1], st[2], st[3]};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    unsigned m = __ballot_sync(0xffffffffu, mine[q] == c);
+                    if (mine[q] == c) plist[run[c] + __popc(m & ((1u << threadIdx.x) - 1))] = (uint8_t)(q * 32 + threadIdx.x);
+                    run[c] += __popc(m);
+                }
+            }
+        }
+        __syncthreads();
+        if (active) {
+            // source position ls feeds output l = ls - tap + p, stored at row l + p = ls - tap + 2p of dys
+            const bf16* col = dys + (2 * p - tap) * C1 + 2 * op;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+                const int e = start[c + 1];
+                int i = start[c];
+                for (; i + 1 < e; i += 2) {                     // two independent chains
+                    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(col + (int)plist[i] * C1);
+                    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(col + (int)plist[i + 1] * C1);
+                    a0 += __uint_as_float(w0 << 16); a1 += __uint_as_float(w0 & 0xFFFF0000u);
+                    b0 += __uint_as_float(w1 << 16); b1 += __uint_as_float(w1 & 0xFFFF0000u);
+                }
+                if (i < e) {
+                    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(col + (int)plist[i] * C1);
+                    a0 += __uint_as_float(w0 << 16); a1 += __uint_as_float(w0 & 0xFFFF0000u);
+                }
+                d[0][c] += a0 + b0;
+                d[1][c] += a1 + b1;
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) atomicAdd(&dw[((size_t)(2 * op + i) * 4 + c) * k + tap], (float)d[i][c]);
+    }
+}
+
 }  // namespace emb
