@@ -31,29 +31,24 @@ METRIC = 'embracenet_train_samples_per_sec'
 UNIT = 'samples/s'
 
 
-def arch(name):
+def oracle_spec(name):
+    """Spec dict of the CPU oracle / port (test infrastructure; used by the cpu_baseline and --impl reference legs only)."""
     from tests.golden.cases import ARCH_L, ARCH_S, ARCH_M, ARCH_W
     return {'L': ARCH_L, 'S': ARCH_S, 'M': ARCH_M, 'W': ARCH_W}[name]
 
 
-def fwd_flops_per_sample(spec):
-    """Dense-equivalent forward FLOPs (2*MAC) per sample of the GEMM-shaped ops; layer 0 counted as a gather."""
-    from oracle.embracenet_oracle import cnn_lengths
-    f, fin = 0, spec['F']
-    for u in spec['ffnn_units']:
-        f += 2 * fin * u
-        fin = u
-    cin, L = 4, 256
-    for i, ((co, k), (Lc, Lp)) in enumerate(zip(zip(spec['cnn_channels'], spec['cnn_kernels']), cnn_lengths(spec['cnn_kernels']))):
-        f += (k * co * Lc) if i == 0 else 2 * cin * k * co * Lc
-        cin, L = co, Lp
-    C = spec['C']
-    f += 2 * (spec['ffnn_units'][-1] + cin * L) * C
-    fin = C
-    for u in spec['post_units']:
-        f += 2 * fin * u
-        fin = u
-    return f + 2 * fin * 2
+def cpu_port_sample(arch_name, batch, budget_s=14.0, max_steps=64):
+    """Time the PyTorch-CPU port of the reference on a bounded sample: one warm-up, one probe step, then as many steps
+    as fit `budget_s` seconds."""
+    import torch
+    from oracle import torch_port as TP
+    spec = oracle_spec(arch_name)
+    torch.set_num_threads(os.cpu_count() or 1)
+    probe = TP.time_train(spec, batch, 1, 1, seed=789)
+    steps = int(max(2, min(max_steps, budget_s / max(probe['seconds'], 1e-3))))
+    r = TP.time_train(spec, batch, steps, 0, seed=789)
+    r['steps'] = steps
+    return r
 
 
 class ClockSampler:
@@ -98,37 +93,26 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def synth_batches(spec, B, n, seed):
-    import numpy as np
-    rs = np.random.RandomState(seed)
-    out = []
-    for _ in range(n):
-        x = rs.random_sample((B, spec['F'])).astype(np.float32)
-        bases = rs.randint(0, 4, size=(B, 256)).astype(np.uint8)
-        # planted signal: logistic on 4 features + base rate ~1/7 (HEPG2 promoters)
-        z = 3.0 * (x[:, :4].sum(1) - 2.0) - 1.9
-        y = (rs.random_sample(B) < 1 / (1 + np.exp(-z))).astype(np.int32)
-        out.append((x, bases, y))
-    return out
-
-
-def run_reference(args, spec, rank, world):
-    """The reference's CPU implementation of the path (PyTorch fp64 library calls, oracle/torch_port.py)."""
+def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path (PyTorch fp64 library calls, oracle/torch_port.py), all host threads.
+    Each step is a bounded sample of the workload: one train step of batch --ref-batch."""
     if rank != 0:
         return
     import torch
     from oracle import torch_port as TP
+    spec = oracle_spec(args.arch)
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     B = args.ref_batch
     r = TP.time_train(spec, B, args.steps, args.warmup, seed=789)
     val = r['samples_per_s']
-    sample = f'{args.steps} train steps of batch {B} (arch {args.arch}, fp64, torch {torch.__version__} CPU)'
+    sample = f'{args.steps} train steps of batch {B} after {args.warmup} warm-up (arch {args.arch}, fp64, torch {torch.__version__} CPU, {r["seconds"]:.1f} s)'
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * r['seconds'] / args.steps, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f'EmbraceNet arch {args.arch} train step, global batch {args.batch} (bounded CPU sample: batch {B})',
+        'config': {'workload': f'EmbraceNet arch {args.arch} full train step (fwd+loss+bwd+Adam), global batch {args.batch}, '
+                               f'F={spec["F"]}, 256-bp bases (BASELINE configs[2]); bounded CPU sample: batch {B} per step',
                    'arch': args.arch, 'global_batch': args.batch, 'in_features': spec['F'], 'optimizer': 'adam+L2'},
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': r['threads'], 'kind': 'port', 'sample': sample},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -149,24 +133,25 @@ def main():
     ap.add_argument('--tensor-core', type=int, default=1)
     ap.add_argument('--ref-batch', type=int, default=256, help='batch of the bounded CPU sample')
     ap.add_argument('--cpu-baseline', type=int, default=1)
+    ap.add_argument('--graph', type=int, default=1, help='replay the train step as one CUDA graph (single GPU)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else max(args.warmup, 1)
 
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
-    spec = arch(args.arch)
-
     if args.impl == 'reference':
-        run_reference(args, spec, rank, world)
+        run_reference(args, rank, world)
         return
 
     import numpy as np
     import torch
     import torch.distributed as dist
     import embrace_b200
-    from tests.test_gpu_parity import to_archspec
-    from oracle.embracenet_oracle import init_params
+    from embrace_b200 import presets
+
+    spec = presets.arch(args.arch)            # product-side spec: the measured arm imports nothing from oracle/ or tests/
+    F = spec.in_features
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -178,11 +163,13 @@ def main():
     B = args.batch // world
     NBUF = 4
 
-    eng = embrace_b200.Engine(to_archspec(spec), max_batch=B, precision=args.precision, device=dev, seed=789,
+    eng = embrace_b200.Engine(spec, max_batch=B, precision=args.precision, device=dev, seed=789,
                               tensor_core=bool(args.tensor_core) and args.precision == 'bf16')
-    eng.load_numpy(init_params(spec, 789))                 # same random-init weights on every rank
+    eng.init_random(789)                                   # same random-init weights on every rank
+    if world == 1 and args.graph:
+        eng.set_graph(True)
     cfg = eng.opt_config('adam', lr=4.1e-5, weight_decay=7.6e-4)
-    glob = synth_batches(spec, args.batch, NBUF, seed=789)   # every rank builds the global batches, keeps its rows
+    glob = presets.synthetic_batches(spec, args.batch, NBUF, seed=789)   # every rank builds the global batches, keeps its rows
     lo = rank * B
     host = [(torch.from_numpy(x[lo:lo + B]).pin_memory(), torch.from_numpy(b[lo:lo + B]).pin_memory(),
              torch.from_numpy(y[lo:lo + B]).pin_memory()) for x, b, y in glob]
@@ -272,16 +259,16 @@ def main():
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
         'config': {'workload': f'EmbraceNet arch {args.arch} full train step (fwd+loss+bwd+Adam), global batch {args.batch}, '
-                               f'F={spec["F"]}, 256-bp bases (BASELINE configs[2])',
-                   'arch': args.arch, 'global_batch': args.batch, 'per_gpu_batch': B, 'in_features': spec['F'],
-                   'optimizer': 'adam+L2', 'precision': args.precision, 'tensor_core': eng.tensor_core,
+                               f'F={F}, 256-bp bases (BASELINE configs[2])',
+                   'arch': args.arch, 'global_batch': args.batch, 'per_gpu_batch': B, 'in_features': F,
+                   'optimizer': 'adam+L2', 'precision': args.precision, 'tensor_core': eng.tensor_core, 'cuda_graph': bool(world == 1 and args.graph),
                    'parallelism': f'dp{world}' if world > 1 else 'single',
                    'l2': f'per-step working set (activations+gradients, ~{eng.ws_bytes / 1e9:.1f} GB) >> 126 MB L2; '
                          f'inputs rotate over {NBUF} resident batches',
-                   'train_flops_per_sample': 3 * fwd_flops_per_sample(spec)},
+                   'train_flops_per_sample': 3 * presets.fwd_flops_per_sample(spec)},
         'clocks': clocks,
         'e2e': {'value': e2e, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
-                'h2d_bytes_per_step': int(args.batch * (spec['F'] * 4 + 256 + 4)), 'd2h_bytes_per_step': 20 * world},
+                'h2d_bytes_per_step': int(args.batch * (F * 4 + 256 + 4)), 'd2h_bytes_per_step': 20 * world},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
                      'frac': achieved_tf / peak_tf, 'traffic': None, 'kernel': 'GEMM class (conv implicit GEMM / docking / linear)',
@@ -291,12 +278,10 @@ def main():
         'final_loss': final[-1]['loss'] if final else None,
     }
     if world == 1 and args.cpu_baseline:
-        from oracle import torch_port as TP
-        torch.set_num_threads(os.cpu_count() or 1)
-        r = TP.time_train(spec, args.ref_batch, 2, 1, seed=789)
+        r = cpu_port_sample(args.arch, args.ref_batch)
         line['cpu_baseline'] = {'value': r['samples_per_s'], 'unit': UNIT, 'cores': r['threads'], 'kind': 'port',
-                                'sample': f'2 train steps of batch {args.ref_batch} after 1 warm-up (arch {args.arch}, fp64 PyTorch CPU '
-                                          f'port of the reference, {r["seconds"]:.1f} s)'}
+                                'sample': f'{r["steps"]} train steps of batch {args.ref_batch} after 1 warm-up (arch {args.arch}, fp64 PyTorch CPU '
+                                          f'port of the reference, {r["seconds"]:.1f} s of CPU work)'}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -205,6 +205,10 @@ int emb_profile_read(EmbEngine* e, double* ms_out, double* flops_out, int64_t* l
 /* select GEMM back end: 0 = SIMT fp32-accumulate kernels only, 1 = tcgen05/TMEM/TMA where the shape
  * allows (bf16 precision only) */
 int emb_set_tensor_core(EmbEngine* e, int32_t on);
+/* on: emb_train_step (no replayed draws, no data-parallel hooks) captures the whole step -- forward, loss, backward and
+ * the optimizer kernel -- into a CUDA graph the second time a batch size is seen and replays it afterwards (inputs are
+ * staged into engine-owned buffers; step-dependent scalars live in device memory).  off: destroys the cached graphs. */
+int emb_set_graph(EmbEngine* e, int32_t on);
 
 /* ---- data-parallel hooks (SyncBN / global loss weights) --------------------------------------
  * When set, BatchNorm statistics are finished by the host's allreduce: the engine writes the local

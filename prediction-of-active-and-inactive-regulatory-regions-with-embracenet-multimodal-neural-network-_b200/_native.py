@@ -88,6 +88,7 @@ SIGNATURES = {
     'emb_last_selection': (C.c_int, [_P, _P, C.c_int32, _P]),
     'emb_launch_count': (C.c_int64, [_P]),
     'emb_set_tensor_core': (C.c_int, [_P, C.c_int32]),
+    'emb_set_graph': (C.c_int, [_P, C.c_int32]),
     'emb_profile_gemm': (C.c_int, [_P, C.c_int32]),
     'emb_profile_read': (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     'emb_set_allreduce': (C.c_int, [_P, ALLREDUCE_FN, _P]),

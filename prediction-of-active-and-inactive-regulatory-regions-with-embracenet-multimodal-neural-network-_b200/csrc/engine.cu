@@ -123,6 +123,14 @@ struct EmbEngine {
     EmbAllreduceFn allreduce = nullptr;
     void* allreduce_user = nullptr;
     int64_t launches = 0;
+    // CUDA-graph replay of the whole train step (emb_set_graph): one instantiated graph per batch size
+    struct StepGraph { int B; int has_opt; int opt_kind; int64_t kernels; cudaGraphExec_t exec; };
+    bool graph_on = false;
+    std::vector<StepGraph> graphs;
+    std::vector<int> graph_seen;     // batch sizes that already ran once eagerly (lazy initialisation happens there)
+    bool capturing = false;
+    cudaStream_t gstream = nullptr;  // graphs are captured and launched on an engine-owned stream (the caller's may be the legacy
+    cudaEvent_t gev_in = nullptr, gev_out = nullptr;   // default stream, which cannot be captured); events order it with the caller's
     // per-kernel timing of the GEMM class (bench.py roofline): CUDA event pairs around each launch
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -1160,6 +1168,8 @@ int emb_create(const EmbArchSpec* spec, int32_t max_batch, int32_t precision, Em
 void emb_destroy(EmbEngine* e) {
     if (!e) return;
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
+    for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+    if (e->gstream) { cudaStreamDestroy(e->gstream); cudaEventDestroy(e->gev_in); cudaEventDestroy(e->gev_out); }
     if (e->owns_memory) {
         cudaFree(e->params); cudaFree(e->grads); cudaFree(e->buffers); cudaFree(e->opt_m); cudaFree(e->opt_v); cudaFree(e->ws);
     }
@@ -1349,21 +1359,92 @@ int emb_backward(EmbEngine* e, const float* dlogits, void* stream) {
     return backward_impl(e, dlogits, (cudaStream_t)stream);
 }
 
+// host half of an optimizer step: the step-dependent scalars travel through a small device slot written by a
+// stream-ordered copy (outside any captured graph, so a replayed graph sees fresh values)
+static int opt_step_prepare(EmbEngine* e, const EmbOptConfig* cfg, cudaStream_t st) {
+    if (!cfg || cfg->kind < 0 || cfg->kind > 3) return set_error(EMB_E_ARG, "bad optimizer config");
+    if (!e->opt_m || !e->opt_v) return set_error(EMB_E_STATE, "no optimizer state bound");
+    OptScalars h;
+    fill_opt_scalars(e, *cfg, &h);
+    EMB_CUDA_OK(cudaMemcpyAsync(e->opt_scalars, &h, sizeof h, cudaMemcpyHostToDevice, st));
+    return EMB_OK;
+}
+static int opt_step_launch(EmbEngine* e, cudaStream_t st) {
+    int grid = std::min<int64_t>(148 * 8, cdiv(e->n_params, 256));
+    opt_step_kernel<<<grid, 256, 0, st>>>(e->params, e->grads, e->opt_m, e->opt_v, e->opt_scalars, (size_t)e->n_params);
+    EMB_CHECK_LAUNCH();
+    LAUNCHED(e);
+    return EMB_OK;
+}
+
 int emb_opt_step(EmbEngine* e, const EmbOptConfig* cfg, void* stream) {
     int rc = check_ready(e, 1, true);
     if (rc) return rc;
-    if (!cfg || cfg->kind < 0 || cfg->kind > 3) return set_error(EMB_E_ARG, "bad optimizer config");
-    if (!e->opt_m || !e->opt_v) return set_error(EMB_E_STATE, "no optimizer state bound");
     cudaStream_t st = (cudaStream_t)stream;
-    OptScalars h;
-    fill_opt_scalars(e, *cfg, &h);
-    // scalars travel through a small device slot written by a stream-ordered copy
-    OptScalars* d = e->opt_scalars;
-    EMB_CUDA_OK(cudaMemcpyAsync(d, &h, sizeof h, cudaMemcpyHostToDevice, st));
-    int grid = std::min<int64_t>(148 * 8, cdiv(e->n_params, 256));
-    opt_step_kernel<<<grid, 256, 0, st>>>(e->params, e->grads, e->opt_m, e->opt_v, d, (size_t)e->n_params);
-    EMB_CHECK_LAUNCH();
-    LAUNCHED(e);
+    if ((rc = opt_step_prepare(e, cfg, st))) return rc;
+    return opt_step_launch(e, st);
+}
+
+int emb_set_graph(EmbEngine* e, int32_t on) {
+    if (!e) return set_error(EMB_E_ARG, "null engine");
+    e->graph_on = on != 0;
+    if (!on) {
+        for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+        e->graphs.clear();
+        e->graph_seen.clear();
+    }
+    return EMB_OK;
+}
+
+// The train step as ONE graph launch.  Inputs are staged into the engine's own buffers first (so the captured kernel
+// arguments never change); everything that varies from step to step lives in device memory: the Philox step counter,
+// the metrics record cursor and the optimizer scalars (written by opt_step_prepare before the launch).
+static int train_step_graph(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const int32_t* labels, int32_t B,
+                            const EmbOptConfig* cfg, cudaStream_t caller) {
+    int rc;
+    if (!e->gstream) {
+        EMB_CUDA_OK(cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking));
+        EMB_CUDA_OK(cudaEventCreateWithFlags(&e->gev_in, cudaEventDisableTiming));
+        EMB_CUDA_OK(cudaEventCreateWithFlags(&e->gev_out, cudaEventDisableTiming));
+    }
+    cudaStream_t st = e->gstream;
+    EMB_CUDA_OK(cudaEventRecord(e->gev_in, caller));
+    EMB_CUDA_OK(cudaStreamWaitEvent(st, e->gev_in, 0));
+    if (e->spec.kind != EMB_KIND_CNN && x_ffnn != e->in_x)
+        EMB_CUDA_OK(cudaMemcpyAsync(e->in_x, x_ffnn, (size_t)B * e->spec.in_features * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (e->spec.kind != EMB_KIND_FFNN && bases != e->in_bases)
+        EMB_CUDA_OK(cudaMemcpyAsync(e->in_bases, bases, (size_t)B * SEQ_LEN, cudaMemcpyDeviceToDevice, st));
+    if (labels != e->in_labels) EMB_CUDA_OK(cudaMemcpyAsync(e->in_labels, labels, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    if (cfg && (rc = opt_step_prepare(e, cfg, st))) return rc;
+    const int has_opt = cfg ? 1 : 0, kind = cfg ? cfg->kind : -1;
+    EmbEngine::StepGraph* g = nullptr;
+    for (auto& c : e->graphs) if (c.B == B && c.has_opt == has_opt && c.opt_kind == kind) g = &c;
+    if (!g) {
+        const int64_t l0 = e->launches;
+        EMB_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        e->capturing = true;
+        rc = forward_impl(e, e->in_x, e->in_bases, nullptr, B, true, nullptr, e->logits, st);
+        if (!rc) rc = emb_loss_ce_weighted(e, e->logits, e->in_labels, B, e->dlogits, (void*)st);
+        if (!rc) rc = backward_impl(e, e->dlogits, st);
+        if (!rc && cfg) rc = opt_step_launch(e, st);
+        e->capturing = false;
+        cudaGraph_t graph = nullptr;
+        cudaError_t err = cudaStreamEndCapture(st, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (err != cudaSuccess) return set_error(EMB_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(err));
+        EmbEngine::StepGraph ng{B, has_opt, kind, e->launches - l0, nullptr};
+        e->launches = l0;
+        err = cudaGraphInstantiate(&ng.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (err != cudaSuccess) return set_error(EMB_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(err));
+        e->graphs.push_back(ng);
+        g = &e->graphs.back();
+    }
+    EMB_CUDA_OK(cudaGraphLaunch(g->exec, st));
+    EMB_CUDA_OK(cudaEventRecord(e->gev_out, st));
+    EMB_CUDA_OK(cudaStreamWaitEvent(caller, e->gev_out, 0));
+    e->launches += g->kernels;
+    e->last_B = B; e->last_training = true; e->last_bases = e->in_bases;
     return EMB_OK;
 }
 
@@ -1372,6 +1453,13 @@ int emb_train_step(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, cons
     int rc = check_ready(e, B, true);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (e->graph_on && !draws && !e->allreduce && !e->prof_on && e->global_batch < 0) {
+        // the first step of a batch size runs eagerly (one-time initialisation such as function attributes happens there)
+        bool seen = false;
+        for (int b : e->graph_seen) seen |= b == B;
+        if (seen) return train_step_graph(e, x_ffnn, bases, labels, B, cfg, st);
+        e->graph_seen.push_back(B);
+    }
     rc = forward_impl(e, x_ffnn, bases, nullptr, B, true, draws, e->logits, st);
     if (rc) return rc;
     rc = emb_loss_ce_weighted(e, e->logits, labels, B, e->dlogits, stream);

@@ -88,6 +88,26 @@ class Engine:
         for t in self.table:
             self.view(t).copy_(torch.from_numpy(np.asarray(P[t['name']], dtype=np.float32)).to(self.device))
 
+    def init_random(self, seed=0):
+        """PyTorch-default-style initialisation in the arenas: nn.Linear / nn.Conv1d weights and biases ~ U(+-1/sqrt(fan_in)),
+        BatchNorm weight 1, bias 0, running_mean 0, running_var 1 (the state a freshly constructed reference model has)."""
+        g = torch.Generator(device='cpu').manual_seed(int(seed))
+        shapes = {t['name']: t['shape'] for t in self.table}
+        for t in self.table:
+            name, shape = t['name'], t['shape']
+            module = name.rsplit('.', 1)[0]
+            if name.endswith('running_mean'):
+                v = torch.zeros(shape)
+            elif name.endswith('running_var'):
+                v = torch.ones(shape)
+            elif module + '.running_mean' in shapes:
+                v = torch.ones(shape) if name.endswith('weight') else torch.zeros(shape)
+            else:
+                w = shapes[module + '.weight']
+                bound = 1.0 / float(np.sqrt(max(int(np.prod(w[1:])), 1)))
+                v = (torch.rand(shape, generator=g) * 2 - 1) * bound
+            self.view(t).copy_(v.to(self.device))
+
     def grads_numpy(self):
         return {t['name']: self.view(t, 'grads').detach().cpu().numpy().astype(np.float64) for t in self.table if not t['is_buffer']}
 
@@ -97,6 +117,11 @@ class Engine:
     def set_tensor_core(self, on):
         N.check(self.lib.emb_set_tensor_core(self._h, 1 if on else 0))
         self.tensor_core = bool(on)
+
+    def set_graph(self, on=True):
+        """Replay the whole train step as one CUDA graph (captured the second time a batch size is seen)."""
+        N.check(self.lib.emb_set_graph(self._h, 1 if on else 0))
+        self.graph = bool(on)
 
     def set_shard(self, row_offset, global_batch):
         N.check(self.lib.emb_set_shard(self._h, int(row_offset), int(global_batch)))

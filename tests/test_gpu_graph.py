@@ -1,0 +1,66 @@
+"""CUDA-graph replay of the whole train step (emb_set_graph) against the same steps launched kernel by kernel."""
+import numpy as np
+import pytest
+
+from oracle import embracenet_oracle as O
+from tests.golden.cases import ARCH_S, ARCH_M, make_inputs
+from tests.test_gpu_parity import to_archspec
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('precision,spec,opt', [('fp32', ARCH_S, 'adam'), ('bf16', ARCH_M, 'nadam'), ('bf16', ARCH_S, 'rmsprop')])
+def test_graph_replay_matches_eager(precision, spec, opt):
+    import torch
+    from embrace_b200 import Engine
+    B, steps = 48, 6
+    P = O.init_params(spec, 11)
+    batches = [make_inputs(spec, B, 20 + i) for i in range(3)]
+    results = []
+    for use_graph in (False, True):
+        eng = Engine(to_archspec(spec), max_batch=B, precision=precision, seed=77)
+        eng.load_numpy(P)
+        eng.set_graph(use_graph)
+        cfg = eng.opt_config(opt, lr=1e-3, weight_decay=1e-3)
+        eng.metrics_reset()
+        for s in range(steps):
+            x, bases, y = batches[s % 3]
+            eng.train_step(torch.from_numpy(x.astype(np.float32)), torch.from_numpy(bases), torch.from_numpy(y.astype(np.int32)), cfg)
+        torch.cuda.synchronize()
+        results.append((eng.params_numpy(), eng.metrics_read(), eng.launch_count, eng.opt_state()))
+    (pe, me, le, se), (pg, mg, lg, sg) = results
+    assert len(me) == len(mg) == steps and se == sg
+    assert lg == le, (lg, le)                         # the graph counts the kernels it replays
+    # same Philox draws (the step counter lives in device memory), same arithmetic; only atomic orders differ
+    tol = 1e-5 if precision == 'fp32' else 2e-2
+    for a, b in zip(me, mg):
+        assert abs(a['loss'] - b['loss']) <= tol * max(1.0, abs(a['loss']))
+    for k in pe:
+        if 'CNN_model' in k and k.endswith('.bias') and int(k.split('.')[-2]) % 5 == 0:
+            continue    # Conv1d bias behind BatchNorm: its gradient is pure rounding noise (analytically 0) that Adam normalises
+        d = np.abs(pe[k] - pg[k]).max()
+        assert d <= tol * max(1e-3, np.abs(pe[k]).max()), (k, d)
+
+
+def test_graph_host_entry_and_ragged_batches():
+    """train_step_host through graphs: one graph per batch size, metrics still delivered per step."""
+    import torch
+    from embrace_b200 import Engine
+    spec = ARCH_S
+    P = O.init_params(spec, 3)
+    eng = Engine(to_archspec(spec), max_batch=64, precision='bf16', seed=5)
+    eng.load_numpy(P)
+    eng.set_graph(True)
+    cfg = eng.opt_config('adam', lr=1e-3, weight_decay=1e-4)
+    losses = []
+    for s in range(12):
+        B = 64 if s % 3 else 40
+        x, bases, y = make_inputs(spec, B, 100 + s)
+        m = eng.train_step_host(np.ascontiguousarray(x.astype(np.float32)), bases, np.ascontiguousarray(y.astype(np.int32)), cfg)
+        losses.append(m.loss)
+        assert m.tp + m.fp + m.fn + m.tn == B
+    assert np.isfinite(losses).all()
+    eng.set_graph(False)
+    x, bases, y = make_inputs(spec, 64, 1)
+    m = eng.train_step_host(np.ascontiguousarray(x.astype(np.float32)), bases, np.ascontiguousarray(y.astype(np.int32)), cfg)
+    assert np.isfinite(m.loss)
