@@ -157,6 +157,7 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ['NCCL_DEBUG'] = os.environ.get('EMB_NCCL_DEBUG', 'WARN')     # stdout carries exactly one JSON line
         dist.init_process_group('nccl', device_id=dev)
     if args.batch % world:
         raise SystemExit('global batch must divide by the number of ranks')

@@ -132,11 +132,15 @@ class Engine:
     def set_allreduce(self, fn):
         """fn(tensor_float64) -> None performs an in-place SUM all-reduce of a device tensor (SyncBN statistics)."""
         base = self._ws_view.data_ptr()
+        views = {}                     # (offset, count) -> float64 view: the same few buffers come back every step
 
         def cb(user, ptr, count, stream):
             try:
-                off = ptr - base
-                fn(self._ws_view[off:off + count * 8].view(torch.float64))
+                key = (ptr - base, count)
+                t = views.get(key)
+                if t is None:
+                    t = views[key] = self._ws_view[key[0]:key[0] + count * 8].view(torch.float64)
+                fn(t)
                 return 0
             except Exception as ex:           # never unwind through C
                 print('allreduce callback failed:', ex)
