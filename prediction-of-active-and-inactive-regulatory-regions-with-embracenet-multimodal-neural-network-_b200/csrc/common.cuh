@@ -98,14 +98,20 @@ __device__ __forceinline__ double rng_uniform_f64(const RngState& s, uint32_t st
     return u32_to_unit_f64(rng_word(rng_raw(s, stream, elem >> 2), (uint32_t)elem & 3u));
 }
 
-// Dropout draws of the CNN stack ([B, C, Lpool] in the reference's layout): one Philox block serves the four pooled
-// positions j = 4q .. 4q+3 of a (row, channel), so a thread walking j refreshes its block every fourth step.
-__device__ __forceinline__ uint4 rng_cnn_block(const RngState& s, uint32_t stream, uint64_t global_row, int C, int c, int Lp, int jq) {
-    const uint64_t q_per_row = (uint64_t)((Lp + 3) >> 2);
-    return rng_raw(s, stream, (global_row * C + c) * q_per_row + jq);
+// Dropout draws of the CNN stack ([B, C, Lpool] in the reference's layout): ONE Philox block serves a channel PAIR x four
+// pooled positions j = 4q .. 4q+3 as eight 16-bit uniforms (word j & 3: low half = even channel, high half = odd channel).
+// The generator dominated the instruction count of the pooling kernel with one 32-bit draw per element (two blocks per
+// thread and four positions); a 16-bit keep/drop decision quantises p to 1/65536.
+__device__ __forceinline__ uint4 rng_cnn_block(const RngState& s, uint32_t stream, uint64_t global_row, int C, int cpair, int Lp, int jq) {
+    const uint64_t q_per_row = (uint64_t)((Lp + 3) >> 2), pairs = (uint64_t)((C + 1) >> 1);
+    return rng_raw(s, stream, (global_row * pairs + cpair) * q_per_row + jq);
+}
+__device__ __forceinline__ float rng_cnn_u16(const uint4& r, uint32_t jj, uint32_t odd) {
+    const uint32_t w = rng_word(r, jj);
+    return ((float)(odd ? (w >> 16) : (w & 0xFFFFu)) + 0.5f) * (1.0f / 65536.0f);      // (0, 1), exact in fp32
 }
 __device__ __forceinline__ float rng_cnn_uniform(const RngState& s, uint32_t stream, uint64_t global_row, int C, int c, int Lp, int j) {
-    return u32_to_unit_f32(rng_word(rng_cnn_block(s, stream, global_row, C, c, Lp, j >> 2), (uint32_t)j & 3u));
+    return rng_cnn_u16(rng_cnn_block(s, stream, global_row, C, c >> 1, Lp, j >> 2), (uint32_t)j & 3u, (uint32_t)c & 1u);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

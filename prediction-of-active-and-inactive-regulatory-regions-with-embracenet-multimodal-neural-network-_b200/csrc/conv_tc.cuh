@@ -30,6 +30,8 @@ struct TcConvParams {
     int n_tile, grid_m, grid_n, total_tiles;
     int a_slot_bytes, a_box_bytes;
     int b_slot_bytes, b_boxes, b_box_bytes, b_stages, b_resident;
+    int b_tail, b_tail_slot_bytes, b_tail_box_bytes;   // dgrad, resident: the last K chunk has < 64 rows and uses its own (smaller) box
+    uint32_t b_tail_lbo_bytes;
     uint32_t b_kstep16, b_lbo_bytes;     // descriptor advance per UMMA K step (in 16-byte units), LBO
     uint32_t idesc, tmem_cols;
     int acc_stride;
@@ -40,13 +42,15 @@ constexpr int TCV_A_SLOTS = 2;
 constexpr int TCV_MAX_B_STAGES = 8;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_conv_reuse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcConvParams p,
-                     const Epilogue ep) {
+tc_conv_reuse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const __grid_constant__ CUtensorMap map_b2, const TcConvParams p, const Epilogue ep) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int n_bslots = p.b_resident ? p.taps * p.n_chunks : p.b_stages;
     uint8_t* smem_b = smem + TCV_A_SLOTS * p.a_slot_bytes;
-    uint64_t* bars = (uint64_t*)(smem_b + (size_t)n_bslots * p.b_slot_bytes);
+    const uint32_t b_tail_base = (uint32_t)((p.n_chunks - 1) * p.taps) * (uint32_t)p.b_slot_bytes;     // resident tail slots start here
+    const size_t b_total = p.b_resident && p.b_tail ? (size_t)b_tail_base + (size_t)p.taps * p.b_tail_slot_bytes : (size_t)n_bslots * p.b_slot_bytes;
+    uint64_t* bars = (uint64_t*)(smem_b + b_total);
     uint64_t* a_full = bars;                       // [2]
     uint64_t* a_empty = a_full + TCV_A_SLOTS;      // [2]
     uint64_t* b_full = a_empty + TCV_A_SLOTS;      // [8]  (resident: b_full[0] covers every weight box)
@@ -96,9 +100,20 @@ tc_conv_reuse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             };
             if (p.b_resident) {
                 const uint32_t bar = smem_u32(&b_full[0]);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b_tx * (uint32_t)n_bslots) : "memory");
-                for (int c = 0; c < p.n_chunks; ++c)
+                const int full_chunks = p.b_tail ? p.n_chunks - 1 : p.n_chunks;
+                const uint32_t tail_tx = p.b_tail ? (uint32_t)(p.taps * p.b_boxes * p.b_tail_box_bytes) : 0u;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b_tx * (uint32_t)(full_chunks * p.taps) + tail_tx) : "memory");
+                for (int c = 0; c < full_chunks; ++c)
                     for (int t = 0; t < p.taps; ++t) load_b(sb0 + (uint32_t)((c * p.taps + t) * p.b_slot_bytes), bar, c, t, 0);
+                if (p.b_tail) {          // dgrad only: MN-major boxes {64 cin, 16 * k_steps_last cout rows, 1 tap} from the second tensor map
+                    const uint64_t mb2 = (uint64_t)&map_b2;
+                    const int c = p.n_chunks - 1;
+                    for (int t = 0; t < p.taps; ++t)
+                        for (int blk = 0; blk < p.b_boxes; ++blk)
+                            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                                         ::"r"(sb0 + b_tail_base + (uint32_t)(t * p.b_tail_slot_bytes + blk * p.b_tail_box_bytes)), "l"(mb2), "r"(bar),
+                                           "r"(blk * 64), "r"(c * 64), "r"(t) : "memory");
+                }
             }
             int as = 0, bs = 0;
             uint32_t aphase = 0, bphase = 0;
@@ -134,6 +149,7 @@ tc_conv_reuse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // 128 x 96 x 16 MMA needs.
         const uint32_t da_hi = (uint32_t)(umma_desc(0, 16, 1024) >> 32), db_hi = (uint32_t)(umma_desc(0, p.b_lbo_bytes, 1024) >> 32);
         const uint32_t da_lo16 = (uint32_t)umma_desc(0, 16, 1024), db_lo16 = (uint32_t)umma_desc(0, p.b_lbo_bytes, 1024);   // LBO field (bits 16-29)
+        const uint32_t db_lo16_tail = (uint32_t)umma_desc(0, p.b_tail_lbo_bytes, 1024);
         const uint32_t sa0 = smem_u32(smem), sb0 = smem_u32(smem_b), idesc = p.idesc, bk = p.b_kstep16;
         const int taps = p.taps, n_chunks = p.n_chunks, resident = p.b_resident, b_stages = p.b_stages;
         const uint32_t a_slot = p.a_slot_bytes, b_slot = p.b_slot_bytes;
@@ -151,17 +167,20 @@ tc_conv_reuse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 tc_fence_after();
                 uint32_t a_lo = (((sa0 + (uint32_t)as * a_slot) & 0x3FFFFu) >> 4) + (uint32_t)shift0;
                 const int ks = (c == n_chunks - 1) ? p.k_steps_last : 4;
-                uint32_t b_res = ((sb0 + (uint32_t)(c * taps) * b_slot) & 0x3FFFFu) >> 4;
+                const bool tail = resident && p.b_tail && c == n_chunks - 1;
+                uint32_t b_res = ((tail ? sb0 + b_tail_base : sb0 + (uint32_t)(c * taps) * b_slot) & 0x3FFFFu) >> 4;
+                const uint32_t b_res_step = (tail ? (uint32_t)p.b_tail_slot_bytes : b_slot) >> 4;
+                const uint32_t db_lo = tail ? db_lo16_tail : db_lo16;
                 for (int t = 0; t < taps; ++t) {
                     uint32_t b_lo;
-                    if (resident) { b_lo = b_res; b_res += b_slot >> 4; }
+                    if (resident) { b_lo = b_res; b_res += b_res_step; }
                     else {
                         mbar_wait(&b_full[bs], bphase);
                         tc_fence_after();
                         b_lo = ((sb0 + (uint32_t)bs * b_slot) & 0x3FFFFu) >> 4;
                     }
                     if (!(p.debug & 1) && elect_one_sync()) {
-                        const uint64_t da0 = ((uint64_t)da_hi << 32) | (da_lo16 | a_lo), db0 = ((uint64_t)db_hi << 32) | (db_lo16 | b_lo);
+                        const uint64_t da0 = ((uint64_t)da_hi << 32) | (da_lo16 | a_lo), db0 = ((uint64_t)db_hi << 32) | (db_lo | b_lo);
                         tc_mma_f16(d_tmem, da0, db0, idesc, accumulate);
                         if (ks > 1) tc_mma_f16(d_tmem, da0 + 2, db0 + bk, idesc, 1u);
                         if (ks > 2) tc_mma_f16(d_tmem, da0 + 4, db0 + 2 * bk, idesc, 1u);
@@ -271,18 +290,32 @@ inline int tc_conv_reuse(const TcProblem& pr, const Epilogue& ep, cudaStream_t s
         p.b_kstep16 = (16 * 128) >> 4; p.b_lbo_bytes = p.b_box_bytes;
     }
     if (rc) return rc;
+    CUtensorMap mb2 = mb;
     p.idesc = make_idesc(0, dgrad ? 1 : 0, p.n_tile);
     p.acc_stride = p.n_tile <= 32 ? 32 : p.n_tile <= 64 ? 64 : p.n_tile <= 128 ? 128 : 256;
     p.tmem_cols = 2 * p.acc_stride;
     p.debug = getenv("EMB_CONV_DEBUG") ? atoi(getenv("EMB_CONV_DEBUG")) : 0;
     const int budget = tc_max_smem() - 2048 - TCV_A_SLOTS * p.a_slot_bytes;
-    const int all_b = p.taps * p.n_chunks * p.b_slot_bytes;
+    int all_b = p.taps * p.n_chunks * p.b_slot_bytes;
+    if (dgrad && p.k_steps_last < 4 && p.grid_n == 1 && all_b > budget) {
+        // the last K chunk holds only 16 * k_steps_last cout rows: give it its own, smaller box so that every tap of W fits
+        const int rows = 16 * p.k_steps_last;
+        const int tail_box = rows * 128, tail_slot = p.b_boxes * tail_box;
+        const int all_tail = p.taps * ((p.n_chunks - 1) * p.b_slot_bytes + tail_slot);
+        if (all_tail <= budget) {
+            rc = make_map(&mb2, pr.b, pr.Cin, pr.Cout, pr.taps, pr.ldb, (int64_t)pr.Cout * pr.ldb, 64, rows, 1);
+            if (rc) return rc;
+            p.b_tail = 1; p.b_tail_box_bytes = tail_box; p.b_tail_slot_bytes = tail_slot; p.b_tail_lbo_bytes = tail_box;
+            all_b = all_tail;
+        }
+    }
     p.b_resident = (p.grid_n == 1 && all_b <= budget && !getenv("EMB_CONV_NO_RESIDENT")) ? 1 : 0;
+    if (!p.b_resident) p.b_tail = 0;
     p.b_stages = std::min(TCV_MAX_B_STAGES, budget / p.b_slot_bytes);
     if (!p.b_resident && p.b_stages < 2) return set_error(-5, "tc_conv_reuse: weight stage of %d bytes does not fit twice", p.b_slot_bytes);
     const size_t smem = (size_t)TCV_A_SLOTS * p.a_slot_bytes + (size_t)(p.b_resident ? all_b : p.b_stages * p.b_slot_bytes) + 1024 + 512;
     const int grid = std::min(p.total_tiles, tc_num_sms());
-    tc_conv_reuse_kernel<<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep);
+    tc_conv_reuse_kernel<<<grid, TC_THREADS, smem, st>>>(ma, mb, mb2, p, ep);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error(-3, "tc_conv_reuse launch failed: %s", cudaGetErrorString(err));
     return 0;

@@ -178,7 +178,7 @@ bn_relu_pool_drop_fwd_stream_kernel(const T* __restrict__ y, const float* __rest
     const float inv_keep = DROP ? 1.f / (1.f - drop_p) : 1.f;
     RngState rs = {0, 0};
     if (DROP == 2) rs = *rng;
-    uint4 blk0 = make_uint4(0, 0, 0, 0), blk1 = blk0;        // current Philox blocks of the two channels
+    uint4 blk0 = make_uint4(0, 0, 0, 0);                     // current Philox block of this channel pair
     float2 w0 = make_float2(0.f, 0.f), w1 = w0, w2 = w0, w3 = w0;   // relu folded in: window values start at 0
     const int n_pairs = Lp + 4;
 
@@ -198,11 +198,10 @@ bn_relu_pool_drop_fwd_stream_kernel(const T* __restrict__ y, const float* __rest
                     uy = drop_u[((size_t)b * C + c + 1) * Lp + j];
                 } else {
                     if ((j & 3) == 0) {                       // uniform across the warp: every thread refreshes at the same j
-                        blk0 = rng_cnn_block(rs, rng_stream, (uint64_t)(row_offset + b), C, c, Lp, j >> 2);
-                        blk1 = rng_cnn_block(rs, rng_stream, (uint64_t)(row_offset + b), C, c + 1, Lp, j >> 2);
+                        blk0 = rng_cnn_block(rs, rng_stream, (uint64_t)(row_offset + b), C, cp, Lp, j >> 2);
                     }
-                    ux = u32_to_unit_f32(rng_word(blk0, (uint32_t)j & 3u));
-                    uy = u32_to_unit_f32(rng_word(blk1, (uint32_t)j & 3u));
+                    ux = rng_cnn_u16(blk0, (uint32_t)j & 3u, 0u);
+                    uy = rng_cnn_u16(blk0, (uint32_t)j & 3u, 1u);
                 }
                 r.x = (ux >= drop_p) ? r.x * inv_keep : 0.f;
                 r.y = (uy >= drop_p) ? r.y * inv_keep : 0.f;

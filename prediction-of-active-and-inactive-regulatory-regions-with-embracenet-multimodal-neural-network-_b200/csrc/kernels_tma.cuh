@@ -311,7 +311,7 @@ bn_relu_pool_drop_fwd_tma_kernel(const PoolFwdArgs g) {
                 return m;
             };
             w0 = pm(j0); w1 = pm(j0 + 1); w2 = pm(j0 + 2); w3 = pm(j0 + 3);
-            uint4 blk0 = make_uint4(0, 0, 0, 0), blk1 = blk0;
+            uint4 blk0 = make_uint4(0, 0, 0, 0);
             for (int j = j0; j < j1; ++j) {
                 const float2 m = pm(j + 4);
                 float2 r;
@@ -319,11 +319,10 @@ bn_relu_pool_drop_fwd_tma_kernel(const PoolFwdArgs g) {
                 r.y = fmaxf(fmaxf(fmaxf(w0.y, w1.y), fmaxf(w2.y, w3.y)), m.y);
                 if (DROP == 2) {
                     if ((j & 3) == 0 || j == j0) {
-                        blk0 = rng_cnn_block(rs, g.rng_stream, (uint64_t)(g.row_offset + b), C, c, Lp, j >> 2);
-                        blk1 = rng_cnn_block(rs, g.rng_stream, (uint64_t)(g.row_offset + b), C, c + 1, Lp, j >> 2);
+                        blk0 = rng_cnn_block(rs, g.rng_stream, (uint64_t)(g.row_offset + b), C, cp, Lp, j >> 2);
                     }
-                    const float ux = u32_to_unit_f32(rng_word(blk0, (uint32_t)j & 3u));
-                    const float uy = u32_to_unit_f32(rng_word(blk1, (uint32_t)j & 3u));
+                    const float ux = rng_cnn_u16(blk0, (uint32_t)j & 3u, 0u);
+                    const float uy = rng_cnn_u16(blk0, (uint32_t)j & 3u, 1u);
                     r.x = (ux >= g.drop_p) ? r.x * inv_keep : 0.f;
                     r.y = (uy >= g.drop_p) ? r.y * inv_keep : 0.f;
                 }
