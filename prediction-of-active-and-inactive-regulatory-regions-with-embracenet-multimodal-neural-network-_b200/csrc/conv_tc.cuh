@@ -171,6 +171,39 @@ tc_conv_reuse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 uint32_t b_res = ((tail ? sb0 + b_tail_base : sb0 + (uint32_t)(c * taps) * b_slot) & 0x3FFFFu) >> 4;
                 const uint32_t b_res_step = (tail ? (uint32_t)p.b_tail_slot_bytes : b_slot) >> 4;
                 const uint32_t db_lo = tail ? db_lo16_tail : db_lo16;
+                if (resident) {
+                    // no per-tap barriers: every MMA of this chunk (taps x K steps) goes out of ONE elected region, so the
+                    // issuing thread spends a handful of uniform-datapath instructions per MMA (the per-tap loop below costs
+                    // ~100 cycles per tap, which bounds the narrow N = 64..96 layers whose MMAs take only 50 cycles)
+                    if (!(p.debug & 1) && elect_one_sync()) {
+                        uint64_t da = ((uint64_t)da_hi << 32) | (da_lo16 | a_lo);
+                        uint64_t db = ((uint64_t)db_hi << 32) | (db_lo | b_res);
+                        const int64_t da_step = (int64_t)dshift;
+                        const uint64_t db_step = (uint64_t)b_res_step;
+                        if (ks == 4) {
+#pragma unroll 1
+                            for (int t = 0; t < taps; ++t) {
+                                tc_mma_f16(d_tmem, da, db, idesc, accumulate);
+                                tc_mma_f16(d_tmem, da + 2, db + bk, idesc, 1u);
+                                tc_mma_f16(d_tmem, da + 4, db + 2 * bk, idesc, 1u);
+                                tc_mma_f16(d_tmem, da + 6, db + 3 * bk, idesc, 1u);
+                                accumulate = 1;
+                                da += da_step; db += db_step;
+                            }
+                        } else {
+#pragma unroll 1
+                            for (int t = 0; t < taps; ++t) {
+                                for (int s2 = 0; s2 < ks; ++s2) {
+                                    tc_mma_f16(d_tmem, da + (uint64_t)(2 * s2), db + (uint64_t)(s2 * bk), idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                                da += da_step; db += db_step;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    accumulate = 1;
+                } else
                 for (int t = 0; t < taps; ++t) {
                     uint32_t b_lo;
                     if (resident) { b_lo = b_res; b_res += b_res_step; }
