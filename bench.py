@@ -252,6 +252,12 @@ def main():
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
     peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback (B200_PROFILING.md)'
     achieved_tf = prof['flops'] / (prof['ms'] * 1e-3) / 1e12 if prof['ms'] > 0 else 0.0
+    # DRAM traffic of the GEMM kernel class per launch, from the committed ncu capture of this same command
+    # (profiles/summarize_launches.py -> profiles/r01_gemm_traffic.json); only valid for the default workload
+    traffic = None
+    tr_path = os.path.join(ROOT, 'profiles', 'r01_gemm_traffic.json')
+    if os.path.exists(tr_path) and args.arch == 'L' and args.batch == 8192 and world == 1:
+        traffic = json.load(open(tr_path)).get('gemm_dram_bytes_per_launch')
 
     value = args.batch * args.steps / (ms * 1e-3)
     e2e = args.batch * args.steps / (ms_e2e * 1e-3)
@@ -272,7 +278,9 @@ def main():
                 'h2d_bytes_per_step': int(args.batch * (F * 4 + 256 + 4)), 'd2h_bytes_per_step': 20 * world},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                     'frac': achieved_tf / peak_tf, 'traffic': None, 'kernel': 'GEMM class (conv implicit GEMM / docking / linear)',
+                     'frac': achieved_tf / peak_tf, 'traffic': traffic, 'traffic_unit': 'DRAM bytes per launch (ncu, mean over the class)',
+                     'algorithmic_flops_per_launch': prof['flops'] / max(prof['launches'], 1),
+                     'kernel': 'GEMM class: tc_gemm_kernel + tc_conv_reuse_kernel (conv implicit GEMMs, docking with the embracement epilogue, linear; fwd/dgrad/wgrad)',
                      'kernel_ms_per_step': prof['ms'] / args.steps, 'kernel_launches_per_step': prof['launches'] / args.steps,
                      'kernel_share_of_step': prof['ms'] / max(ms, 1e-9) if ms_clean >= ms else prof['ms'] / max(ms_clean, 1e-9),
                      'peak_source': peak_src},
