@@ -215,6 +215,11 @@ int emb_set_graph(EmbEngine* e, int32_t on);
  * partial sums into a device buffer and calls back between the stats and the finalize kernels. */
 typedef int (*EmbAllreduceFn)(void* user, double* device_buf, int64_t count, void* stream);
 int emb_set_allreduce(EmbEngine* e, EmbAllreduceFn fn, void* user);
+/* Called from emb_backward / emb_train_step with phase = 1 once every gradient OUTSIDE the CNN stack is complete (head, post,
+ * docking and FFNN layers), before the CNN backward is enqueued on `stream`: a data-parallel host starts the all-reduce of
+ * those slices of the gradient arena there, overlapped with the rest of the backward pass.  Return 0 on success. */
+typedef int (*EmbPhaseFn)(void* user, int32_t phase, void* stream);
+int emb_set_phase_hook(EmbEngine* e, EmbPhaseFn fn, void* user);
 
 /* ---- single-kernel entry points (unit tests and micro-benchmarks) ----------------------------*/
 /* K1: Conv1d(4->C1,k) over one-hot input as a gather-sum (CNN_pre.py:39 with in_channels=4).

@@ -54,6 +54,7 @@ class EmbStepMetrics(C.Structure):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+PHASE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_void_p)
 
 # every symbol include/embrace_b200.h declares: (restype, argtypes)
 _P = C.c_void_p
@@ -92,6 +93,7 @@ SIGNATURES = {
     'emb_profile_gemm': (C.c_int, [_P, C.c_int32]),
     'emb_profile_read': (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     'emb_set_allreduce': (C.c_int, [_P, ALLREDUCE_FN, _P]),
+    'emb_set_phase_hook': (C.c_int, [_P, PHASE_FN, _P]),
     'emb_k_onehot_conv_fwd': (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     'emb_k_onehot_conv_bwd': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     'emb_k_umma_shift_probe': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),

@@ -99,6 +99,12 @@ struct EmbEngine {
     Act gflat;                       // gradient w.r.t. the flattened CNN output (== cnn.back().ga)
     uint8_t* idx = nullptr;
     double* cum0 = nullptr;
+    // zero-before-use buffers, carved contiguously so that one memset per phase clears them
+    char *zero_fwd = nullptr, *zero_bwd = nullptr;        // [BatchNorm stats of all layers] / [backward stats + weight-gradient scratch]
+    int64_t zero_fwd_bytes = 0, zero_bwd_bytes = 0;
+    void* wc_table = nullptr;                              // device table (WcEntry[]) of the fused weight-cache refresh
+    int wc_entries = 0;
+    int64_t wc_total = 0;
     float *logits = nullptr, *dlogits = nullptr, *probs = nullptr;
     float* in_x = nullptr;           // staging for the *_host entries
     uint8_t* in_bases = nullptr;
@@ -122,6 +128,8 @@ struct EmbEngine {
     uint64_t seed = 0x5EEDull;
     EmbAllreduceFn allreduce = nullptr;
     void* allreduce_user = nullptr;
+    EmbPhaseFn phase_hook = nullptr;
+    void* phase_user = nullptr;
     int64_t launches = 0;
     // CUDA-graph replay of the whole train step (emb_set_graph): one instantiated graph per batch size
     struct StepGraph { int B; int has_opt; int opt_kind; int64_t kernels; cudaGraphExec_t exec; };
@@ -274,6 +282,41 @@ __global__ void wcache_conv_kernel(const float* __restrict__ w, bf16* __restrict
     out[i] = __float2bfloat16_rn(c < Cin ? w[((size_t)o * Cin + c) * taps + tap] : 0.f);
 }
 
+// All bf16 operand copies in ONE launch: a small device table lists the tensors; a thread finds its entry by a linear scan
+// over the (<= 32) start offsets.  kind 0: Linear [N][ldk] (optionally permuted to channels-last input order), 1: Conv [taps][Cout][ldc].
+struct WcEntry {
+    const float* src;
+    bf16* dst;
+    unsigned long long start, count;
+    int kind, N, K, ldk, perm, L, C, taps;
+};
+__global__ void wcache_fused_kernel(const WcEntry* __restrict__ tab, int n_entries, unsigned long long total) {
+    __shared__ WcEntry s_tab[32];
+    for (int i = threadIdx.x; i < n_entries; i += blockDim.x) s_tab[i] = tab[i];
+    __syncthreads();
+    for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (unsigned long long)gridDim.x * blockDim.x) {
+        int ei = 0;
+        while (ei + 1 < n_entries && g >= s_tab[ei + 1].start) ++ei;
+        const WcEntry& t = s_tab[ei];
+        const size_t i = (size_t)(g - t.start);
+        float v = 0.f;
+        if (t.kind == 0) {
+            const int n = (int)(i / t.ldk), kk = (int)(i - (size_t)n * t.ldk);
+            if (kk < t.K) {
+                int srck = kk;
+                if (t.perm) { const int l = kk / t.C, c = kk - l * t.C; srck = c * t.L + l; }
+                v = t.src[(size_t)n * t.K + srck];
+            }
+        } else {      // conv: N = Cout, K = Cin, ldk = ldc
+            const int c = (int)(i % t.ldk);
+            const size_t r = i / t.ldk;
+            const int o = (int)(r % t.N), tap = (int)(r / t.N);
+            if (c < t.K) v = t.src[((size_t)o * t.K + c) * t.taps + tap];
+        }
+        t.dst[i] = __float2bfloat16_rn(v);
+    }
+}
+
 // dW[n][c*L + l] = tmp[n][l*C + c]: the permuted-input Linear's weight gradient back to the reference's flatten order
 __global__ void unpermute_wgrad_kernel(const float* __restrict__ tmp, float* __restrict__ dw, int N, int L, int C) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -377,7 +420,6 @@ int64_t carve(EmbEngine* e, char* base) {
     if (e->prec == EMB_PREC_BF16) {
         auto wl = [&](LinearLayer& l) {
             l.wc = bp.take<bf16>((int64_t)l.out * round_up(l.in, 8));
-            if (l.perm_in) l.wg_tmp = bp.take<float>((int64_t)l.out * l.in);
         };
         for (auto& l : e->ffnn) wl(l);
         for (auto& l : e->post) wl(l);
@@ -385,7 +427,6 @@ int64_t carve(EmbEngine* e, char* base) {
         if (s.kind == EMB_KIND_EMBRACENET) { wl(e->dock0); wl(e->dock1); }
         for (size_t i = 1; i < e->cnn.size(); ++i) {
             e->cnn[i].wc = bp.take<bf16>((int64_t)e->cnn[i].k * e->cnn[i].cout * round_up(e->cnn[i].cin, 8));
-            e->cnn[i].wg_tmp = bp.take<float>((int64_t)e->cnn[i].k * e->cnn[i].cout * e->cnn[i].cin);
         }
     }
     if (s.kind != EMB_KIND_CNN) {
@@ -404,8 +445,26 @@ int64_t carve(EmbEngine* e, char* base) {
         c.shift = bp.take<float>(c.cout);
         c.mean = bp.take<float>(c.cout);
         c.rstd = bp.take<float>(c.cout);
-        c.stats = bp.take<double>(2 * c.cout);
-        c.bstats = bp.take<double>(2 * c.cout);
+    }
+    {   // the forward's zero region: BatchNorm sum / sum-of-squares of every layer
+        bp.off = round_up64(bp.off, 256);
+        const int64_t z0 = bp.off;
+        e->zero_fwd = base ? base + z0 : nullptr;
+        for (auto& c : e->cnn) c.stats = bp.take<double>(2 * c.cout);
+        e->zero_fwd_bytes = round_up64(bp.off, 256) - z0;
+        // the backward's zero region: backward BatchNorm sums and the weight-gradient scratch in operand layout
+        bp.off = round_up64(bp.off, 256);
+        const int64_t z1 = bp.off;
+        e->zero_bwd = base ? base + z1 : nullptr;
+        for (auto& c : e->cnn) c.bstats = bp.take<double>(2 * c.cout);
+        if (e->prec == EMB_PREC_BF16) {
+            for (size_t i = 1; i < e->cnn.size(); ++i) e->cnn[i].wg_tmp = bp.take<float>((int64_t)e->cnn[i].k * e->cnn[i].cout * e->cnn[i].cin);
+            auto wt = [&](LinearLayer& l) { if (l.perm_in) l.wg_tmp = bp.take<float>((int64_t)l.out * l.in); };
+            for (auto& l : e->head) wt(l);
+            if (s.kind == EMB_KIND_EMBRACENET) wt(e->dock1);
+        }
+        e->zero_bwd_bytes = round_up64(bp.off, 256) - z1;
+        e->wc_table = bp.take_bytes(32 * 128);
     }
     if (s.kind == EMB_KIND_EMBRACENET) {
         const int C = s.embracement_size;
@@ -525,30 +584,44 @@ bool tc_linear_ok(const EmbEngine* e, const LinearLayer& l) {
     return true;
 }
 
-int refresh_wcache(EmbEngine* e, cudaStream_t st) {
-    if (!tc_on(e)) return EMB_OK;
-    auto wl = [&](const LinearLayer& l) -> int {
-        if (!l.wc) return EMB_OK;
-        const int ldk = round_up(l.in, 8);
-        size_t tot = (size_t)l.out * ldk;
-        wcache_linear_kernel<<<cdiv(tot, 256), 256, 0, st>>>(e->params + l.w, l.wc, l.out, l.in, ldk, l.perm_in ? 1 : 0, e->cnn_Lp_last, e->cnn_C_last);
-        EMB_CHECK_LAUNCH();
-        LAUNCHED(e);
-        return EMB_OK;
+int build_wcache_table(EmbEngine* e) {
+    std::vector<WcEntry> tab;
+    unsigned long long cursor = 0;
+    auto wl = [&](const LinearLayer& l) {
+        if (!l.wc) return;
+        WcEntry t = {};
+        t.src = e->params + l.w; t.dst = l.wc; t.kind = 0; t.N = l.out; t.K = l.in; t.ldk = round_up(l.in, 8);
+        t.perm = l.perm_in ? 1 : 0; t.L = e->cnn_Lp_last; t.C = e->cnn_C_last; t.taps = 1;
+        t.start = cursor; t.count = (unsigned long long)l.out * t.ldk;
+        cursor += t.count;
+        tab.push_back(t);
     };
-    int rc;
-    for (auto& l : e->ffnn) if ((rc = wl(l))) return rc;
-    for (auto& l : e->post) if ((rc = wl(l))) return rc;
-    for (auto& l : e->head) if ((rc = wl(l))) return rc;
-    if (e->spec.kind == EMB_KIND_EMBRACENET) { if ((rc = wl(e->dock0))) return rc; if ((rc = wl(e->dock1))) return rc; }
+    for (auto& l : e->ffnn) wl(l);
+    for (auto& l : e->post) wl(l);
+    for (auto& l : e->head) wl(l);
+    if (e->spec.kind == EMB_KIND_EMBRACENET) { wl(e->dock0); wl(e->dock1); }
     for (size_t i = 1; i < e->cnn.size(); ++i) {
         ConvLayer& c = e->cnn[i];
-        const int ldc = round_up(c.cin, 8);
-        size_t tot = (size_t)c.k * c.cout * ldc;
-        wcache_conv_kernel<<<cdiv(tot, 256), 256, 0, st>>>(e->params + c.w, c.wc, c.cout, c.cin, c.k, ldc);
-        EMB_CHECK_LAUNCH();
-        LAUNCHED(e);
+        if (!c.wc) continue;
+        WcEntry t = {};
+        t.src = e->params + c.w; t.dst = c.wc; t.kind = 1; t.N = c.cout; t.K = c.cin; t.ldk = round_up(c.cin, 8); t.taps = c.k;
+        t.start = cursor; t.count = (unsigned long long)c.k * c.cout * t.ldk;
+        cursor += t.count;
+        tab.push_back(t);
     }
+    if (tab.size() > 32) return set_error(EMB_E_UNSUPPORTED, "too many weight tensors for the fused weight-cache refresh");
+    e->wc_entries = (int)tab.size();
+    e->wc_total = (int64_t)cursor;
+    if (!tab.empty()) EMB_CUDA_OK(cudaMemcpy(e->wc_table, tab.data(), tab.size() * sizeof(WcEntry), cudaMemcpyHostToDevice));
+    return EMB_OK;
+}
+
+int refresh_wcache(EmbEngine* e, cudaStream_t st) {
+    if (!tc_on(e) || e->wc_entries == 0) return EMB_OK;
+    const int grid = (int)std::min<int64_t>(148 * 16, cdiv(e->wc_total, 256));
+    wcache_fused_kernel<<<grid, 256, 0, st>>>((const WcEntry*)e->wc_table, e->wc_entries, (unsigned long long)e->wc_total);
+    EMB_CHECK_LAUNCH();
+    LAUNCHED(e);
     return EMB_OK;
 }
 
@@ -596,7 +669,6 @@ int linear_wgrad(EmbEngine* e, const LinearLayer& l, const void* g, int g_dtype,
         pr.M = l.out; pr.N = l.in; pr.K = B;
         if (l.perm_in && l.wg_tmp) {
             // accumulate in the engine's column order (coalesced), then un-permute once into the gradient arena
-            EMB_CUDA_OK(cudaMemsetAsync(l.wg_tmp, 0, (size_t)l.out * l.in * sizeof(float), st));
             Epilogue et = base_epi(e, EPI_ATOMIC, l.wg_tmp, l.in);
             rc = run_tc(e, pr, et, 2.0 * B * l.out * l.in, st);
             if (rc) return rc;
@@ -650,7 +722,6 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
             const int groups = c.cout / 8;
             if ((c.cout % 8) == 0 && (256 % groups) == 0) {
                 // vectorised gather-sum; BatchNorm statistics of layer 0 are accumulated by the same kernel
-                if (training) EMB_CUDA_OK(cudaMemsetAsync(c.stats, 0, 2 * c.cout * sizeof(double), st));
                 const int n_tp = (c.k + 1) / 2;
                 size_t smem = (size_t)(n_tp * 25 * c.cout + c.cout + 256 * 16) * sizeof(float) + SEQ_LEN + 2 * c.pad + 32;
                 int grid = std::min(B, 148 * 3);
@@ -686,7 +757,6 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
         const int64_t R = (int64_t)B * c.Lc;
         if (training) {
             if (!stats_done) {
-                EMB_CUDA_OK(cudaMemsetAsync(c.stats, 0, 2 * c.cout * sizeof(double), st));
                 if (even) {
                     dim3 grid(cdiv(c.cout / 2, 32), (unsigned)std::min<int64_t>(148 * 8 / std::max(1, cdiv(c.cout / 2, 32)), cdiv(R, 8)));
                     bn_stats_v2_kernel<T><<<grid, dim3(32, 8), 0, st>>>((const T*)c.y, c.stats, R, c.cout, c.ld);
@@ -752,7 +822,6 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
     for (int i = (int)e->cnn.size() - 1; i >= 0; --i) {
         ConvLayer& c = e->cnn[i];
         const int64_t R = (int64_t)B * c.Lc;
-        EMB_CUDA_OK(cudaMemsetAsync(c.bstats, 0, 2 * c.cout * sizeof(double), st));
         const bool even = (c.cout % 2) == 0;
         const bool kt = std::is_same<T, bf16>::value && kt_ok(c.cout, c.ld) && kt_bwd_smem(c.Lc, c.Lp, c.cout) <= (size_t)kt_max_smem() &&
                         !getenv("EMB_NO_TMA_K2");
@@ -849,7 +918,6 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
                 tp.M = c.cout; tp.N = c.cin; tp.B = B; tp.L = c.Lc; tp.Cin = c.cin; tp.Cout = c.cout; tp.taps = c.k; tp.pad = c.pad;
                 // accumulate as [tap][Cout][Cin] (coalesced atomics), then one permuted write-back into the gradient arena
                 const size_t wn = (size_t)c.k * c.cout * c.cin;
-                EMB_CUDA_OK(cudaMemsetAsync(c.wg_tmp, 0, wn * sizeof(float), st));
                 tp.wgrad_tap_stride = c.cout * c.cin;
                 Epilogue et = base_epi(e, EPI_ATOMIC, c.wg_tmp, c.cin);
                 rc = run_tc(e, tp, et, flops, st);
@@ -902,6 +970,7 @@ int forward_impl(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const 
     e->last_training = training;
     e->last_bases = bases;
     if ((rc = refresh_wcache(e, st))) return rc;
+    if (training && e->zero_fwd_bytes) EMB_CUDA_OK(cudaMemsetAsync(e->zero_fwd, 0, e->zero_fwd_bytes, st));
     const Act* ffnn_last = nullptr;
     if (s.kind != EMB_KIND_CNN) {
         if (!x_ffnn) return set_error(EMB_E_ARG, "x_ffnn is NULL");
@@ -1014,6 +1083,7 @@ int backward_impl(EmbEngine* e, const float* dlogits, cudaStream_t st) {
     if (!e->last_training || B < 1) return set_error(EMB_E_STATE, "emb_backward needs a preceding emb_forward_train");
     int rc;
     EMB_CUDA_OK(cudaMemsetAsync(e->grads, 0, e->n_params * sizeof(float), st));
+    if (e->zero_bwd_bytes) EMB_CUDA_OK(cudaMemsetAsync(e->zero_bwd, 0, e->zero_bwd_bytes, st));
     const void* g = dlogits;     // gradient w.r.t. the current layer's pre-activation
     int g_dt = 0, g_ld = 2;
 
@@ -1099,6 +1169,12 @@ int backward_impl(EmbEngine* e, const float* dlogits, cudaStream_t st) {
                 if (rc) return rc;
             }
         }
+    }
+    if (e->phase_hook) {
+        // every gradient outside the CNN stack is final here: a data-parallel host can start reducing those arena slices
+        // while the CNN backward (the bulk of the step) still runs
+        rc = e->phase_hook(e->phase_user, 1, (void*)st);
+        if (rc) return set_error(EMB_E_STATE, "phase hook failed (%d)", rc);
     }
     if (s.kind != EMB_KIND_FFNN) {
         rc = cnn_backward(e, B, st);
@@ -1218,6 +1294,7 @@ int emb_bind(EmbEngine* e, float* params, float* grads, float* buffers, float* o
         e->params = params; e->grads = grads; e->buffers = buffers; e->opt_m = opt_m; e->opt_v = opt_v; e->ws = (char*)workspace;
     }
     carve(e, e->ws);
+    if (e->prec == EMB_PREC_BF16) { int rcw = build_wcache_table(e); if (rcw) return rcw; }
     RngState rs{e->seed, 0};
     EMB_CUDA_OK(cudaMemcpy(e->rng, &rs, sizeof rs, cudaMemcpyHostToDevice));
     EMB_CUDA_OK(cudaMemset(e->rec_count, 0, sizeof(int)));
@@ -1263,6 +1340,13 @@ int emb_set_allreduce(EmbEngine* e, EmbAllreduceFn fn, void* user) {
     if (!e) return set_error(EMB_E_ARG, "null engine");
     e->allreduce = fn;
     e->allreduce_user = user;
+    return EMB_OK;
+}
+
+int emb_set_phase_hook(EmbEngine* e, EmbPhaseFn fn, void* user) {
+    if (!e) return set_error(EMB_E_ARG, "null engine");
+    e->phase_hook = fn;
+    e->phase_user = user;
     return EMB_OK;
 }
 
@@ -1453,7 +1537,7 @@ int emb_train_step(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, cons
     int rc = check_ready(e, B, true);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (e->graph_on && !draws && !e->allreduce && !e->prof_on && e->global_batch < 0) {
+    if (e->graph_on && !draws && !e->allreduce && !e->phase_hook && !e->prof_on && e->global_batch < 0) {
         // the first step of a batch size runs eagerly (one-time initialisation such as function attributes happens there)
         bool seen = false;
         for (int b : e->graph_seen) seen |= b == B;

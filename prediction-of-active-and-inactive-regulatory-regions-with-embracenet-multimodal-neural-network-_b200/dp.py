@@ -8,7 +8,8 @@ large-batch step:
                                        between its stats and finalize kernels (SyncBN); n is the GLOBAL B*L
   * per-batch class weights of the loss -> computed from the GLOBAL positive count (labels are known to the host)
   * random draws                    -> Philox counters are keyed by GLOBAL row, so the partition does not change them
-  * parameter gradients             -> ONE all-reduce (sum) of the flat fp32 gradient arena per step
+  * parameter gradients             -> all-reduce (sum) of the flat fp32 gradient arena, in two parts: the non-CNN slices
+                                       start while the CNN backward still runs (engine phase hook), the CNN slice follows
 No other collective exists on the path.
 """
 import torch
@@ -37,7 +38,7 @@ def merge_step_metrics(records, group=None):
 class DataParallel:
     """Wraps an Engine whose rows are this rank's shard of the global batch."""
 
-    def __init__(self, engine, global_batch, rank=None, world=None, group=None):
+    def __init__(self, engine, global_batch, rank=None, world=None, group=None, overlap=True):
         self.engine, self.group = engine, group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
@@ -45,6 +46,25 @@ class DataParallel:
         self.lo, self.hi = shard_rows(global_batch, self.rank, self.world)
         engine.set_shard(self.lo, global_batch)
         engine.set_allreduce(lambda t: dist.all_reduce(t, group=group))
+        # Gradient all-reduce in two parts: everything outside the CNN stack is final before the CNN backward starts, so
+        # those arena slices are reduced on a side stream while the CNN backward (most of the step) still runs.
+        pc = 'CNN.' if engine.spec.kind == 'embracenet' else 'CNN_model.'
+        self.cnn_lo, self.cnn_hi = engine.arena_range(pc)
+        self.overlap = overlap and dist.get_backend(group) == 'nccl' and self.cnn_hi > self.cnn_lo
+        self._pending = []
+        if self.overlap:
+            self.comm_stream = torch.cuda.Stream(device=engine.device)
+            engine.set_phase_hook(self._grads_ready)
+
+    def _grads_ready(self, phase):
+        g = self.engine.grads
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.engine.device))
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            for lo, hi in ((0, self.cnn_lo), (self.cnn_hi, g.numel())):
+                if hi > lo:
+                    self._pending.append(dist.all_reduce(g[lo:hi], group=self.group, async_op=True))
 
     def broadcast_parameters(self, src=0):
         dist.broadcast(self.engine.params, src, group=self.group)
@@ -54,5 +74,11 @@ class DataParallel:
         eng = self.engine
         eng.set_global_positives(n_pos_global)
         eng.train_step(x_local, bases_local, y_local, None)       # forward + loss + backward (SyncBN inside)
-        dist.all_reduce(eng.grads, group=self.group)               # the gradient all-reduce
+        if self.overlap:
+            dist.all_reduce(eng.grads[self.cnn_lo:self.cnn_hi], group=self.group)     # the CNN slice, after its backward
+            for w in self._pending:
+                w.wait()                                            # the current stream waits for the early slices
+            self._pending = []
+        else:
+            dist.all_reduce(eng.grads, group=self.group)           # the gradient all-reduce
         eng.opt_step(cfg)

@@ -148,6 +148,26 @@ class Engine:
         self._allreduce_cb = N.ALLREDUCE_FN(cb) if fn is not None else N.ALLREDUCE_FN()
         N.check(self.lib.emb_set_allreduce(self._h, self._allreduce_cb, None))
 
+    def set_phase_hook(self, fn):
+        """fn(phase) -> None is called from inside backward once the non-CNN gradients are final (phase 1)."""
+        def cb(user, phase, stream):
+            try:
+                fn(int(phase))
+                return 0
+            except Exception as ex:           # never unwind through C
+                print('phase hook failed:', ex)
+                return 1
+        self._phase_cb = N.PHASE_FN(cb) if fn is not None else N.PHASE_FN()
+        N.check(self.lib.emb_set_phase_hook(self._h, self._phase_cb, None))
+
+    def arena_range(self, prefix):
+        """[lo, hi) of the parameter-arena elements whose state_dict key starts with `prefix` (tensors are laid out in
+        state_dict order, so a module's parameters are contiguous)."""
+        ts = [t for t in self.table if not t['is_buffer'] and t['name'].startswith(prefix)]
+        if not ts:
+            return 0, 0
+        return min(t['offset'] for t in ts), max(t['offset'] + t['numel'] for t in ts)
+
     # ---- draws -----------------------------------------------------------------------------------
     def _draws(self, draws):
         """dict of replayed uniforms (numpy or torch, reference layouts) -> EmbDraws (device pointers)."""

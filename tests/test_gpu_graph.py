@@ -32,7 +32,7 @@ def test_graph_replay_matches_eager(precision, spec, opt):
     assert len(me) == len(mg) == steps and se == sg
     assert lg == le, (lg, le)                         # the graph counts the kernels it replays
     # same Philox draws (the step counter lives in device memory), same arithmetic; only atomic orders differ
-    tol = 1e-5 if precision == 'fp32' else 5e-2
+    tol = 1e-4 if precision == 'fp32' else 5e-2      # fp32: only the order of the split-K / wgrad atomics differs between the two runs
     for a, b in zip(me, mg):
         assert abs(a['loss'] - b['loss']) <= tol * max(1.0, abs(a['loss']))
     for k in pe:
@@ -41,7 +41,8 @@ def test_graph_replay_matches_eager(precision, spec, opt):
         d = np.abs(pe[k] - pg[k]).max()
         # bf16 storage makes the step chaotic at small batch: one rounding flip caused by a different atomic order
         # re-routes a max-pool gradient, and Adam-type optimizers turn a sign flip into 2*lr per step
-        bound = tol * max(1e-3, np.abs(pe[k]).max()) if precision == 'fp32' else 2 * 1e-3 * steps
+        # (RMSprop's first steps are lr / sqrt(1 - alpha) = 10 lr long)
+        bound = tol * max(1e-3, np.abs(pe[k]).max()) if precision == 'fp32' else (20 if opt == 'rmsprop' else 2) * 1e-3 * steps
         assert d <= bound, (k, d)
 
 
