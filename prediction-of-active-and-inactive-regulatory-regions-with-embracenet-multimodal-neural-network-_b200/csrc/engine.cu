@@ -63,6 +63,7 @@ struct ConvLayer {
     float* wg_tmp;               // weight gradient accumulated as [k][cout][cin] (coalesced atomics) before the permuted write-back
     // workspace
     void *y, *a, *dy, *ga;
+    uint8_t* amax;               // [B, Lp, cout] where each pooled element's gradient goes (written by the forward pooling kernel)
     float *scale, *shift, *mean, *rstd;
     double *stats, *bstats;
 };
@@ -441,6 +442,7 @@ int64_t carve(EmbEngine* e, char* base) {
         c.dy = bp.take_bytes(Bm * c.Lc * c.ld * es);
         c.a = bp.take_bytes(Bm * c.Lp * c.ld * es);
         c.ga = bp.take_bytes(Bm * c.Lp * c.ld * es);
+        c.amax = bp.take<uint8_t>(Bm * c.Lp * c.ld + 64);
         c.scale = bp.take<float>(c.cout);
         c.shift = bp.take<float>(c.cout);
         c.mean = bp.take<float>(c.cout);
@@ -780,23 +782,13 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
         size_t total = (size_t)B * c.Lp * c.cout;
         float p = training ? c.drop : 0.f;
         const float* du = (dr && p > 0.f) ? dr->cnn_drop[i] : nullptr;
-        const bool kt = std::is_same<T, bf16>::value && kt_ok(c.cout, c.ld) && !du && kt_fwd_smem(c.Lc, c.cout) <= (size_t)kt_max_smem() &&
-                        getenv("EMB_TMA_K2_FWD");     // instruction-bound on the Philox draws either way: the streaming kernel is faster
-        if (kt) {
-            // whole samples staged by bulk copies two ahead of the arithmetic (kernels_tma.cuh)
-            PoolFwdArgs a = {};
-            a.y = (const bf16*)c.y; a.scale = c.scale; a.shift = c.shift; a.a = (bf16*)c.a; a.rng = e->rng; a.row_offset = e->row_offset;
-            a.rng_stream = RNG_CNN_DROP + (uint32_t)i; a.B = B; a.Lc = c.Lc; a.Lp = c.Lp; a.C = c.cout; a.drop_p = p;
-            kt_segments(c.cout, c.Lp, 4, &a.nseg, &a.P);
-            const size_t smem = kt_fwd_smem(c.Lc, c.cout);
-            const int grid = std::min(B, tc_num_sms() * kt_ctas_per_sm(smem, 4));
-            if (p > 0.f) bn_relu_pool_drop_fwd_tma_kernel<2><<<grid, KT_THREADS, smem, st>>>(a);
-            else bn_relu_pool_drop_fwd_tma_kernel<0><<<grid, KT_THREADS, smem, st>>>(a);
-        } else if (even) {
+        const bool kt_bwd = std::is_same<T, bf16>::value && kt_ok(c.cout, c.ld) && kt_bwd_smem(c.Lc, c.Lp, c.cout) <= (size_t)kt_max_smem() &&
+                            !getenv("EMB_NO_TMA_K2");    // the backward will consume the arg-max codes
+        if (even) {
             const int blocks = cdiv((size_t)B * (c.cout / 2), 256);
 #define EMB_K2_FWD(MODE)                                                                                                          \
             bn_relu_pool_drop_fwd_stream_kernel<T, MODE><<<blocks, 256, 0, st>>>((const T*)c.y, c.scale, c.shift, (T*)c.a, B, c.Lc, c.Lp, \
-                                                                                c.cout, c.ld, p, du, e->rng, RNG_CNN_DROP + (uint32_t)i, e->row_offset)
+                                                                                c.cout, c.ld, p, du, e->rng, RNG_CNN_DROP + (uint32_t)i, e->row_offset, (training && kt_bwd) ? c.amax : nullptr)
             if (p <= 0.f) EMB_K2_FWD(0);
             else if (du) EMB_K2_FWD(1);
             else EMB_K2_FWD(2);
@@ -828,7 +820,7 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
         PoolBwdArgs ka = {};
         if (kt) {
             // pass 1 of 2: the BatchNorm reductions only; dz is recomputed (not stored) by pass 2 below
-            ka.y = (const bf16*)c.y; ka.a = (const bf16*)c.a; ka.ga = (const bf16*)c.ga; ka.scale = c.scale; ka.shift = c.shift;
+            ka.y = (const bf16*)c.y; ka.amax = c.amax; ka.ga = (const bf16*)c.ga; ka.scale = c.scale; ka.shift = c.shift;
             ka.mean = c.mean; ka.rstd = c.rstd; ka.gamma = e->params + c.gamma; ka.bstats_in = c.bstats; ka.bstats_out = c.bstats;
             ka.dy = (bf16*)c.dy; ka.dbias = e->grads + c.b; ka.B = B; ka.Lc = c.Lc; ka.Lp = c.Lp; ka.C = c.cout; ka.drop_p = c.drop;
             ka.n = (double)(e->global_batch > 0 ? e->global_batch : B) * c.Lc;
@@ -1308,8 +1300,6 @@ int emb_bind(EmbEngine* e, float* params, float* grads, float* buffers, float* o
     if (rc) return rc;
     EMB_CUDA_OK(cudaFuncSetAttribute(pool_bn_bwd_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kt_max_smem()));
     EMB_CUDA_OK(cudaFuncSetAttribute(pool_bn_bwd_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kt_max_smem()));
-    EMB_CUDA_OK(cudaFuncSetAttribute(bn_relu_pool_drop_fwd_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kt_max_smem()));
-    EMB_CUDA_OK(cudaFuncSetAttribute(bn_relu_pool_drop_fwd_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kt_max_smem()));
     return EMB_OK;
 }
 

@@ -166,7 +166,8 @@ template <typename T, int DROP>
 __global__ void __launch_bounds__(256)
 bn_relu_pool_drop_fwd_stream_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                                     T* __restrict__ a, int B, int Lc, int Lp, int C, int ld, float drop_p,
-                                    const float* __restrict__ drop_u, RngState const* rng, uint32_t rng_stream, int64_t row_offset) {
+                                    const float* __restrict__ drop_u, RngState const* rng, uint32_t rng_stream, int64_t row_offset,
+                                    uint8_t* __restrict__ amax) {
     const int pairs = C / 2;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)B * pairs) return;
@@ -180,17 +181,35 @@ bn_relu_pool_drop_fwd_stream_kernel(const T* __restrict__ y, const float* __rest
     if (DROP == 2) rs = *rng;
     uint4 blk0 = make_uint4(0, 0, 0, 0);                     // current Philox block of this channel pair
     float2 w0 = make_float2(0.f, 0.f), w1 = w0, w2 = w0, w3 = w0;   // relu folded in: window values start at 0
+    uint32_t sx = 0, sy = 0;                 // bit q: the pair held in window slot q has its (first) maximum at its SECOND position
     const int n_pairs = Lp + 4;
+    uint8_t* adst = amax ? amax + (size_t)b * Lp * C + c : nullptr;
 
     auto step = [&](int i, float2 u0, float2 u1) {
+        const float z0x = fmaxf(fmaf(u0.x, sc.x, sh.x), 0.f), z1x = fmaxf(fmaf(u1.x, sc.x, sh.x), 0.f);
+        const float z0y = fmaxf(fmaf(u0.y, sc.y, sh.y), 0.f), z1y = fmaxf(fmaf(u1.y, sc.y, sh.y), 0.f);
         float2 m;
-        m.x = fmaxf(fmaxf(fmaf(u0.x, sc.x, sh.x), fmaf(u1.x, sc.x, sh.x)), 0.f);
-        m.y = fmaxf(fmaxf(fmaf(u0.y, sc.y, sh.y), fmaf(u1.y, sc.y, sh.y)), 0.f);
+        m.x = fmaxf(z0x, z1x);
+        m.y = fmaxf(z0y, z1y);
+        if (amax) { sx |= (z1x > z0x ? 1u : 0u) << 4; sy |= (z1y > z0y ? 1u : 0u) << 4; }
         if (i >= 4) {
             const int j = i - 4;
             float2 r;
             r.x = fmaxf(fmaxf(fmaxf(w0.x, w1.x), fmaxf(w2.x, w3.x)), m.x);
             r.y = fmaxf(fmaxf(fmaxf(w0.y, w1.y), fmaxf(w2.y, w3.y)), m.y);
+            // where the max-pool gradient will go: offset (0..9) of the FIRST maximum inside the window, 255 = nowhere
+            // (window maximum not positive, or dropped below).  Consumed by pool_bn_bwd_tma_kernel.
+            uint32_t cx = 255u, cy = 255u;
+            if (amax) {
+                // first slot that attains the maximum r: independent equality tests instead of a running-maximum chain
+                int bx = 4, by = 4;
+                bx = w3.x == r.x ? 3 : bx; by = w3.y == r.y ? 3 : by;
+                bx = w2.x == r.x ? 2 : bx; by = w2.y == r.y ? 2 : by;
+                bx = w1.x == r.x ? 1 : bx; by = w1.y == r.y ? 1 : by;
+                bx = w0.x == r.x ? 0 : bx; by = w0.y == r.y ? 0 : by;
+                if (r.x > 0.f) cx = 2u * bx + ((sx >> bx) & 1u);
+                if (r.y > 0.f) cy = 2u * by + ((sy >> by) & 1u);
+            }
             if (DROP) {
                 float ux, uy;
                 if (DROP == 1) {
@@ -203,12 +222,14 @@ bn_relu_pool_drop_fwd_stream_kernel(const T* __restrict__ y, const float* __rest
                     ux = rng_cnn_u16(blk0, (uint32_t)j & 3u, 0u);
                     uy = rng_cnn_u16(blk0, (uint32_t)j & 3u, 1u);
                 }
-                r.x = (ux >= drop_p) ? r.x * inv_keep : 0.f;
-                r.y = (uy >= drop_p) ? r.y * inv_keep : 0.f;
+                if (ux >= drop_p) r.x *= inv_keep; else { r.x = 0.f; cx = 255u; }
+                if (uy >= drop_p) r.y *= inv_keep; else { r.y = 0.f; cy = 255u; }
             }
             st2(dst + (size_t)j * ld, r);
+            if (amax) *reinterpret_cast<uint16_t*>(adst + (size_t)j * C) = (uint16_t)(cx | (cy << 8));
         }
         w0 = w1; w1 = w2; w2 = w3; w3 = m;
+        sx >>= 1; sy >>= 1;
     };
 
     int i = 0;
