@@ -58,9 +58,12 @@ tc_conv_reuse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint64_t* tfull_bar = b_empty + TCV_MAX_B_STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+    float* s_stats = (float*)((uint8_t*)bars + 512);           // [2][N] BatchNorm accumulators (only with ep.bn_stats)
+    const bool bn_on = ep.bn_stats != nullptr && ep.mode == EPI_LINEAR;
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
+    if (bn_on) for (int i = threadIdx.x; i < 8 * p.N; i += TC_THREADS) s_stats[i] = 0.f;
     {   // halo / tail rows of the A slots must read as zero
         uint4 z = make_uint4(0, 0, 0, 0);
         for (int i = threadIdx.x; i < TCV_A_SLOTS * p.a_slot_bytes / 16; i += TC_THREADS) ((uint4*)smem)[i] = z;
@@ -254,6 +257,7 @@ tc_conv_reuse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 if (n_base + c0 >= p.N) break;
                 float v[16];
                 tc_ld16(t_addr + (uint32_t)c0, v);
+                if (bn_on) tc_bn_stats16(ep, s_stats + q * 2 * p.N, p.N, n_base + c0, p.N, row_ok, v, lane);
                 if (row_ok && !(p.debug & 4)) tc_epilogue_row16(ep, m, n_base + c0, 0, p.M, p.N, p.N, v);
             }
             tc_fence_before();
@@ -264,6 +268,8 @@ tc_conv_reuse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    if (bn_on) for (int i = threadIdx.x; i < 2 * p.N; i += TC_THREADS)
+        atomicAdd(&ep.bn_stats[i], (double)s_stats[i] + (double)s_stats[2 * p.N + i] + (double)s_stats[4 * p.N + i] + (double)s_stats[6 * p.N + i]);
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
@@ -328,7 +334,8 @@ inline int tc_conv_reuse(const TcProblem& pr, const Epilogue& ep, cudaStream_t s
     p.acc_stride = p.n_tile <= 32 ? 32 : p.n_tile <= 64 ? 64 : p.n_tile <= 128 ? 128 : 256;
     p.tmem_cols = 2 * p.acc_stride;
     p.debug = getenv("EMB_CONV_DEBUG") ? atoi(getenv("EMB_CONV_DEBUG")) : 0;
-    const int budget = tc_max_smem() - 2048 - TCV_A_SLOTS * p.a_slot_bytes;
+    const int stats_bytes = ep.bn_stats ? round_up(8 * N * 4, 128) : 0;      // [4 epilogue warps][2][N] floats
+    const int budget = tc_max_smem() - 2048 - stats_bytes - TCV_A_SLOTS * p.a_slot_bytes;
     int all_b = p.taps * p.n_chunks * p.b_slot_bytes;
     if (dgrad && p.k_steps_last < 4 && p.grid_n == 1 && all_b > budget) {
         // the last K chunk holds only 16 * k_steps_last cout rows: give it its own, smaller box so that every tap of W fits
@@ -346,7 +353,7 @@ inline int tc_conv_reuse(const TcProblem& pr, const Epilogue& ep, cudaStream_t s
     if (!p.b_resident) p.b_tail = 0;
     p.b_stages = std::min(TCV_MAX_B_STAGES, budget / p.b_slot_bytes);
     if (!p.b_resident && p.b_stages < 2) return set_error(-5, "tc_conv_reuse: weight stage of %d bytes does not fit twice", p.b_slot_bytes);
-    const size_t smem = (size_t)TCV_A_SLOTS * p.a_slot_bytes + (size_t)(p.b_resident ? all_b : p.b_stages * p.b_slot_bytes) + 1024 + 512;
+    const size_t smem = (size_t)TCV_A_SLOTS * p.a_slot_bytes + (size_t)(p.b_resident ? all_b : p.b_stages * p.b_slot_bytes) + 1024 + 512 + stats_bytes;
     const int grid = std::min(p.total_tiles, tc_num_sms());
     tc_conv_reuse_kernel<<<grid, TC_THREADS, smem, st>>>(ma, mb, mb2, p, ep);
     cudaError_t err = cudaGetLastError();

@@ -750,6 +750,10 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
                 TcProblem pr = {};
                 pr.kind = TC_CONV_FWD; pr.a = (const bf16*)pr_.a; pr.lda = pr_.ld; pr.b = c.wc; pr.ldb = round_up(c.cin, 8);
                 pr.M = B * c.Lc; pr.N = c.cout; pr.B = B; pr.L = c.Lc; pr.Cin = c.cin; pr.Cout = c.cout; pr.taps = c.k; pr.pad = c.pad;
+                if (training && c.cout <= 512 && getenv("EMB_EPI_STATS")) {
+                    ep.bn_stats = c.stats;         // BatchNorm batch statistics accumulated by the GEMM epilogue: no separate pass over y
+                    stats_done = true;
+                }
                 rc = run_tc(e, pr, ep, 2.0 * B * c.Lc * c.cout * c.k * c.cin, st);
             } else {
                 rc = run_gemm(e, A, W, ep, B * c.Lc, c.cout, c.k * c.cin, 1, st);

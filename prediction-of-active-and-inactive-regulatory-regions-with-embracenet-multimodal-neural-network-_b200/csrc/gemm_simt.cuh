@@ -125,6 +125,9 @@ struct Epilogue {
     void* out2;
     // EPI_ATOMIC
     int map, mapC, mapL, map_taps, map_wrows;
+    // tensor-core conv forward only: per-column sum / sum of squares of the STORED (bf16-rounded) outputs, i.e. the
+    // BatchNorm batch statistics of the layer, accumulated in the epilogue ([N] sums then [N] sums of squares)
+    double* bn_stats;
 };
 
 __device__ __forceinline__ void epilogue_apply(const Epilogue& ep, int m, int n, int M, int N, float acc) {

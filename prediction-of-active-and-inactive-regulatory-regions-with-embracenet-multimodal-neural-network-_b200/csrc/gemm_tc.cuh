@@ -282,6 +282,76 @@ __device__ __forceinline__ void tc_epilogue_row16(const Epilogue& ep, int m, int
     }
 }
 
+// Column sums over the 32 rows a warp holds (16 columns per lane): a transpose-reduce butterfly -- each step halves the
+// number of columns a lane carries while doubling the rows folded into them (8 + 4 + 2 + 1 + 1 = 16 shuffles instead of
+// 16 x 5).  On return lane l holds the total of column ((l >> 1) & 15) ... precisely: column index col16_of_lane(l).
+__device__ __forceinline__ float warp_colsum16(const float* v, int lane) {
+    float a[8];
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float send = hi ? v[i] : v[i + 8], keep = hi ? v[i + 8] : v[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    float b[4];
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = hi ? a[i] : a[i + 4], keep = hi ? a[i + 4] : a[i];
+            b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    float c2[2];
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = hi ? b[i] : b[i + 2], keep = hi ? b[i + 2] : b[i];
+            c2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    float d;
+    {
+        const bool hi = lane & 2;
+        const float send = hi ? c2[0] : c2[1], keep = hi ? c2[1] : c2[0];
+        d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;      // column = 8 * bit4 + 4 * bit3 + 2 * bit2 + bit1 of the lane index
+}
+__device__ __forceinline__ int col16_of_lane(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+
+// BatchNorm statistics of a conv forward tile chunk: v = the 16 fp32 accumulators of this lane's row (bias not yet added).
+// s_warp: this warp's PRIVATE [2][n_stat] accumulators (plain read-modify-write by one lane per column: no atomics).
+__device__ __forceinline__ void tc_bn_stats16(const Epilogue& ep, float* s_warp, int n_stat, int n0, int N, bool row_ok, const float* v, int lane) {
+    float r[16], q[16];
+    const bool full = n0 + 16 <= N;
+    float b[16];
+    if (full && ep.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float4 t = __ldg(b4 + i); b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) b[i] = (ep.bias && n0 + i < N) ? __ldg(ep.bias + n0 + i) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float x = (row_ok && n0 + i < N) ? __bfloat162float(__float2bfloat16_rn(v[i] + b[i])) : 0.f;
+        r[i] = x;
+        q[i] = x * x;
+    }
+    const float s1 = warp_colsum16(r, lane), s2 = warp_colsum16(q, lane);
+    if (!(lane & 1)) {
+        const int n = n0 + col16_of_lane(lane);
+        if (n < N) { s_warp[n] += s1; s_warp[n_stat + n] += s2; }
+    }
+    __syncwarp();
+}
+
 // Persistent: one CTA per SM walks the tile list; two TMEM accumulator stages let the epilogue of tile i
 // overlap the main loop of tile i+1.
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -299,6 +369,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
+    const bool bn_on = ep.bn_stats != nullptr && ep.mode == EPI_LINEAR;       // the transpose scratch holds [4 warps][2][N] accumulators (N <= 512)
+    if (bn_on) for (int i = threadIdx.x; i < 8 * p.N; i += TC_THREADS) epi_scratch[i] = 0.f;
     if (p.zero_smem) {
         uint4 z = make_uint4(0, 0, 0, 0);
         for (int i = threadIdx.x; i < p.stages * stage_bytes / 16; i += TC_THREADS) ((uint4*)smem)[i] = z;
@@ -500,6 +572,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (n_base + c0 >= p.N) break;                          // warp-uniform
                     float v[16];
                     tc_ld16(t_addr + (uint32_t)(t * p.n_tile + c0), v);
+                    if (bn_on) tc_bn_stats16(ep, epi_scratch + q * 2 * p.N, p.N, n_base + c0, p.N, row_ok, v, lane);
                     if (row_ok) tc_epilogue_row16(ep, m, n_base + c0, n_off, p.M, p.N, p.n_logical, v);
                 }
             }
@@ -512,6 +585,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #undef TC_DECODE_TILE
     tc_fence_before();
     __syncthreads();
+    if (bn_on) for (int i = threadIdx.x; i < 2 * p.N; i += TC_THREADS)
+        atomicAdd(&ep.bn_stats[i], (double)epi_scratch[i] + (double)epi_scratch[2 * p.N + i] + (double)epi_scratch[4 * p.N + i] + (double)epi_scratch[6 * p.N + i]);
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
