@@ -167,6 +167,20 @@ def test_arch_M_tensor_core_four_conv_layers():
         del CASES['archM_tc']
 
 
+@pytest.mark.parametrize('arch,B', [('L', 40), ('W', 36), ('S', 130)])
+def test_benchmark_archs_tensor_core_full_step(arch, B):
+    """The benchmark architectures themselves (L = largest point of the search space, W = widest docking): every
+    production path at once -- resident / streamed tap-reuse convolutions, multi-tap wgrad (4, 5 and 8 taps per CTA), the
+    dgrad tail-chunk box, coalesced split-K atomics, the arg-max-code pooling backward -- against the bf16-emulating oracle."""
+    from tests.golden.cases import ARCH_L, ARCH_W
+    spec = {'L': ARCH_L, 'W': ARCH_W, 'S': ARCH_S}[arch]
+    CASES['bench_arch'] = dict(spec=spec, B=B, seed=123, steps=1, force_modal=[False], lr=1e-3, wd=1e-3)
+    try:
+        print(arch, run_case('bench_arch', 'bf16', tensor_core=True, B_override=B))
+    finally:
+        del CASES['bench_arch']
+
+
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 def test_eval_forward_and_predict(precision):
     import torch

@@ -66,7 +66,8 @@ def conv_ref(x_blc, W):
     return np.transpose(y, (0, 2, 1))
 
 
-CONV_SHAPES = [(3, 124, 64, 96, 15), (7, 58, 96, 256, 15), (11, 25, 256, 512, 5), (5, 124, 32, 32, 11), (4, 58, 16, 64, 5), (9, 25, 64, 128, 11)]
+CONV_SHAPES = [(3, 124, 64, 96, 15), (7, 58, 96, 256, 15), (11, 25, 256, 512, 5), (5, 124, 32, 32, 11), (4, 58, 16, 64, 5), (9, 25, 64, 128, 11),
+               (6, 25, 256, 512, 15), (10, 8, 128, 256, 15), (5, 124, 16, 32, 15)]
 
 
 @pytest.mark.parametrize('backend', [0, 1])
