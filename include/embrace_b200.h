@@ -29,19 +29,19 @@
 extern "C" {
 #endif
 
-#define EMB_ABI_VERSION 1
+#define EMB_ABI_VERSION 2
 
 #define EMB_MAX_FFNN 4   /* FFNN_pre.py:19  suggest_int("FFNN_n_layers", 1, 4) */
 #define EMB_MAX_CNN 4    /* CNN_pre.py:24   suggest_int("CNN_n_layers", 1, 4)  */
-#define EMB_MAX_POST 2   /* EmbraceNetMultimodal.py:135 suggest_int("n_post_layers", 0, 2) */
+#define EMB_MAX_POST 3   /* EmbraceNetMultimodal.py:135 n_post_layers in 0..2; ConcatNetMultimodal.py:42 CONCATNET_n_post_layers in 1..3 */
 #define EMB_SEQ_LEN 256  /* CNN_pre.py:21 */
 #define EMB_POOL_K 10    /* CNN_pre.py:18 */
 #define EMB_POOL_S 2     /* CNN_pre.py:20 */
 
 enum { EMB_OK = 0, EMB_E_ARG = -1, EMB_E_NO_DEVICE = -2, EMB_E_CUDA = -3, EMB_E_STATE = -4, EMB_E_UNSUPPORTED = -5 };
 
-/* model kind: EmbraceNetMultimodal.py:94 / FF_net.py:8 / CNN_net.py:10 */
-enum { EMB_KIND_EMBRACENET = 0, EMB_KIND_FFNN = 1, EMB_KIND_CNN = 2 };
+/* model kind: EmbraceNetMultimodal.py:94 / FF_net.py:8 / CNN_net.py:10 / ConcatNetMultimodal.py:12 */
+enum { EMB_KIND_EMBRACENET = 0, EMB_KIND_FFNN = 1, EMB_KIND_CNN = 2, EMB_KIND_CONCATNET = 3 };
 /* arithmetic of activations and GEMM operands (accumulation, BN statistics, loss, master
  * weights and optimizer state are always fp32) */
 enum { EMB_PREC_FP32 = 0, EMB_PREC_BF16 = 1 };

@@ -101,11 +101,11 @@ def param_shapes(spec):
     """Ordered {state_dict key: shape} exactly as the reference nn.Sequential
     builds them (checkpoint row)."""
     kind = spec.get('kind', 'embracenet')
-    pre_f = 'FFNN.model.' if kind == 'embracenet' else 'model.'
-    pre_c = 'CNN.CNN_model.' if kind == 'embracenet' else 'CNN_model.'
+    pre_f = 'FFNN.model.' if kind in ('embracenet', 'concatnet') else 'model.'
+    pre_c = 'CNN.CNN_model.' if kind in ('embracenet', 'concatnet') else 'CNN_model.'
     shp = {}
     fin = spec.get('F', 0)
-    if kind in ('embracenet', 'ffnn'):
+    if kind in ('embracenet', 'concatnet', 'ffnn'):
         for i, u in enumerate(spec['ffnn_units']):
             shp[f'{pre_f}{3*i}.weight'] = (u, fin)
             shp[f'{pre_f}{3*i}.bias'] = (u,)
@@ -114,7 +114,7 @@ def param_shapes(spec):
             n = len(spec['ffnn_units'])
             shp[f'{pre_f}{3*n}.weight'] = (2, fin)
             shp[f'{pre_f}{3*n}.bias'] = (2,)
-    if kind in ('embracenet', 'cnn'):
+    if kind in ('embracenet', 'concatnet', 'cnn'):
         cin = N_BASES
         for i, (co, k) in enumerate(zip(spec['cnn_channels'], spec['cnn_kernels'])):
             shp[f'{pre_c}{5*i}.weight'] = (co, cin, k)
@@ -133,6 +133,15 @@ def param_shapes(spec):
             shp['last_layer2.bias'] = (64,)
             shp['last_output.weight'] = (2, 64)
             shp['last_output.bias'] = (2,)
+    if kind == 'concatnet':      # ConcatNetMultimodal.py:38-62: post over cat(FFNN out, CNN out)
+        fin = spec['ffnn_units'][-1] + cnn_out
+        for i, u in enumerate(spec['post_units']):
+            shp[f'post.{3*i}.weight'] = (u, fin)
+            shp[f'post.{3*i}.bias'] = (u,)
+            fin = u
+        n = len(spec['post_units'])
+        shp[f'post.{3*n}.weight'] = (2, fin)
+        shp[f'post.{3*n}.bias'] = (2,)
     if kind == 'embracenet':
         C = spec['C']
         shp['embracenet.docking_0.weight'] = (C, spec['ffnn_units'][-1])
@@ -436,8 +445,8 @@ class EarlyStopping:
 # --------------------------------------------------------------------------
 def _keys(spec):
     kind = spec.get('kind', 'embracenet')
-    pre_f = 'FFNN.model.' if kind == 'embracenet' else 'model.'
-    pre_c = 'CNN.CNN_model.' if kind == 'embracenet' else 'CNN_model.'
+    pre_f = 'FFNN.model.' if kind in ('embracenet', 'concatnet') else 'model.'
+    pre_c = 'CNN.CNN_model.' if kind in ('embracenet', 'concatnet') else 'CNN_model.'
     return kind, pre_f, pre_c
 
 
@@ -540,6 +549,19 @@ def forward(spec, P, x_ffnn, bases, draws=None, training=False, availabilities=N
     B = x_ffnn.shape[0]
     xf = ffnn_forward(spec, P, x_ffnn, draws, training, cache)
     xc = cnn_forward(spec, P, bases, draws, training, cache, cache['new_buffers'])
+    if kind == 'concatnet':      # ConcatNetMultimodal.forward (:65-82): post(cat(FFNN(x1), CNN(x2)))
+        h = np.concatenate([xf, xc], axis=1)
+        cache.update(xf=xf, xc=xc)
+        cache['post'] = []
+        for i, (u, p) in enumerate(zip(spec['post_units'], spec['post_dropout'])):
+            pre = linear_fwd(h, _q(P[f'post.{3*i}.weight']), P[f'post.{3*i}.bias'])
+            r = np.maximum(pre, 0.0)
+            out, keep = dropout_fwd(r, draws['post_drop'][i] if (training and p > 0) else None, p, training)
+            cache['post'].append((h, pre, keep, p))
+            h = _q(out)
+        n = len(spec['post_units'])
+        cache['head_in'] = h
+        return linear_fwd(h, _q(P[f'post.{3*n}.weight']), P[f'post.{3*n}.bias']), cache
     if training and embracenet_dropout:
         av = modality_dropout_availabilities(B, draws['modal_u0'], draws.get('modal_rows'))
         if av is not None:
@@ -597,6 +619,12 @@ def backward(spec, P, dlogits, bases, cache):
         G[f'post.{3*i}.weight'] = g.T @ h
         G[f'post.{3*i}.bias'] = g.sum(axis=0)
         g = g @ _q(P[f'post.{3*i}.weight'])
+    if kind == 'concatnet':
+        g = _q(g)
+        fo = cache['xf'].shape[1]
+        ffnn_backward(spec, P, g[:, :fo], cache, G)
+        cnn_backward(spec, P, g[:, fo:], bases, cache, G)
+        return G
     idx = cache['idx']
     dd0 = _q(g * (idx == 0) * (cache['pre0'] > 0))
     dd1 = _q(g * (idx == 1) * (cache['pre1'] > 0))
@@ -687,12 +715,15 @@ def make_draws(spec, B, seed, force_modal=None):
     rs = np.random.RandomState(seed)
     kind = spec.get('kind', 'embracenet')
     d = {'ffnn_drop': [], 'cnn_drop': [], 'post_drop': []}
-    if kind in ('embracenet', 'ffnn'):
+    if kind in ('embracenet', 'concatnet', 'ffnn'):
         for u in spec['ffnn_units']:
             d['ffnn_drop'].append(rs.random_sample((B, u)).astype(np.float32))
-    if kind in ('embracenet', 'cnn'):
+    if kind in ('embracenet', 'concatnet', 'cnn'):
         for co, (_, Lp) in zip(spec['cnn_channels'], cnn_lengths(spec['cnn_kernels'])):
             d['cnn_drop'].append(rs.random_sample((B, co, Lp)).astype(np.float32))
+    if kind == 'concatnet':
+        for u in spec['post_units']:
+            d['post_drop'].append(rs.random_sample((B, u)).astype(np.float32))
     if kind == 'embracenet':
         u0 = np.float32(rs.random_sample())
         if force_modal is not None:

@@ -4,6 +4,7 @@ from .FF_net import FFNN
 from .CNN_pre import CNN_pre, CNN_pre_NoTrain
 from .FFNN_pre import FFNN_pre, FFNN_pre_NoTrain
 from .EmbraceNetMultimodal import EmbraceNet, EmbraceNetMultimodal, EmbraceNetMultimodal_NoTrain
+from .ConcatNetMultimodal import ConcatNetMultimodal, ConcatNetMultimodal_NoTrain
 
 __all__ = ['CNN', 'FFNN', 'CNN_pre', 'FFNN_pre', 'EmbraceNetMultimodal', 'CNN_pre_NoTrain', 'FFNN_pre_NoTrain',
-           'EmbraceNetMultimodal_NoTrain', 'EmbraceNet']
+           'EmbraceNetMultimodal_NoTrain', 'EmbraceNet', 'ConcatNetMultimodal', 'ConcatNetMultimodal_NoTrain']

@@ -14,8 +14,8 @@ LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libembrace_sm100.so')
 INCLUDE = os.path.join(REPO, 'include')
 
-EMB_MAX_FFNN, EMB_MAX_CNN, EMB_MAX_POST = 4, 4, 2
-KIND = {'embracenet': 0, 'ffnn': 1, 'cnn': 2}
+EMB_MAX_FFNN, EMB_MAX_CNN, EMB_MAX_POST = 4, 4, 3
+KIND = {'embracenet': 0, 'ffnn': 1, 'cnn': 2, 'concatnet': 3}
 PREC = {'fp32': 0, 'bf16': 1}
 OPT = {'adam': 0, 'adamw': 1, 'nadam': 2, 'rmsprop': 3}
 

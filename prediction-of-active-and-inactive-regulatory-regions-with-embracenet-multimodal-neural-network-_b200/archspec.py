@@ -16,6 +16,7 @@ FFNN_UNITS = [[32, 64, 128, 256], [16, 32, 64, 128], [4, 16, 32, 64], [4, 16, 32
 CNN_CHANNELS = [[16, 32, 64], [32, 64, 96], [64, 96, 128, 256], [128, 256, 512]]
 CNN_KERNELS = [5, 11, 15]
 POST_UNITS = [[32, 64, 128, 256, 512], [16, 32, 64, 128, 256]]
+CONCAT_UNITS = [[512, 768, 1024], [32, 64, 128, 256, 512], [16, 32, 64, 128, 256]]     # ConcatNetMultimodal.py:46-52
 SEQ_LEN, POOL_K, POOL_S = 256, 10, 2
 
 
@@ -71,6 +72,12 @@ class ArchSpec:
                 s.post_units.append(trial.suggest_categorical(f'EMBRACENET_n_units_l{i}', POST_UNITS[i]))
                 s.post_dropout.append(trial.suggest_categorical(f'EMBRACENET_dropout_l{i}', [0.0, 0.2, 0.3, 0.5]))
             s.p_ffnn = trial.suggest_float('selection_probabilities_FFNN', 0.0, 1.0)
+        elif kind == 'concatnet':          # ConcatNetMultimodal.py:33-58
+            s.ffnn_units, s.ffnn_dropout = cls.suggest_ffnn(trial, 'FFNN_')
+            s.cnn_channels, s.cnn_kernels, s.cnn_dropout = cls.suggest_cnn(trial, 'CNN_')
+            for i in range(trial.suggest_int('CONCATNET_n_post_layers', 1, 3)):
+                s.post_units.append(trial.suggest_categorical(f'CONCATNET_n_units_l{i}', CONCAT_UNITS[i]))
+                s.post_dropout.append(trial.suggest_categorical(f'CONCATNET_dropout_l{i}', [0.0, 0.2, 0.3, 0.5]))
         elif kind == 'ffnn':
             s.ffnn_units, s.ffnn_dropout = cls.suggest_ffnn(trial, '')
         elif kind == 'cnn':
@@ -84,12 +91,12 @@ class ArchSpec:
         """model_params: the trial-parameter dict stored in a reference checkpoint."""
         mp = model_params
         s = cls(kind=kind, in_features=int(in_features_FFNN or 0), embracenet_dropout=embracenet_dropout)
-        pf, pc = ('FFNN_', 'CNN_') if kind == 'embracenet' else ('', '')
-        if kind in ('embracenet', 'ffnn'):
+        pf, pc = ('FFNN_', 'CNN_') if kind in ('embracenet', 'concatnet') else ('', '')
+        if kind in ('embracenet', 'concatnet', 'ffnn'):
             for i in range(int(mp[f'{pf}n_layers'])):
                 s.ffnn_units.append(int(mp[f'{pf}n_units_l{i}']))
                 s.ffnn_dropout.append(float(mp[f'{pf}dropout_l{i}']))
-        if kind in ('embracenet', 'cnn'):
+        if kind in ('embracenet', 'concatnet', 'cnn'):
             for i in range(int(mp[f'{pc}n_layers'])):
                 s.cnn_channels.append(int(mp[f'{pc}out_channels_l{i}']))
                 s.cnn_kernels.append(int(mp[f'{pc}kernel_size_l{i}']))
@@ -100,16 +107,20 @@ class ArchSpec:
                 s.post_units.append(int(mp[f'EMBRACENET_n_units_l{i}']))
                 s.post_dropout.append(float(mp[f'EMBRACENET_dropout_l{i}']))
             s.p_ffnn = float(mp['selection_probabilities_FFNN'])
+        if kind == 'concatnet':
+            for i in range(int(mp['CONCATNET_n_post_layers'])):
+                s.post_units.append(int(mp[f'CONCATNET_n_units_l{i}']))
+                s.post_dropout.append(float(mp[f'CONCATNET_dropout_l{i}']))
         return s.validate()
 
     def to_model_params(self):
-        pf, pc = ('FFNN_', 'CNN_') if self.kind == 'embracenet' else ('', '')
+        pf, pc = ('FFNN_', 'CNN_') if self.kind in ('embracenet', 'concatnet') else ('', '')
         mp = {}
-        if self.kind in ('embracenet', 'ffnn'):
+        if self.kind in ('embracenet', 'concatnet', 'ffnn'):
             mp[f'{pf}n_layers'] = len(self.ffnn_units)
             for i, (u, p) in enumerate(zip(self.ffnn_units, self.ffnn_dropout)):
                 mp[f'{pf}n_units_l{i}'], mp[f'{pf}dropout_l{i}'] = u, p
-        if self.kind in ('embracenet', 'cnn'):
+        if self.kind in ('embracenet', 'concatnet', 'cnn'):
             mp[f'{pc}n_layers'] = len(self.cnn_channels)
             for i, (c, k, p) in enumerate(zip(self.cnn_channels, self.cnn_kernels, self.cnn_dropout)):
                 mp[f'{pc}out_channels_l{i}'], mp[f'{pc}kernel_size_l{i}'], mp[f'{pc}dropout_l{i}'] = c, k, p
@@ -119,14 +130,18 @@ class ArchSpec:
             for i, (u, p) in enumerate(zip(self.post_units, self.post_dropout)):
                 mp[f'EMBRACENET_n_units_l{i}'], mp[f'EMBRACENET_dropout_l{i}'] = u, p
             mp['selection_probabilities_FFNN'] = self.p_ffnn
+        if self.kind == 'concatnet':
+            mp['CONCATNET_n_post_layers'] = len(self.post_units)
+            for i, (u, p) in enumerate(zip(self.post_units, self.post_dropout)):
+                mp[f'CONCATNET_n_units_l{i}'], mp[f'CONCATNET_dropout_l{i}'] = u, p
         return mp
 
     # ---- derived shapes --------------------------------------------------------------------
     def validate(self):
         if self.kind not in N.KIND:
             raise ValueError(f'unknown model kind {self.kind!r}')
-        if len(self.ffnn_units) > 4 or len(self.cnn_channels) > 4 or len(self.post_units) > 2:
-            raise ValueError('too many layers (FFNN<=4, CNN<=4, post<=2)')
+        if len(self.ffnn_units) > 4 or len(self.cnn_channels) > 4 or len(self.post_units) > (3 if self.kind == 'concatnet' else 2):
+            raise ValueError('too many layers (FFNN<=4, CNN<=4, post<=2; ConcatNet post<=3)')
         for k in self.cnn_kernels:
             if k % 2 == 0:
                 raise ValueError('only odd kernel sizes ("same" padding) are supported')

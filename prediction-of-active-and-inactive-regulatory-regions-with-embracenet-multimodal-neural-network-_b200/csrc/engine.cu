@@ -51,7 +51,9 @@ struct LinearLayer {
     int64_t w, b;     // offsets into the params arena
     float drop;
     bool relu;
-    bool perm_in;     // input is the channels-last flattened CNN activation (docking_1, last_layer1)
+    bool perm_in;     // weight columns follow the reference's flatten order c*L + l while the engine's activation is l*C + c
+    bool flat_in;     // the input operand IS the in-place channels-last CNN activation (docking_1, last_layer1)
+    int perm_off;     // leading weight columns that are NOT permuted (ConcatNet: the FFNN part of the concatenation)
 };
 
 struct ConvLayer {
@@ -96,6 +98,7 @@ struct EmbEngine {
 
     // workspace carve-out
     Act x0, d0, e, dd0, dd1;
+    Act xcat, gcat;                  // ConcatNet: cat(FFNN out, flattened CNN out) in engine column order, and its gradient
     std::vector<Act> ffnn_h, ffnn_g, post_h, post_g, head_h, head_g;
     Act gflat;                       // gradient w.r.t. the flattened CNN output (== cnn.back().ga)
     uint8_t* idx = nullptr;
@@ -171,7 +174,7 @@ void add_tensor(EmbEngine* e, const std::string& name, std::initializer_list<int
 
 LinearLayer add_linear(EmbEngine* e, const std::string& prefix, int in, int out, float drop, bool relu, bool perm_in) {
     LinearLayer l{};
-    l.in = in; l.out = out; l.drop = drop; l.relu = relu; l.perm_in = perm_in;
+    l.in = in; l.out = out; l.drop = drop; l.relu = relu; l.perm_in = perm_in; l.flat_in = perm_in; l.perm_off = 0;
     add_tensor(e, prefix + ".weight", {out, in}, false, &l.w);
     add_tensor(e, prefix + ".bias", {out}, false, &l.b);
     return l;
@@ -179,7 +182,8 @@ LinearLayer add_linear(EmbEngine* e, const std::string& prefix, int in, int out,
 
 int plan(EmbEngine* e) {
     const EmbArchSpec& s = e->spec;
-    const bool emb_kind = s.kind == EMB_KIND_EMBRACENET;
+    const bool cat_kind = s.kind == EMB_KIND_CONCATNET;
+    const bool emb_kind = s.kind == EMB_KIND_EMBRACENET || cat_kind;     // both carry the FFNN. / CNN. prefixes
     const std::string pf = emb_kind ? "FFNN.model." : "model.";
     const std::string pc = emb_kind ? "CNN.CNN_model." : "CNN_model.";
     if (s.kind != EMB_KIND_CNN) {
@@ -226,7 +230,17 @@ int plan(EmbEngine* e) {
             e->head.push_back(add_linear(e, "last_output", 64, 2, 0.f, false, false));
         }
     }
-    if (emb_kind) {
+    if (cat_kind) {
+        // ConcatNetMultimodal.py:36-62: post = (Linear -> ReLU -> Dropout) x n (1..3) -> Linear(-> 2) over cat(FFNN, CNN)
+        if (s.n_post < 1 || s.n_post > EMB_MAX_POST) return set_error(EMB_E_ARG, "ConcatNet needs 1..%d post layers", EMB_MAX_POST);
+        int in = e->ffnn_out + e->cnn_out;
+        for (int i = 0; i < s.n_post; ++i) {
+            e->post.push_back(add_linear(e, "post." + std::to_string(3 * i), in, s.post_units[i], s.post_dropout[i], true, false));
+            if (i == 0) { e->post[0].perm_in = true; e->post[0].perm_off = e->ffnn_out; }     // the CNN columns are in c*L + l order
+            in = s.post_units[i];
+        }
+        e->head.push_back(add_linear(e, "post." + std::to_string(3 * s.n_post), in, 2, 0.f, false, false));
+    } else if (emb_kind) {
         const int C = s.embracement_size;
         if (C < 1 || s.n_post < 0 || s.n_post > EMB_MAX_POST || s.p_ffnn < 0 || s.p_ffnn > 1) return set_error(EMB_E_ARG, "bad EmbraceNet spec");
         e->dock0 = add_linear(e, "embracenet.docking_0", e->ffnn_out, C, 0.f, true, false);
@@ -305,7 +319,7 @@ __global__ void wcache_fused_kernel(const WcEntry* __restrict__ tab, int n_entri
             const int n = (int)(i / t.ldk), kk = (int)(i - (size_t)n * t.ldk);
             if (kk < t.K) {
                 int srck = kk;
-                if (t.perm) { const int l = kk / t.C, c = kk - l * t.C; srck = c * t.L + l; }
+                if (t.perm && kk >= t.taps) { const int k2 = kk - t.taps, l = k2 / t.C, c = k2 - l * t.C; srck = t.taps + c * t.L + l; }
                 v = t.src[(size_t)n * t.K + srck];
             }
         } else {      // conv: N = Cout, K = Cin, ldk = ldc
@@ -319,14 +333,16 @@ __global__ void wcache_fused_kernel(const WcEntry* __restrict__ tab, int n_entri
 }
 
 // dW[n][c*L + l] = tmp[n][l*C + c]: the permuted-input Linear's weight gradient back to the reference's flatten order
-__global__ void unpermute_wgrad_kernel(const float* __restrict__ tmp, float* __restrict__ dw, int N, int L, int C) {
+__global__ void unpermute_wgrad_kernel(const float* __restrict__ tmp, float* __restrict__ dw, int N, int L, int C, int off) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t K = (size_t)L * C;
+    const size_t K = (size_t)off + (size_t)L * C;       // `off` leading columns are not permuted (ConcatNet)
     if (i >= (size_t)N * K) return;
     size_t n = i / K;
     int r = (int)(i - n * K);
+    if (r < off) { dw[i] = tmp[i]; return; }
+    r -= off;
     int c = r / L, l = r - c * L;                        // destination index walks the reference layout (coalesced writes)
-    dw[i] = tmp[n * K + (size_t)l * C + c];
+    dw[i] = tmp[n * K + off + (size_t)l * C + c];
 }
 
 // dW[o][c][tap] = tmp[tap][o][c]: the conv weight gradient back to the reference's [Cout, Cin, k] layout
@@ -400,6 +416,35 @@ head_dgrad_kernel(const float* __restrict__ dl, const float* __restrict__ w, int
     epilogue_apply(ep, b, k, B, K, fmaf(dl[2 * b], w0, dl[2 * b + 1] * w1));
 }
 
+// ConcatNet (ConcatNetMultimodal.py:74): cat(FFNN out [B, fo], flattened CNN out) in engine column order (l*C + c)
+template <typename T>
+__global__ void concat_kernel(const T* __restrict__ f, int ldf, int fo, const T* __restrict__ a, int Lp, int C, int lda,
+                              T* __restrict__ out, int ldo, int B) {
+    const size_t K = (size_t)fo + (size_t)Lp * C;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * K) return;
+    const size_t b = i / K;
+    const int k = (int)(i - b * K);
+    if (k < fo) { out[b * ldo + k] = f[b * ldf + k]; return; }
+    const int k2 = k - fo, l = k2 / C, c = k2 - l * C;
+    out[b * ldo + k] = a[(b * Lp + l) * lda + c];
+}
+// ... and its backward: the FFNN part goes through the ReLU / Dropout mask of the last FFNN layer, the CNN part is the
+// gradient of the flattened pooled output
+template <typename T>
+__global__ void concat_split_kernel(const T* __restrict__ g, int ldg, int fo, const T* __restrict__ href, int ldh, float scale,
+                                    T* __restrict__ gf, int ldgf, T* __restrict__ ga, int Lp, int C, int lda, int B) {
+    const size_t K = (size_t)fo + (size_t)Lp * C;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * K) return;
+    const size_t b = i / K;
+    const int k = (int)(i - b * K);
+    const float v = to_f(g[b * ldg + k]);
+    if (k < fo) { gf[b * ldgf + k] = from_f<T>(to_f(href[b * ldh + k]) > 0.f ? v * scale : 0.f); return; }
+    const int k2 = k - fo, l = k2 / C, c = k2 - l * C;
+    ga[(b * Lp + l) * lda + c] = from_f<T>(v);
+}
+
 // carve the workspace; with base == nullptr only the size is computed
 int64_t carve(EmbEngine* e, char* base) {
     Bump bp{base};
@@ -463,10 +508,19 @@ int64_t carve(EmbEngine* e, char* base) {
             for (size_t i = 1; i < e->cnn.size(); ++i) e->cnn[i].wg_tmp = bp.take<float>((int64_t)e->cnn[i].k * e->cnn[i].cout * e->cnn[i].cin);
             auto wt = [&](LinearLayer& l) { if (l.perm_in) l.wg_tmp = bp.take<float>((int64_t)l.out * l.in); };
             for (auto& l : e->head) wt(l);
+            for (auto& l : e->post) wt(l);
             if (s.kind == EMB_KIND_EMBRACENET) wt(e->dock1);
         }
         e->zero_bwd_bytes = round_up64(bp.off, 256) - z1;
         e->wc_table = bp.take_bytes(32 * 128);
+    }
+    if (s.kind == EMB_KIND_CONCATNET) {
+        e->xcat = take_act(bp, Bm, e->ffnn_out + e->cnn_out, es);
+        e->gcat = take_act(bp, Bm, e->ffnn_out + e->cnn_out, es);
+        for (auto& l : e->post) {
+            e->post_h.push_back(take_act(bp, Bm, l.out, es));
+            e->post_g.push_back(take_act(bp, Bm, l.out, es));
+        }
     }
     if (s.kind == EMB_KIND_EMBRACENET) {
         const int C = s.embracement_size;
@@ -515,7 +569,7 @@ Operand weight_operand(EmbEngine* e, const LinearLayer& l, bool transposed) {
     } else {
         o = transposed ? make_operand(e->params + l.w, 0, OP_W_PERM_T, 0, l.in, l.out)
                        : make_operand(e->params + l.w, 0, OP_W_PERM, 0, l.out, l.in);
-        o.L = e->cnn_Lp_last; o.C = e->cnn_C_last; o.wrows = l.in;
+        o.L = e->cnn_Lp_last; o.C = e->cnn_C_last; o.wrows = l.in; o.perm_off = l.perm_off;
     }
     o.round_bf16 = e->prec == EMB_PREC_BF16;
     return o;
@@ -525,7 +579,7 @@ Operand weight_operand(EmbEngine* e, const LinearLayer& l, bool transposed) {
 Operand input_operand(EmbEngine* e, const LinearLayer& l, const Act& in, int B, bool transposed) {
     Operand o;
     const int dt = dtype_of(e);
-    if (!l.perm_in) {
+    if (!l.flat_in) {
         o = transposed ? make_operand(in.p, dt, OP_TRANSPOSED, in.ld, l.in, B) : make_operand(in.p, dt, OP_ROWMAJOR, in.ld, B, l.in);
     } else {
         o = transposed ? make_operand(in.p, dt, OP_FLAT_ACT_T, e->cnn_ld_last, l.in, B)
@@ -582,7 +636,7 @@ bool tc_on(const EmbEngine* e) { return e->use_tc && e->prec == EMB_PREC_BF16; }
 // can this Linear layer's GEMMs run on the tensor-core kernel?  (the flattened CNN input must be dense)
 bool tc_linear_ok(const EmbEngine* e, const LinearLayer& l) {
     if (!tc_on(e) || l.out < 16 || l.in < 16) return false;
-    if (l.perm_in && e->cnn_ld_last != e->cnn_C_last) return false;
+    if (l.flat_in && e->cnn_ld_last != e->cnn_C_last) return false;
     return true;
 }
 
@@ -593,7 +647,7 @@ int build_wcache_table(EmbEngine* e) {
         if (!l.wc) return;
         WcEntry t = {};
         t.src = e->params + l.w; t.dst = l.wc; t.kind = 0; t.N = l.out; t.K = l.in; t.ldk = round_up(l.in, 8);
-        t.perm = l.perm_in ? 1 : 0; t.L = e->cnn_Lp_last; t.C = e->cnn_C_last; t.taps = 1;
+        t.perm = l.perm_in ? 1 : 0; t.L = e->cnn_Lp_last; t.C = e->cnn_C_last; t.taps = l.perm_off;     // taps doubles as the un-permuted prefix
         t.start = cursor; t.count = (unsigned long long)l.out * t.ldk;
         cursor += t.count;
         tab.push_back(t);
@@ -654,7 +708,7 @@ int linear_wgrad(EmbEngine* e, const LinearLayer& l, const void* g, int g_dtype,
     Operand A = make_operand(g, g_dtype, OP_TRANSPOSED, g_ld, l.out, B);
     Operand X = input_operand(e, l, in, B, true);
     Epilogue ep = base_epi(e, EPI_ATOMIC, e->grads + l.w, l.in);
-    if (l.perm_in) { ep.map = MAP_W_PERM; ep.mapC = e->cnn_C_last; ep.mapL = e->cnn_Lp_last; ep.map_wrows = l.in; }
+    if (l.perm_in) { ep.map = MAP_W_PERM; ep.mapC = e->cnn_C_last; ep.mapL = e->cnn_Lp_last; ep.map_wrows = l.in; ep.map_off = l.perm_off; }
     int rc;
     if (l.out == 2 && g_dtype == 0 && g_ld == 2 && !l.perm_in) {
         // the 2-logit head: weight and bias gradient in one small kernel
@@ -675,7 +729,7 @@ int linear_wgrad(EmbEngine* e, const LinearLayer& l, const void* g, int g_dtype,
             rc = run_tc(e, pr, et, 2.0 * B * l.out * l.in, st);
             if (rc) return rc;
             size_t tot = (size_t)l.out * l.in;
-            unpermute_wgrad_kernel<<<cdiv(tot, 256), 256, 0, st>>>(l.wg_tmp, e->grads + l.w, l.out, e->cnn_Lp_last, e->cnn_C_last);
+            unpermute_wgrad_kernel<<<cdiv(tot, 256), 256, 0, st>>>(l.wg_tmp, e->grads + l.w, l.out, e->cnn_Lp_last, e->cnn_C_last, l.perm_off);
             EMB_CHECK_LAUNCH();
             LAUNCHED(e);
         } else {
@@ -1036,6 +1090,22 @@ int forward_impl(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const 
             in = &e->post_h[i];
         }
         head_in = in;
+    } else if (s.kind == EMB_KIND_CONCATNET) {
+        const size_t tot = (size_t)B * (e->ffnn_out + e->cnn_out);
+        if (dt) concat_kernel<bf16><<<cdiv(tot, 256), 256, 0, st>>>((const bf16*)ffnn_last->p, ffnn_last->ld, e->ffnn_out, (const bf16*)flat.p, e->cnn_Lp_last,
+                                                                 e->cnn_C_last, e->cnn_ld_last, (bf16*)e->xcat.p, e->xcat.ld, B);
+        else concat_kernel<float><<<cdiv(tot, 256), 256, 0, st>>>((const float*)ffnn_last->p, ffnn_last->ld, e->ffnn_out, (const float*)flat.p, e->cnn_Lp_last,
+                                                                 e->cnn_C_last, e->cnn_ld_last, (float*)e->xcat.p, e->xcat.ld, B);
+        EMB_CHECK_LAUNCH();
+        LAUNCHED(e);
+        const Act* in = &e->xcat;
+        for (size_t i = 0; i < e->post.size(); ++i) {
+            const float* du = (dr && training && e->post[i].drop > 0) ? dr->post_drop[i] : nullptr;
+            rc = linear_forward(e, e->post[i], *in, e->post_h[i], B, training, du, RNG_POST_DROP + (uint32_t)i, st);
+            if (rc) return rc;
+            in = &e->post_h[i];
+        }
+        head_in = in;
     } else if (s.kind == EMB_KIND_FFNN) {
         head_in = ffnn_last;
     } else {
@@ -1130,6 +1200,29 @@ int backward_impl(EmbEngine* e, const float* dlogits, cudaStream_t st) {
             rc = linear_dgrad(e, e->dock1, e->dd1.p, dt, e->dd1.ld, B, ep, st);
             if (rc) return rc;
         }
+    } else if (s.kind == EMB_KIND_CONCATNET) {
+        const LinearLayer& hl = e->head.back();
+        const int np = (int)e->post.size(), nf = (int)e->ffnn.size();
+        rc = linear_wgrad(e, hl, g, g_dt, g_ld, e->post_h[np - 1], B, st);
+        if (rc) return rc;
+        rc = linear_dgrad(e, hl, g, g_dt, g_ld, B, mask_epi(e->post_h[np - 1], e->post[np - 1].drop, e->post_g[np - 1]), st);
+        if (rc) return rc;
+        for (int i = np - 1; i >= 0; --i) {
+            const Act& in = i ? e->post_h[i - 1] : e->xcat;
+            rc = linear_wgrad(e, e->post[i], e->post_g[i].p, dt, e->post_g[i].ld, in, B, st);
+            if (rc) return rc;
+            if (i) rc = linear_dgrad(e, e->post[i], e->post_g[i].p, dt, e->post_g[i].ld, B, mask_epi(e->post_h[i - 1], e->post[i - 1].drop, e->post_g[i - 1]), st);
+            else rc = linear_dgrad(e, e->post[i], e->post_g[i].p, dt, e->post_g[i].ld, B, base_epi(e, EPI_LINEAR, e->gcat.p, e->gcat.ld), st);
+            if (rc) return rc;
+        }
+        const size_t tot = (size_t)B * (e->ffnn_out + e->cnn_out);
+        const float scale = e->ffnn[nf - 1].drop > 0.f ? 1.f / (1.f - e->ffnn[nf - 1].drop) : 1.f;
+        if (dt) concat_split_kernel<bf16><<<cdiv(tot, 256), 256, 0, st>>>((const bf16*)e->gcat.p, e->gcat.ld, e->ffnn_out, (const bf16*)e->ffnn_h[nf - 1].p,
+                e->ffnn_h[nf - 1].ld, scale, (bf16*)e->ffnn_g[nf - 1].p, e->ffnn_g[nf - 1].ld, (bf16*)e->cnn.back().ga, e->cnn_Lp_last, e->cnn_C_last, e->cnn_ld_last, B);
+        else concat_split_kernel<float><<<cdiv(tot, 256), 256, 0, st>>>((const float*)e->gcat.p, e->gcat.ld, e->ffnn_out, (const float*)e->ffnn_h[nf - 1].p,
+                e->ffnn_h[nf - 1].ld, scale, (float*)e->ffnn_g[nf - 1].p, e->ffnn_g[nf - 1].ld, (float*)e->cnn.back().ga, e->cnn_Lp_last, e->cnn_C_last, e->cnn_ld_last, B);
+        EMB_CHECK_LAUNCH();
+        LAUNCHED(e);
     } else if (s.kind == EMB_KIND_FFNN) {
         const LinearLayer& hl = e->head.back();
         const int nf = (int)e->ffnn.size();
@@ -1224,7 +1317,7 @@ int emb_create(const EmbArchSpec* spec, int32_t max_batch, int32_t precision, Em
     if (!spec || !out) return set_error(EMB_E_ARG, "null argument");
     if (max_batch < 1) return set_error(EMB_E_ARG, "max_batch must be >= 1");
     if (precision != EMB_PREC_FP32 && precision != EMB_PREC_BF16) return set_error(EMB_E_ARG, "unknown precision %d", precision);
-    if (spec->kind < 0 || spec->kind > 2) return set_error(EMB_E_ARG, "unknown kind %d", spec->kind);
+    if (spec->kind < 0 || spec->kind > 3) return set_error(EMB_E_ARG, "unknown kind %d", spec->kind);
     EmbEngine* e = new EmbEngine();
     e->spec = *spec;
     e->max_batch = max_batch;

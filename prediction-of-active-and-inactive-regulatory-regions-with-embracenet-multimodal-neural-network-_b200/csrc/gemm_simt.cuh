@@ -33,6 +33,7 @@ struct Operand {
     int L, C;        // conv / flatten geometry: L positions, C channels of the indexed activation
     int taps, pad, sign;
     int wrows;       // OP_CONV_W_DGRAD: Cin; OP_W_PERM*: K of the weight row
+    int perm_off;    // OP_W_PERM*: leading columns that are not permuted
     int round_bf16;  // round fp32 source values to bf16 on load (bf16 precision with fp32 master weights)
 };
 
@@ -73,12 +74,14 @@ __device__ __forceinline__ float operand_fetch(const Operand& o, int r, int k) {
             idx = ((size_t)k * o.L + l) * o.ld + c;
         } break;
         case OP_W_PERM: {
-            int l = k / o.C, c = k - l * o.C;
-            idx = (size_t)r * o.wrows + (size_t)c * o.L + l;
+            if (k < o.perm_off) { idx = (size_t)r * o.wrows + k; break; }
+            int k2 = k - o.perm_off, l = k2 / o.C, c = k2 - l * o.C;
+            idx = (size_t)r * o.wrows + o.perm_off + (size_t)c * o.L + l;
         } break;
         default: {  // OP_W_PERM_T
-            int l = r / o.C, c = r - l * o.C;
-            idx = (size_t)k * o.wrows + (size_t)c * o.L + l;
+            if (r < o.perm_off) { idx = (size_t)k * o.wrows + r; break; }
+            int r2 = r - o.perm_off, l = r2 / o.C, c = r2 - l * o.C;
+            idx = (size_t)k * o.wrows + o.perm_off + (size_t)c * o.L + l;
         } break;
     }
     float v = o.dtype ? __bfloat162float(((const bf16*)o.p)[idx]) : ((const float*)o.p)[idx];
@@ -124,7 +127,7 @@ struct Epilogue {
     int ld_e;
     void* out2;
     // EPI_ATOMIC
-    int map, mapC, mapL, map_taps, map_wrows;
+    int map, mapC, mapL, map_taps, map_wrows, map_off;
     // tensor-core conv forward only: per-column sum / sum of squares of the STORED (bf16-rounded) outputs, i.e. the
     // BatchNorm batch statistics of the layer, accumulated in the epilogue ([N] sums then [N] sums of squares)
     double* bn_stats;
@@ -170,9 +173,11 @@ __device__ __forceinline__ void epilogue_apply(const Epilogue& ep, int m, int n,
             else if (ep.map == MAP_CONV_W) {  // n = (tap, c) -> dW[m][c][tap]
                 int tap = n / ep.mapC, c = n - tap * ep.mapC;
                 idx = ((size_t)m * ep.mapC + c) * ep.map_taps + tap;
-            } else {  // MAP_W_PERM: n = (l, c) -> dW[m][c*L + l]
-                int l = n / ep.mapC, c = n - l * ep.mapC;
-                idx = (size_t)m * ep.map_wrows + (size_t)c * ep.mapL + l;
+            } else if (n < ep.map_off) {  // MAP_W_PERM, un-permuted prefix
+                idx = (size_t)m * ep.map_wrows + n;
+            } else {  // MAP_W_PERM: n = off + (l, c) -> dW[m][off + c*L + l]
+                int n2 = n - ep.map_off, l = n2 / ep.mapC, c = n2 - l * ep.mapC;
+                idx = (size_t)m * ep.map_wrows + ep.map_off + (size_t)c * ep.mapL + l;
             }
             atomicAdd((float*)ep.out + idx, acc);
         } break;

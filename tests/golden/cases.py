@@ -35,6 +35,10 @@ CASES = {
                       B=7, seed=71, steps=2),
     'cnn_only': dict(spec=dict(kind='cnn', cnn_channels=[8, 16], cnn_kernels=[11, 5], cnn_dropout=[0.2, 0.4]),
                      B=3, seed=81, steps=1),
+    # ConcatNetMultimodal: post(cat(FFNN, CNN)), 1..3 post layers
+    'concat_small': dict(spec=dict(kind='concatnet', F=9, ffnn_units=[16, 8], ffnn_dropout=[0.2, 0.0], cnn_channels=[8, 16],
+                                   cnn_kernels=[5, 11], cnn_dropout=[0.0, 0.4], post_units=[24, 16, 8], post_dropout=[0.3, 0.0, 0.5]),
+                         B=6, seed=95, steps=2),
 }
 
 

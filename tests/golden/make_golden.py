@@ -64,6 +64,8 @@ def run_case(M, name, case):
                 torch.multinomial = spy
                 output = model([x1, x2], is_training=True)
                 torch.multinomial = orig
+            elif kind == 'concatnet':
+                output = model([x1, x2])
             elif kind == 'ffnn':
                 output = model(x1)
             else:
@@ -92,6 +94,8 @@ def run_case(M, name, case):
             av = np.ones((B, 2), dtype=np.float32)
             av[0::3, 0] = 0
             av[1::3, 1] = 0
+        elif kind == 'concatnet':
+            ev = model([x1, x2])
         elif kind == 'ffnn':
             ev = model(x1)
         else:

@@ -92,15 +92,15 @@ class FixedTrial:
 def spec_to_trial_params(spec):
     """oracle spec dict -> the reference's trial parameter names."""
     kind = spec.get('kind', 'embracenet')
-    pf = 'FFNN_' if kind == 'embracenet' else ''
-    pc = 'CNN_' if kind == 'embracenet' else ''
+    pf = 'FFNN_' if kind in ('embracenet', 'concatnet') else ''
+    pc = 'CNN_' if kind in ('embracenet', 'concatnet') else ''
     tp = {}
-    if kind in ('embracenet', 'ffnn'):
+    if kind in ('embracenet', 'concatnet', 'ffnn'):
         tp[f'{pf}n_layers'] = len(spec['ffnn_units'])
         for i, (u, p) in enumerate(zip(spec['ffnn_units'], spec['ffnn_dropout'])):
             tp[f'{pf}n_units_l{i}'] = u
             tp[f'{pf}dropout_l{i}'] = p
-    if kind in ('embracenet', 'cnn'):
+    if kind in ('embracenet', 'concatnet', 'cnn'):
         tp[f'{pc}n_layers'] = len(spec['cnn_channels'])
         for i, (c, k, p) in enumerate(zip(spec['cnn_channels'], spec['cnn_kernels'], spec['cnn_dropout'])):
             tp[f'{pc}out_channels_l{i}'] = c
@@ -113,6 +113,11 @@ def spec_to_trial_params(spec):
             tp[f'EMBRACENET_n_units_l{i}'] = u
             tp[f'EMBRACENET_dropout_l{i}'] = p
         tp['selection_probabilities_FFNN'] = spec['p_ffnn']
+    if kind == 'concatnet':
+        tp['CONCATNET_n_post_layers'] = len(spec['post_units'])
+        for i, (u, p) in enumerate(zip(spec['post_units'], spec['post_dropout'])):
+            tp[f'CONCATNET_n_units_l{i}'] = u
+            tp[f'CONCATNET_dropout_l{i}'] = p
     return tp
 
 
@@ -123,6 +128,10 @@ def build_reference_model(M, spec, P):
     if kind == 'embracenet':
         model = M.EmbraceNetMultimodal(trial, cell_line='A549', task='active_E_vs_inactive_E', device='cpu',
                                        in_features_FFNN=spec['F'])
+    elif kind == 'concatnet':
+        import importlib
+        CN = importlib.import_module('BIOINF_tesi.models.ConcatNetMultimodal')
+        model = CN.ConcatNetMultimodal(trial, cell_line='A549', task='active_E_vs_inactive_E', in_features_FFNN=spec['F'], device='cpu')
     elif kind == 'ffnn':
         model = M.FFNN(trial, spec['F'], device='cpu')
     else:
@@ -179,14 +188,18 @@ def draws_to_queue(spec, draws, training=True):
     """Order in which one reference forward consumes draws."""
     kind = spec.get('kind', 'embracenet')
     q = []
-    if training and kind in ('embracenet', 'ffnn'):
+    if training and kind in ('embracenet', 'concatnet', 'ffnn'):
         for i, p in enumerate(spec['ffnn_dropout']):
             if p > 0:
                 q.append(('dropout', draws['ffnn_drop'][i]))
-    if training and kind in ('embracenet', 'cnn'):
+    if training and kind in ('embracenet', 'concatnet', 'cnn'):
         for i, p in enumerate(spec['cnn_dropout']):
             if p > 0:
                 q.append(('dropout', draws['cnn_drop'][i]))
+    if kind == 'concatnet' and training:
+        for i, p in enumerate(spec['post_dropout']):
+            if p > 0:
+                q.append(('dropout', draws['post_drop'][i]))
     if kind == 'embracenet':
         if training:
             q.append(('rand', np.asarray([draws['modal_u0']], dtype=np.float32)))

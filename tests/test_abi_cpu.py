@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.emb_abi_version() == 1
+    assert lib.emb_abi_version() == 2
 
 
 @pytest.mark.parametrize('spec', [ARCH_S, ARCH_M, ARCH_L, ARCH_W] + [c['spec'] for c in CASES.values()])

@@ -153,7 +153,7 @@ def test_train_step_bf16_simt_matches_oracle(name):
     print(name, run_case(name, 'bf16', tensor_core=False, B_override=32))
 
 
-@pytest.mark.parametrize('name,B', [('archS', 40), ('deep4', 37), ('cnn_only', 33), ('small2', 32), ('ffnn_only', 130)])
+@pytest.mark.parametrize('name,B', [('archS', 40), ('deep4', 37), ('cnn_only', 33), ('small2', 32), ('ffnn_only', 130), ('concat_small', 36)])
 def test_train_step_bf16_tensor_core_matches_oracle(name, B):
     """Same check with the tcgen05/TMEM/TMA GEMM back end (layers too small for it stay on the SIMT kernel)."""
     print(name, run_case(name, 'bf16', tensor_core=True, B_override=B))

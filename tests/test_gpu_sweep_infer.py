@@ -96,3 +96,40 @@ def test_sharded_inference_equals_unsharded_and_masks_modalities(precision):
     u = np.full((n, spec['C']), 0.5)      # cum0 is 1 (FFNN only) or 0 (CNN only) on those rows: any u in (0, 1) selects the available one
     ref = O.predict_proba(spec, P, x, codes, u, availabilities=av)
     assert np.abs(full[one] - ref[one]).max() <= (2e-6 if precision == 'fp32' else 2e-2)
+
+
+def test_concatnet_mirror_matches_the_oracle_and_runs_a_study(tmp_path, monkeypatch):
+    """ConcatNetMultimodal: reference constructor order and state_dict keys, eval forward vs the oracle
+    (itself pinned to the reference's golden vectors), and the class plugs into Param_Search_Multimodal unchanged."""
+    import torch
+    from embrace_b200.BIOINF_tesi.models import ConcatNetMultimodal, ConcatNetMultimodal_NoTrain
+    from embrace_b200.BIOINF_tesi.models.utils import Param_Search_Multimodal
+    from embrace_b200.BIOINF_tesi.data_pipe import PackedDataset, build_loaders
+    from tests.golden.cases import CASES
+    from tests.golden.ref_harness import FixedTrial, spec_to_trial_params
+    monkeypatch.chdir(tmp_path)
+    spec = CASES['concat_small']['spec']
+    P = O.init_params(spec, 17)
+    tp = spec_to_trial_params(spec)
+    model = ConcatNetMultimodal(FixedTrial(tp), 'A549', 'active_E_vs_inactive_E', spec['F'], 'cuda', precision='fp32')
+    assert list(model.state_dict()) == list(O.param_shapes(spec))
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in P.items()})
+    x, codes, _ = make_inputs(spec, 9, 18)
+    model.eval()
+    with torch.no_grad():
+        got = model([torch.from_numpy(x), torch.from_numpy(codes)]).cpu().numpy()
+    ref, _ = O.forward(spec, P, x, codes, training=False)
+    assert np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+    torch.save({'model_state_dict': model.state_dict(), 'model_params': tp}, 'A549_ConcatNetMultimodal_active_E_vs_inactive_E_1_test_.pt')
+    twin = ConcatNetMultimodal_NoTrain('A549', 'active_E_vs_inactive_E', 1, spec['F'], 'cuda', precision='fp32')
+    twin.load_state_dict(torch.load('A549_ConcatNetMultimodal_active_E_vs_inactive_E_1_test_.pt', weights_only=False)['model_state_dict'])
+    twin.eval()
+    with torch.no_grad():
+        assert np.abs(twin([torch.from_numpy(x), torch.from_numpy(codes)]).cpu().numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+    xs, cs, ys = _data(500, 48, 7)
+    tr = build_loaders(PackedDataset(xs[:350], cs[:350], ys[:350]), batch_size=100, training=True)
+    te = build_loaders(PackedDataset(xs[350:], cs[350:], ys[350:]), batch_size=100, training=False)
+    ps = Param_Search_Multimodal(ConcatNetMultimodal, tr, te, num_epochs=1, study_name='A549_concat_1', device='cuda', cell_line='A549',
+                                 task='active_E_vs_inactive_E', sampler='random', n_trials=2, storage='c.db', seed=3)
+    ps.run_trial()
+    assert 'CONCATNET_n_post_layers' in ps.best_params and type(ps.best_model).__name__ == 'ConcatNetMultimodal'
