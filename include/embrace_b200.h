@@ -186,6 +186,15 @@ int emb_train_step(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, cons
 int emb_train_step_host(EmbEngine* e, const float* x_ffnn_host, const uint8_t* bases_host,
                         const int32_t* labels_host, int32_t B, const EmbOptConfig* cfg,
                         EmbStepMetrics* metrics_host, void* stream);
+
+/* Software-pipelined form of emb_train_step_host for training loops (host buffers should be pinned): call i copies batch i
+ * host->device on an engine-owned copy stream (overlapping the compute of step i-1), enqueues step i on `stream` and
+ * returns the EmbStepMetrics of step i-1 (*have_metrics = 0 on the first call).  emb_train_step_host_flush returns the
+ * last step's record.  Replaces the same loop body; the host never stalls the device. */
+int emb_train_step_host_pipelined(EmbEngine* e, const float* x_ffnn_host, const uint8_t* bases_host, const int32_t* labels_host,
+                                  int32_t B, const EmbOptConfig* cfg, EmbStepMetrics* metrics_prev_host, int32_t* have_metrics,
+                                  void* stream);
+int emb_train_step_host_flush(EmbEngine* e, EmbStepMetrics* metrics_host, int32_t* have_metrics, void* stream);
 /* Predict through HOST buffers (probs_host [B]); synchronises the stream. */
 int emb_predict_host(EmbEngine* e, const float* x_ffnn_host, const uint8_t* bases_host,
                      const float* availabilities_host, int32_t B, float* probs_host, void* stream);

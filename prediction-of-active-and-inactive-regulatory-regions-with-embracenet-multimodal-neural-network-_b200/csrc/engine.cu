@@ -141,6 +141,15 @@ struct EmbEngine {
     std::vector<StepGraph> graphs;
     std::vector<int> graph_seen;     // batch sizes that already ran once eagerly (lazy initialisation happens there)
     bool capturing = false;
+    // pipelined host entry (emb_train_step_host_pipelined): two device staging slots filled by a copy stream one step ahead
+    float* stg_x[2] = {nullptr, nullptr};
+    uint8_t* stg_bases[2] = {nullptr, nullptr};
+    int32_t* stg_labels[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_step[2] = {nullptr, nullptr}, ev_d2h = nullptr;
+    EmbStepMetrics* pin_metrics = nullptr;      // pinned host landing slot of the previous step's record
+    int64_t pipe_steps = 0;                     // steps enqueued so far
+    bool pipe_pending = false;                  // a step whose metrics have not been delivered yet
     cudaStream_t gstream = nullptr;  // graphs are captured and launched on an engine-owned stream (the caller's may be the legacy
     cudaEvent_t gev_in = nullptr, gev_out = nullptr;   // default stream, which cannot be captured); events order it with the caller's
     // per-kernel timing of the GEMM class (bench.py roofline): CUDA event pairs around each launch
@@ -463,6 +472,11 @@ int64_t carve(EmbEngine* e, char* base) {
     e->in_bases = bp.take<uint8_t>(Bm * SEQ_LEN);
     e->in_labels = bp.take<int32_t>(Bm);
     e->in_avail = bp.take<float>(Bm * 2);
+    for (int k = 0; k < 2; ++k) {
+        e->stg_x[k] = bp.take<float>(Bm * std::max(1, s.in_features));
+        e->stg_bases[k] = bp.take<uint8_t>(Bm * SEQ_LEN);
+        e->stg_labels[k] = bp.take<int32_t>(Bm);
+    }
     if (e->prec == EMB_PREC_BF16) {
         auto wl = [&](LinearLayer& l) {
             l.wc = bp.take<bf16>((int64_t)l.out * round_up(l.in, 8));
@@ -1335,6 +1349,12 @@ void emb_destroy(EmbEngine* e) {
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
     if (e->gstream) { cudaStreamDestroy(e->gstream); cudaEventDestroy(e->gev_in); cudaEventDestroy(e->gev_out); }
+    if (e->copy_stream) {
+        cudaStreamDestroy(e->copy_stream);
+        for (int k = 0; k < 2; ++k) { cudaEventDestroy(e->ev_h2d[k]); cudaEventDestroy(e->ev_consumed[k]); cudaEventDestroy(e->ev_step[k]); }
+        cudaEventDestroy(e->ev_d2h);
+        cudaFreeHost(e->pin_metrics);
+    }
     if (e->owns_memory) {
         cudaFree(e->params); cudaFree(e->grads); cudaFree(e->buffers); cudaFree(e->opt_m); cudaFree(e->opt_v); cudaFree(e->ws);
     }
@@ -1656,6 +1676,80 @@ int emb_train_step_host(EmbEngine* e, const float* x_ffnn_host, const uint8_t* b
         EMB_CUDA_OK(cudaMemcpyAsync(metrics_host, e->rec, sizeof(EmbStepMetrics), cudaMemcpyDeviceToHost, st));
         EMB_CUDA_OK(cudaStreamSynchronize(st));
     }
+    return EMB_OK;
+}
+
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
+// Software-pipelined host entry.  Call i copies batch i host->device on a COPY stream into staging slot i & 1 (it overlaps
+// the compute of step i-1, which is still running), enqueues step i on `stream`, and returns the metrics of step i-1
+// (*have_metrics = 0 on the first call).  emb_train_step_host_flush() returns the last step's metrics.  Every step's
+// inputs cross PCIe/NVLink-C2C and every step's record is read back, but the device never waits for the host.
+int emb_train_step_host_pipelined(EmbEngine* e, const float* x_ffnn_host, const uint8_t* bases_host, const int32_t* labels_host, int32_t B,
+                                  const EmbOptConfig* cfg, EmbStepMetrics* metrics_prev_host, int32_t* have_metrics, void* stream) {
+    int rc = check_ready(e, B, true);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!e->copy_stream) {
+        EMB_CUDA_OK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            EMB_CUDA_OK(cudaEventCreateWithFlags(&e->ev_h2d[k], cudaEventDisableTiming));
+            EMB_CUDA_OK(cudaEventCreateWithFlags(&e->ev_consumed[k], cudaEventDisableTiming));
+            EMB_CUDA_OK(cudaEventCreateWithFlags(&e->ev_step[k], cudaEventDisableTiming));
+        }
+        EMB_CUDA_OK(cudaEventCreateWithFlags(&e->ev_d2h, cudaEventDisableTiming));
+        EMB_CUDA_OK(cudaMallocHost(&e->pin_metrics, 2 * sizeof(EmbStepMetrics)));
+    }
+    const int64_t i = e->pipe_steps;
+    const int k = (int)(i & 1);
+    cudaStream_t cs = e->copy_stream;
+    // staging slot k was last read by the device-to-device copy of step i-2
+    if (i >= 2) EMB_CUDA_OK(cudaStreamWaitEvent(cs, e->ev_consumed[k], 0));
+    if (e->spec.kind != EMB_KIND_CNN) EMB_CUDA_OK(cudaMemcpyAsync(e->stg_x[k], x_ffnn_host, (size_t)B * e->spec.in_features * sizeof(float), cudaMemcpyHostToDevice, cs));
+    if (e->spec.kind != EMB_KIND_FFNN) EMB_CUDA_OK(cudaMemcpyAsync(e->stg_bases[k], bases_host, (size_t)B * SEQ_LEN, cudaMemcpyHostToDevice, cs));
+    EMB_CUDA_OK(cudaMemcpyAsync(e->stg_labels[k], labels_host, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+    EMB_CUDA_OK(cudaEventRecord(e->ev_h2d[k], cs));
+    // compute stream: wait for the copy, move the batch into the engine's fixed input buffers (what a captured graph reads)
+    EMB_CUDA_OK(cudaStreamWaitEvent(st, e->ev_h2d[k], 0));
+    if (e->spec.kind != EMB_KIND_CNN) EMB_CUDA_OK(cudaMemcpyAsync(e->in_x, e->stg_x[k], (size_t)B * e->spec.in_features * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (e->spec.kind != EMB_KIND_FFNN) EMB_CUDA_OK(cudaMemcpyAsync(e->in_bases, e->stg_bases[k], (size_t)B * SEQ_LEN, cudaMemcpyDeviceToDevice, st));
+    EMB_CUDA_OK(cudaMemcpyAsync(e->in_labels, e->stg_labels[k], (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    EMB_CUDA_OK(cudaEventRecord(e->ev_consumed[k], st));
+    set_int_kernel<<<1, 1, 0, st>>>(e->rec_count, k);          // this step's record lands in rec[k]
+    EMB_CHECK_LAUNCH();
+    rc = emb_train_step(e, e->in_x, e->in_bases, e->in_labels, B, nullptr, cfg, stream);
+    if (rc) return rc;
+    EMB_CUDA_OK(cudaEventRecord(e->ev_step[k], st));
+    e->pipe_steps = i + 1;
+    // deliver the record of step i-1: its device-to-host copy rides the copy stream behind this step's host-to-device copy
+    if (have_metrics) *have_metrics = 0;
+    if (e->pipe_pending) {
+        const int kp = k ^ 1;
+        EMB_CUDA_OK(cudaStreamWaitEvent(cs, e->ev_step[kp], 0));
+        EMB_CUDA_OK(cudaMemcpyAsync(&e->pin_metrics[kp], e->rec + kp, sizeof(EmbStepMetrics), cudaMemcpyDeviceToHost, cs));
+        EMB_CUDA_OK(cudaEventRecord(e->ev_d2h, cs));
+        EMB_CUDA_OK(cudaEventSynchronize(e->ev_d2h));
+        if (metrics_prev_host) *metrics_prev_host = e->pin_metrics[kp];
+        if (have_metrics) *have_metrics = 1;
+    }
+    e->pipe_pending = true;
+    return EMB_OK;
+}
+
+int emb_train_step_host_flush(EmbEngine* e, EmbStepMetrics* metrics_host, int32_t* have_metrics, void* stream) {
+    int rc = check_ready(e, 1, false);
+    if (rc) return rc;
+    if (have_metrics) *have_metrics = 0;
+    if (!e->pipe_pending) return EMB_OK;
+    const int kp = (int)((e->pipe_steps - 1) & 1);
+    cudaStream_t cs = e->copy_stream;
+    EMB_CUDA_OK(cudaStreamWaitEvent(cs, e->ev_step[kp], 0));
+    EMB_CUDA_OK(cudaMemcpyAsync(&e->pin_metrics[kp], e->rec + kp, sizeof(EmbStepMetrics), cudaMemcpyDeviceToHost, cs));
+    EMB_CUDA_OK(cudaStreamSynchronize(cs));
+    if (metrics_host) *metrics_host = e->pin_metrics[kp];
+    if (have_metrics) *have_metrics = 1;
+    e->pipe_pending = false;
+    (void)stream;
     return EMB_OK;
 }
 

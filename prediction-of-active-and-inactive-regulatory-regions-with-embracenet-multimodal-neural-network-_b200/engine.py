@@ -268,6 +268,25 @@ class Engine:
         N.check(self.lib.emb_train_step_host(self._h, hp(x_ffnn_host), hp(bases_host), hp(labels_host), B, C.byref(cfg), C.byref(m), self.stream))
         return m
 
+    def train_step_host_pipelined(self, x_ffnn_host, bases_host, labels_host, cfg):
+        """Like train_step_host, but the copy of this batch overlaps the previous step's compute and the call returns the
+        PREVIOUS step's EmbStepMetrics (None on the first call); finish with flush_host()."""
+        m, have = N.EmbStepMetrics(), C.c_int32(0)
+        B = (x_ffnn_host if x_ffnn_host is not None else bases_host).shape[0]
+
+        def hp(a):
+            if a is None:
+                return C.c_void_p(0)
+            return C.c_void_p(a.data_ptr() if torch.is_tensor(a) else a.ctypes.data)
+        N.check(self.lib.emb_train_step_host_pipelined(self._h, hp(x_ffnn_host), hp(bases_host), hp(labels_host), B, C.byref(cfg),
+                                                       C.byref(m), C.byref(have), self.stream))
+        return m if have.value else None
+
+    def flush_host(self):
+        m, have = N.EmbStepMetrics(), C.c_int32(0)
+        N.check(self.lib.emb_train_step_host_flush(self._h, C.byref(m), C.byref(have), self.stream))
+        return m if have.value else None
+
     def predict_host(self, x_ffnn_host, bases_host, availabilities_host=None):
         B = (x_ffnn_host if x_ffnn_host is not None else bases_host).shape[0]
         out = np.empty(B, dtype=np.float32)

@@ -72,3 +72,37 @@ def test_graph_host_entry_and_ragged_batches():
     x, bases, y = make_inputs(spec, 64, 1)
     m = eng.train_step_host(np.ascontiguousarray(x.astype(np.float32)), bases, np.ascontiguousarray(y.astype(np.int32)), cfg)
     assert np.isfinite(m.loss)
+
+
+def test_pipelined_host_entry_delivers_the_same_records_one_step_late():
+    """emb_train_step_host_pipelined: batch i is copied while step i-1 computes; call i returns the record of step i-1."""
+    import torch
+    from embrace_b200 import Engine
+    spec, B, steps = ARCH_S, 64, 7
+    P = O.init_params(spec, 2)
+    batches = [make_inputs(spec, B, 300 + i) for i in range(steps)]
+    host = [(torch.from_numpy(x.astype(np.float32)).pin_memory(), torch.from_numpy(b).pin_memory(),
+             torch.from_numpy(y.astype(np.int32)).pin_memory()) for x, b, y in batches]
+    out = {}
+    for mode in ('sync', 'pipelined', 'pipelined+graph'):
+        eng = Engine(to_archspec(spec), max_batch=B, precision='fp32', seed=9)
+        eng.load_numpy(P)
+        eng.set_graph('graph' in mode)
+        cfg = eng.opt_config('adam', lr=1e-3, weight_decay=1e-4)
+        recs = []
+        for call, (x, b, y) in enumerate(host):
+            if mode == 'sync':
+                recs.append(eng.train_step_host(x, b, y, cfg))
+            else:
+                m = eng.train_step_host_pipelined(x, b, y, cfg)
+                assert (m is None) == (call == 0)             # only the first call has nothing to deliver
+                if m is not None:
+                    recs.append(m)
+        if mode != 'sync':
+            recs.append(eng.flush_host())
+            assert eng.flush_host() is None
+        out[mode] = [(r.loss, r.tp, r.fp, r.fn, r.tn) for r in recs]
+        assert len(recs) == steps
+    for mode in ('pipelined', 'pipelined+graph'):
+        for a, b in zip(out['sync'], out[mode]):
+            assert abs(a[0] - b[0]) <= 1e-4 * max(1.0, abs(a[0])) and sum(b[1:]) == B
