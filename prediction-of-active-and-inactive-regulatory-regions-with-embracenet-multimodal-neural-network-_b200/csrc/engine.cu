@@ -792,11 +792,18 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
             const int groups = c.cout / 8;
             if ((c.cout % 8) == 0 && (256 % groups) == 0) {
                 // vectorised gather-sum; BatchNorm statistics of layer 0 are accumulated by the same kernel
-                const int n_tp = (c.k + 1) / 2;
+                const int n_tp = (c.k + 1) / 2, n_tr = (c.k + 2) / 3;
+                const size_t smem3 = (size_t)(n_tr * 125 * c.cout + c.cout + 32 * groups * 16) * sizeof(float) + SEQ_LEN + 2 * c.pad + 32;
+                if (smem3 <= (size_t)tc_max_smem() && B >= 32 && (1024 % groups) == 0 && !getenv("EMB_K1_PAIRS")) {
+                    // tap-triple tables (160 KB for 64 channels, k = 15): one persistent 1024-thread CTA per SM
+                    onehot_conv_fwd_triple_kernel<T><<<std::min(B, tc_num_sms()), 1024, smem3, st>>>(bases, e->params + c.w, e->params + c.b, (T*)c.y,
+                                                                                                   training ? c.stats : nullptr, B, c.cout, c.k, c.ld);
+                } else {
                 size_t smem = (size_t)(n_tp * 25 * c.cout + c.cout + 256 * 16) * sizeof(float) + SEQ_LEN + 2 * c.pad + 32;
                 int grid = std::min(B, 148 * 3);
                 onehot_conv_fwd_pair_kernel<T><<<grid, 256, smem, st>>>(bases, e->params + c.w, e->params + c.b, (T*)c.y,
                                                                        training ? c.stats : nullptr, B, c.cout, c.k, c.ld);
+                }
                 stats_done = true;
             } else {
                 size_t smem = (size_t)(c.k * 4 * c.cout + c.cout) * sizeof(float) + SEQ_LEN + 2 * c.pad + 16;
@@ -1415,6 +1422,8 @@ int emb_bind(EmbEngine* e, float* params, float* grads, float* buffers, float* o
     cudaFuncSetAttribute(onehot_conv_fwd_pair_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (8 * 25 * 64 + 64 + 4096) * 4 + 512);
     int rc = tc_init();
     if (rc) return rc;
+    EMB_CUDA_OK(cudaFuncSetAttribute(onehot_conv_fwd_triple_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_max_smem()));
+    EMB_CUDA_OK(cudaFuncSetAttribute(onehot_conv_fwd_triple_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_max_smem()));
     EMB_CUDA_OK(cudaFuncSetAttribute(pool_bn_bwd_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kt_max_smem()));
     EMB_CUDA_OK(cudaFuncSetAttribute(pool_bn_bwd_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kt_max_smem()));
     return EMB_OK;

@@ -712,4 +712,86 @@ onehot_conv_bwd_lists16_kernel(const uint8_t* __restrict__ bases, const bf16* __
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K1 forward with TAP-TRIPLE tables: three adjacent taps are looked up at once (5^3 = 125 base combinations incl.
+// "outside"), so a k = 15 convolution is 5 table rows per output instead of 15 (or 8 with tap pairs): the kernel is bound by
+// shared-memory reads.  tab3[(triple * 125 + b0 * 25 + b1 * 5 + b2) * C1 + o]: 160 KB for C1 = 64, k = 15 -> one persistent
+// 1024-thread CTA per SM.  Requires C1 % 8 == 0, 1024 % (C1 / 8) == 0.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024, 1)
+onehot_conv_fwd_triple_kernel(const uint8_t* __restrict__ bases, const float* __restrict__ w, const float* __restrict__ bias,
+                              T* __restrict__ y, double* __restrict__ stats, int B, int C1, int k, int ld) {
+    extern __shared__ float smem[];
+    const int n_tr = (k + 2) / 3;                  // the last triple of k = 5 / 11 has empty taps
+    float* tab = smem;                             // [n_tr][125][C1]
+    float* sb = tab + n_tr * 125 * C1;             // [C1]
+    float* red = sb + C1;                          // [32 warps][groups][16]
+    const int p = (k - 1) / 2;
+    const int groups = C1 / 8;
+    uint8_t* sbase = (uint8_t*)(red + 32 * groups * 16);   // [256 + 2p + 2]
+    for (int i = threadIdx.x; i < n_tr * 125 * C1; i += blockDim.x) {
+        const int o = i % C1, combo = (i / C1) % 125, tr = i / (125 * C1);
+        const int b0 = combo / 25, b1 = (combo / 5) % 5, b2 = combo % 5, t0 = 3 * tr;
+        float v = 0.f;
+        if (b0 < 4) v += w[((size_t)o * 4 + b0) * k + t0];
+        if (b1 < 4 && t0 + 1 < k) v += w[((size_t)o * 4 + b1) * k + t0 + 1];
+        if (b2 < 4 && t0 + 2 < k) v += w[((size_t)o * 4 + b2) * k + t0 + 2];
+        tab[i] = v;
+    }
+    for (int i = threadIdx.x; i < C1; i += blockDim.x) sb[i] = bias[i];
+    const int og = threadIdx.x % groups;           // constant per thread: 1024 % groups == 0
+    float s1[8], s2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < SEQ_LEN + 2 * p + 2; i += blockDim.x) {
+            const int l = i - p;
+            sbase[i] = (l >= 0 && l < SEQ_LEN) ? bases[(size_t)b * SEQ_LEN + l] : 4;
+        }
+        __syncthreads();
+        for (int item = threadIdx.x; item < SEQ_LEN * groups; item += blockDim.x) {
+            const int l = item / groups;
+            float acc[8];
+            const float4* b4 = reinterpret_cast<const float4*>(sb + og * 8);
+            float4 t0 = b4[0], t1 = b4[1];
+            acc[0] = t0.x; acc[1] = t0.y; acc[2] = t0.z; acc[3] = t0.w; acc[4] = t1.x; acc[5] = t1.y; acc[6] = t1.z; acc[7] = t1.w;
+            for (int tr = 0; tr < n_tr; ++tr) {
+                const int combo = sbase[l + 3 * tr] * 25 + sbase[l + 3 * tr + 1] * 5 + sbase[l + 3 * tr + 2];
+                const float4* r4 = reinterpret_cast<const float4*>(tab + (tr * 125 + combo) * C1 + og * 8);
+                float4 a0 = r4[0], a1 = r4[1];
+                acc[0] += a0.x; acc[1] += a0.y; acc[2] += a0.z; acc[3] += a0.w;
+                acc[4] += a1.x; acc[5] += a1.y; acc[6] += a1.z; acc[7] += a1.w;
+            }
+            st8(y + ((size_t)b * SEQ_LEN + l) * ld + og * 8, acc);
+            if (stats) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { float v = round_like<T>(acc[i]); s1[i] += v; s2[i] += v * v; }
+            }
+        }
+    }
+    if (stats) {   // lanes with the same og hold partials of the same 8 channels: fold them inside the warp, then across warps
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            for (int off = 16; off >= groups; off >>= 1) {
+                s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], off);
+                s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
+            }
+        __syncthreads();
+        if (lane < groups) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { red[(warp * groups + lane) * 16 + i] = s1[i]; red[(warp * groups + lane) * 16 + 8 + i] = s2[i]; }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < groups * 16; i += blockDim.x) {
+            const int g = i / 16, j = i - g * 16;
+            double tot = 0;
+            for (int wv = 0; wv < 32; ++wv) tot += red[(wv * groups + g) * 16 + j];
+            atomicAdd(&stats[(j < 8 ? 0 : C1) + g * 8 + (j & 7)], tot);
+        }
+    }
+}
+
 }  // namespace emb
