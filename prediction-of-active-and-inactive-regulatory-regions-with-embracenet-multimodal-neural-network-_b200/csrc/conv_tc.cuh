@@ -30,6 +30,7 @@ struct TcConvParams {
     int n_tile, grid_m, grid_n, total_tiles;
     int a_slot_bytes, a_box_bytes;
     int b_slot_bytes, b_boxes, b_box_bytes, b_stages, b_resident;
+    int tps;                  // streamed weights: taps per pipeline stage (one barrier round trip per `tps` taps)
     int b_tail, b_tail_slot_bytes, b_tail_box_bytes;   // dgrad, resident: the last K chunk has < 64 rows and uses its own (smaller) box
     uint32_t b_tail_lbo_bytes;
     uint32_t b_kstep16, b_lbo_bytes;     // descriptor advance per UMMA K step (in 16-byte units), LBO
@@ -46,7 +47,7 @@ tc_conv_reuse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                      const __grid_constant__ CUtensorMap map_b2, const TcConvParams p, const Epilogue ep) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int n_bslots = p.b_resident ? p.taps * p.n_chunks : p.b_stages;
+    const int n_bslots = p.b_resident ? p.taps * p.n_chunks : p.b_stages * p.tps;
     uint8_t* smem_b = smem + TCV_A_SLOTS * p.a_slot_bytes;
     const uint32_t b_tail_base = (uint32_t)((p.n_chunks - 1) * p.taps) * (uint32_t)p.b_slot_bytes;     // resident tail slots start here
     const size_t b_total = p.b_resident && p.b_tail ? (size_t)b_tail_base + (size_t)p.taps * p.b_tail_slot_bytes : (size_t)n_bslots * p.b_slot_bytes;
@@ -133,11 +134,13 @@ tc_conv_reuse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     }
                     if (++as == TCV_A_SLOTS) { as = 0; aphase ^= 1; }
                     if (!p.b_resident) {
-                        for (int t = 0; t < p.taps; ++t) {
+                        for (int t = 0; t < p.taps; t += p.tps) {
+                            const int nt = min(p.tps, p.taps - t);
                             mbar_wait(&b_empty[bs], bphase ^ 1);
                             const uint32_t bar = smem_u32(&b_full[bs]);
-                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b_tx) : "memory");
-                            load_b(sb0 + (uint32_t)(bs * p.b_slot_bytes), bar, c, t, tile_n);
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b_tx * (uint32_t)nt) : "memory");
+                            for (int tt = 0; tt < nt; ++tt)
+                                load_b(sb0 + (uint32_t)((bs * p.tps + tt) * p.b_slot_bytes), bar, c, t + tt, tile_n);
                             if (++bs == p.b_stages) { bs = 0; bphase ^= 1; }
                         }
                     }
@@ -206,27 +209,32 @@ tc_conv_reuse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     }
                     __syncwarp();
                     accumulate = 1;
-                } else
-                for (int t = 0; t < taps; ++t) {
-                    uint32_t b_lo;
-                    if (resident) { b_lo = b_res; b_res += b_res_step; }
-                    else {
+                } else {
+                    // streamed weights: one barrier round trip per stage of `tps` taps
+                    const int tps = p.tps;
+                    for (int t = 0; t < taps; t += tps) {
+                        const int nt = min(tps, taps - t);
                         mbar_wait(&b_full[bs], bphase);
                         tc_fence_after();
-                        b_lo = ((sb0 + (uint32_t)bs * b_slot) & 0x3FFFFu) >> 4;
+                        if (!(p.debug & 1) && elect_one_sync()) {
+                            uint64_t da = ((uint64_t)da_hi << 32) | (da_lo16 | a_lo);
+                            uint64_t db = ((uint64_t)db_hi << 32) | (db_lo16 | (((sb0 + (uint32_t)(bs * tps) * b_slot) & 0x3FFFFu) >> 4));
+                            for (int tt = 0; tt < nt; ++tt) {
+                                tc_mma_f16(d_tmem, da, db, idesc, accumulate);
+                                if (ks > 1) tc_mma_f16(d_tmem, da + 2, db + bk, idesc, 1u);
+                                if (ks > 2) tc_mma_f16(d_tmem, da + 4, db + 2 * bk, idesc, 1u);
+                                if (ks > 3) tc_mma_f16(d_tmem, da + 6, db + 3 * bk, idesc, 1u);
+                                accumulate = 1;
+                                da += (int64_t)dshift;
+                                db += (uint64_t)(b_slot >> 4);
+                            }
+                            tc_commit(&b_empty[bs]);
+                        }
+                        __syncwarp();
+                        accumulate = 1;
+                        a_lo += (uint32_t)(dshift * nt);
+                        if (++bs == b_stages) { bs = 0; bphase ^= 1; }
                     }
-                    if (!(p.debug & 1) && elect_one_sync()) {
-                        const uint64_t da0 = ((uint64_t)da_hi << 32) | (da_lo16 | a_lo), db0 = ((uint64_t)db_hi << 32) | (db_lo | b_lo);
-                        tc_mma_f16(d_tmem, da0, db0, idesc, accumulate);
-                        if (ks > 1) tc_mma_f16(d_tmem, da0 + 2, db0 + bk, idesc, 1u);
-                        if (ks > 2) tc_mma_f16(d_tmem, da0 + 4, db0 + 2 * bk, idesc, 1u);
-                        if (ks > 3) tc_mma_f16(d_tmem, da0 + 6, db0 + 3 * bk, idesc, 1u);
-                        if (!resident) tc_commit(&b_empty[bs]);
-                    }
-                    __syncwarp();
-                    accumulate = 1;
-                    a_lo += (uint32_t)dshift;
-                    if (!resident && ++bs == b_stages) { bs = 0; bphase ^= 1; }
                 }
                 if (elect_one_sync()) tc_commit(&a_empty[as]);
                 __syncwarp();
@@ -351,9 +359,13 @@ inline int tc_conv_reuse(const TcProblem& pr, const Epilogue& ep, cudaStream_t s
     }
     p.b_resident = (p.grid_n == 1 && all_b <= budget && !getenv("EMB_CONV_NO_RESIDENT")) ? 1 : 0;
     if (!p.b_resident) p.b_tail = 0;
-    p.b_stages = std::min(TCV_MAX_B_STAGES, budget / p.b_slot_bytes);
+    p.tps = 1;
+    if (!p.b_resident && !getenv("EMB_CONV_TPS1"))
+        for (int t : {5, 3, 2})               // the largest group that still leaves three stages in flight
+            if (t <= p.taps && budget / (t * p.b_slot_bytes) >= 3 && t * p.b_slot_bytes <= 64 * 1024) { p.tps = t; break; }
+    p.b_stages = std::min(TCV_MAX_B_STAGES, budget / (p.tps * p.b_slot_bytes));
     if (!p.b_resident && p.b_stages < 2) return set_error(-5, "tc_conv_reuse: weight stage of %d bytes does not fit twice", p.b_slot_bytes);
-    const size_t smem = (size_t)TCV_A_SLOTS * p.a_slot_bytes + (size_t)(p.b_resident ? all_b : p.b_stages * p.b_slot_bytes) + 1024 + 512 + stats_bytes;
+    const size_t smem = (size_t)TCV_A_SLOTS * p.a_slot_bytes + (size_t)(p.b_resident ? all_b : p.b_stages * p.tps * p.b_slot_bytes) + 1024 + 512 + stats_bytes;
     const int grid = std::min(p.total_tiles, tc_num_sms());
     tc_conv_reuse_kernel<<<grid, TC_THREADS, smem, st>>>(ma, mb, mb2, p, ep);
     cudaError_t err = cudaGetLastError();
