@@ -108,19 +108,6 @@ class EmbraceNetMultimodal_NoTrain(EngineModule):
         logits = self._run(x_FFNN, x_CNN, availabilities, draws, modality_dropout=bool(is_training and embracenet_dropout))
         return torch.softmax(logits, dim=1).reshape(-1)
 
-    @torch.no_grad()
     def predict_proba(self, x_FFNN, x_CNN, availabilities=None, batch_size=65536, draws=None):
         """P(class 1) for every row, batched (replaces the batch-1 Python loop of visual.py:290-293)."""
-        was_training = self.training
-        self.eval()
-        out = []
-        n = len(x_FFNN)
-        for lo in range(0, n, batch_size):
-            hi = min(n, lo + batch_size)
-            xf = torch.as_tensor(x_FFNN[lo:hi]).to(self._dev, torch.float32).contiguous()
-            bases = self._to_bases(x_CNN[lo:hi], self._dev).contiguous()
-            av = None if availabilities is None else torch.as_tensor(availabilities[lo:hi])
-            _, probs = self._engine_for(xf, bases).forward(xf, bases, training=False, draws=draws, availabilities=av, want_probs=True)
-            out.append(probs)
-        self.train(was_training)
-        return torch.cat(out)
+        return self.predict_scores(x_FFNN, x_CNN, availabilities, batch_size, draws, column='prob')

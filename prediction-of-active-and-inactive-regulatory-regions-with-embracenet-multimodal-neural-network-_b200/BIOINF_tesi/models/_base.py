@@ -202,6 +202,30 @@ class EngineModule(nn.Module):
         eng.loss(logits, y, want_grad=False)
         return logits
 
+    @torch.no_grad()
+    def predict_scores(self, x_FFNN=None, x_CNN=None, availabilities=None, batch_size=65536, draws=None, column='prob'):
+        """Batched form of the predict loop `[model_(x_i)[1] for i in range(n)]` (visual.py:284-293): one eval-mode forward
+        per `batch_size` rows.  column='prob' returns softmax(logits)[:, 1] (the `_NoTrain` twins that apply their
+        softmax), column='logit' returns logits[:, 1] (ConcatNetMultimodal_NoTrain, whose softmax is lost to a typo).
+        `draws['embrace_u']`, when given, holds one row of uniforms per sample and is sliced with the batch."""
+        was_training = self.training
+        self.eval()
+        out = []
+        n = len(x_FFNN if x_FFNN is not None else x_CNN)
+        for lo in range(0, n, batch_size):
+            hi = min(n, lo + batch_size)
+            xf = torch.as_tensor(x_FFNN[lo:hi]).to(self._dev, torch.float32).contiguous() if x_FFNN is not None else None
+            bases = self._to_bases(x_CNN[lo:hi], self._dev).contiguous() if x_CNN is not None else None
+            av = None if availabilities is None else torch.as_tensor(availabilities[lo:hi])
+            d = None if draws is None else {k: (v[lo:hi] if k == 'embrace_u' else v) for k, v in draws.items()}
+            if self.spec.kind == 'embracenet':
+                d = dict(d or {})
+                d.setdefault('modal_u0', 0.0)
+            logits, probs = self._engine_for(xf, bases).forward(xf, bases, training=False, draws=d, availabilities=av, want_probs=True)
+            out.append(probs if column == 'prob' else logits[:, 1].clone())
+        self.train(was_training)
+        return torch.cat(out)
+
     def state_dict(self, *args, **kwargs):
         """Reference key names; tensors are detached COPIES (the live parameters are views of one flat arena)."""
         sd = super().state_dict(*args, **kwargs)
