@@ -237,6 +237,10 @@ int emb_k_onehot_conv_fwd(const uint8_t* bases, const float* w, const float* bia
                           int32_t k, int32_t precision, void* y, void* stream);
 int emb_k_onehot_conv_bwd(const uint8_t* bases, const void* dy, int32_t B, int32_t C1, int32_t k,
                           int32_t precision, float* dw, float* dbias, void* stream);
+/* The same weight gradient on the tensor cores (what the bf16 train step runs): the one-hot operand is expanded in shared
+ * memory from the base codes and all taps come out of one tcgen05.mma per 16 positions (csrc/onehot_wgrad_tc.cuh).
+ * dy bf16 [B,256,C1], C1 % 8 == 0, C1 <= 64, odd k <= 15, dw [C1,4,k] fp32 (zeroed by the call). */
+int emb_k_onehot_conv_wgrad_tc(const uint8_t* bases, const void* dy_bf16, int32_t B, int32_t C1, int32_t k, float* dw, void* stream);
 /* One GEMM-shaped op of the step on either back end (backend 0 = SIMT fp32-accumulate kernel, 1 = tcgen05/TMEM/TMA
  * kernel); fp32 in / fp32 out, inputs rounded to bf16 as the bf16 precision does.  kind:
  *   0 linear fwd   a[M,K] b[N,K] -> out[M,N]       3 conv fwd   a[B,L,Cin]  b=W[Cout,Cin,taps] -> out[B*L,Cout]

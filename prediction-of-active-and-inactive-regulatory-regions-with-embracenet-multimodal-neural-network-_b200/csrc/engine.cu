@@ -21,6 +21,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "conv_tc.cuh"
+#include "onehot_wgrad_tc.cuh"
 #include "probe.cuh"
 
 namespace emb {
@@ -957,7 +958,11 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
         LAUNCHED(e);
         if (i == 0) {
             // conv-0 dbias was already accumulated by the bn_bwd_apply kernel
-            if (even && (c.cout / 2) * c.k <= 1024) {
+            if (std::is_same<T, bf16>::value && tc_on(e) && onehot_wgrad_tc_ok(c.dy, e->last_bases, c.cout, c.k, c.ld)) {
+                // the weight gradient of the one-hot layer as ONE tensor-core contraction per 16 positions (onehot_wgrad_tc.cuh)
+                int rcw = onehot_conv_wgrad_tc(e->last_bases, (const bf16*)c.dy, e->grads + c.w, B, c.cout, c.k, c.ld, st);
+                if (rcw) return rcw;
+            } else if (even && (c.cout / 2) * c.k <= 1024) {
                 const int threads = round_up((c.cout / 2) * c.k, 32);
                 size_t smem = (size_t)(SEQ_LEN + 2 * c.pad) * c.cout * sizeof(float) + SEQ_LEN + 16;
                 int grid = std::min(B, 148 * 2);
@@ -1834,6 +1839,16 @@ int emb_k_onehot_conv_bwd(const uint8_t* bases, const void* dy, int32_t B, int32
     else onehot_conv_bwd_kernel<float><<<grid, 256, 0, st>>>(bases, (const float*)dy, dw, dbias, B, C1, k, ld);
     EMB_CHECK_LAUNCH();
     return EMB_OK;
+}
+
+// The tensor-core form of the same gradient (onehot_wgrad_tc.cuh): dy bf16 [B, 256, C1], C1 % 8 == 0, C1 <= 64, odd k <= 15.
+int emb_k_onehot_conv_wgrad_tc(const uint8_t* bases, const void* dy_bf16, int32_t B, int32_t C1, int32_t k, float* dw, void* stream) {
+    if (emb_device_count() < 1) return set_error(EMB_E_NO_DEVICE, "no sm_100 device");
+    if (B < 1 || !onehot_wgrad_tc_ok(dy_bf16, bases, C1, k, C1)) return set_error(EMB_E_ARG, "bad shape or alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    EMB_CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)C1 * 4 * k * sizeof(float), st));
+    int rc = onehot_conv_wgrad_tc(bases, (const bf16*)dy_bf16, dw, B, C1, k, C1, st);
+    return rc ? rc : EMB_OK;
 }
 
 // One GEMM-shaped op of the step on either back end (0 = SIMT, 1 = tcgen05), fp32 in / fp32 out; the

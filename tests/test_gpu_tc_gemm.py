@@ -98,3 +98,28 @@ def test_conv_wgrad(backend, B, L, Cin, Cout, k):
     _, dW, _ = O.conv1d_bwd(np.transpose(q(x), (0, 2, 1)), np.zeros((Cout, Cin, k)), np.transpose(q(g), (0, 2, 1)))
     got = run(5, backend, g, x, (Cout, Cin, k), B=B, L=L, Cin=Cin, Cout=Cout, taps=k)
     check(got, dW, ('conv wgrad', backend, B, L, Cin, Cout, k))
+
+
+@pytest.mark.parametrize('B,C1,k', [(1, 64, 15), (3, 64, 15), (37, 64, 11), (300, 64, 15), (5, 32, 5), (9, 16, 11), (150, 8, 15), (8, 24, 1)])
+def test_onehot_conv_wgrad_tc(B, C1, k):
+    """First-layer weight gradient as a tensor-core contraction against an in-smem one-hot Toeplitz operand
+    (csrc/onehot_wgrad_tc.cuh) vs the oracle's histogram form."""
+    import torch
+    from embrace_b200 import _native as N_
+    lib = N_.lib()
+    rs = np.random.RandomState(B * 131 + C1 + k)
+    bases = rs.randint(0, 4, size=(B, 256)).astype(np.uint8)
+    bases[0, :8] = [0, 1, 2, 3, 3, 2, 1, 0]
+    g = q(rs.standard_normal((B, C1, 256)))                                    # oracle layout [B, C, L]
+    ref, _ = O.onehot_conv_bwd(bases, g, k)
+    dy = torch.from_numpy(np.ascontiguousarray(g.transpose(0, 2, 1))).to(torch.bfloat16).cuda()       # channels-last
+    tb = torch.from_numpy(bases).cuda()
+    dw = torch.full((C1, 4, k), float('nan'), dtype=torch.float32, device='cuda')
+    for _ in range(2):                                                         # twice: the call zeroes its output itself
+        N_.check(lib.emb_k_onehot_conv_wgrad_tc(C.c_void_p(tb.data_ptr()), C.c_void_p(dy.data_ptr()), B, C1, k, C.c_void_p(dw.data_ptr()),
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    got = dw.cpu().numpy().astype(np.float64)
+    assert np.isfinite(got).all()
+    err = np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30)
+    assert err < 1e-5, err                                                     # exact products, fp32 accumulation
