@@ -237,6 +237,11 @@ int emb_k_onehot_conv_fwd(const uint8_t* bases, const float* w, const float* bia
                           int32_t k, int32_t precision, void* y, void* stream);
 int emb_k_onehot_conv_bwd(const uint8_t* bases, const void* dy, int32_t B, int32_t C1, int32_t k,
                           int32_t precision, float* dw, float* dbias, void* stream);
+/* K1 on the tensor cores (what the bf16 train step and inference run): one-hot rows expanded in shared memory, read through a
+ * Toeplitz descriptor; the fp32 weights enter as an exact hi/mid/lo bf16 split.  y bf16 [B,256,C1]; stats (nullable) [2][C1] doubles
+ * accumulate sum / sum of squares of the rounded outputs (layer-0 BatchNorm statistics).  C1 % 8 == 0, C1 <= 64, odd k <= 15. */
+int emb_k_onehot_conv_fwd_tc(const uint8_t* bases, const float* w, const float* bias, int32_t B, int32_t C1, int32_t k, void* y_bf16,
+                             double* stats, void* stream);
 /* The same weight gradient on the tensor cores (what the bf16 train step runs): the one-hot operand is expanded in shared
  * memory from the base codes and all taps come out of one tcgen05.mma per 16 positions (csrc/onehot_wgrad_tc.cuh).
  * dy bf16 [B,256,C1], C1 % 8 == 0, C1 <= 64, odd k <= 15, dw [C1,4,k] fp32 (zeroed by the call). */

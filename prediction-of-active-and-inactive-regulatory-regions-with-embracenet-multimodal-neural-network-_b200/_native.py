@@ -98,6 +98,7 @@ SIGNATURES = {
     'emb_set_phase_hook': (C.c_int, [_P, PHASE_FN, _P]),
     'emb_k_onehot_conv_fwd': (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     'emb_k_onehot_conv_bwd': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
+    'emb_k_onehot_conv_fwd_tc': (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     'emb_k_onehot_conv_wgrad_tc': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     'emb_k_umma_shift_probe': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     'emb_k_gemm': (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P] + [C.c_int32] * 8 + [_P]),

@@ -791,7 +791,12 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
         const bool even = (c.cout % 2) == 0;
         if (i == 0) {
             const int groups = c.cout / 8;
-            if ((c.cout % 8) == 0 && (256 % groups) == 0) {
+            if (std::is_same<T, bf16>::value && tc_on(e) && onehot_fwd_tc_ok(c.y, bases, c.cout, c.k, c.ld)) {
+                // one-hot rows expanded in shared memory, all taps through a Toeplitz descriptor, fp32 weights as an exact hi/mid/lo bf16 split
+                int rcf = onehot_conv_fwd_tc(bases, e->params + c.w, e->params + c.b, (bf16*)c.y, training ? c.stats : nullptr, B, c.cout, c.k, c.ld, st);
+                if (rcf) return rcf;
+                stats_done = true;
+            } else if ((c.cout % 8) == 0 && (256 % groups) == 0) {
                 // vectorised gather-sum; BatchNorm statistics of layer 0 are accumulated by the same kernel
                 const int n_tp = (c.k + 1) / 2, n_tr = (c.k + 2) / 3;
                 const size_t smem3 = (size_t)(n_tr * 125 * c.cout + c.cout + 32 * groups * 16) * sizeof(float) + SEQ_LEN + 2 * c.pad + 32;
@@ -1839,6 +1844,15 @@ int emb_k_onehot_conv_bwd(const uint8_t* bases, const void* dy, int32_t B, int32
     else onehot_conv_bwd_kernel<float><<<grid, 256, 0, st>>>(bases, (const float*)dy, dw, dbias, B, C1, k, ld);
     EMB_CHECK_LAUNCH();
     return EMB_OK;
+}
+
+// The tensor-core form of K1 (onehot_wgrad_tc.cuh): y bf16 [B, 256, C1]; stats (nullable) [2][C1] doubles are ACCUMULATED.
+int emb_k_onehot_conv_fwd_tc(const uint8_t* bases, const float* w, const float* bias, int32_t B, int32_t C1, int32_t k, void* y_bf16, double* stats,
+                             void* stream) {
+    if (emb_device_count() < 1) return set_error(EMB_E_NO_DEVICE, "no sm_100 device");
+    if (B < 1 || !onehot_fwd_tc_ok(y_bf16, bases, C1, k, C1)) return set_error(EMB_E_ARG, "bad shape or alignment");
+    int rc = onehot_conv_fwd_tc(bases, w, bias, (bf16*)y_bf16, stats, B, C1, k, C1, (cudaStream_t)stream);
+    return rc ? rc : EMB_OK;
 }
 
 // The tensor-core form of the same gradient (onehot_wgrad_tc.cuh): dy bf16 [B, 256, C1], C1 % 8 == 0, C1 <= 64, odd k <= 15.

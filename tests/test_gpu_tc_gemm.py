@@ -123,3 +123,32 @@ def test_onehot_conv_wgrad_tc(B, C1, k):
     assert np.isfinite(got).all()
     err = np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30)
     assert err < 1e-5, err                                                     # exact products, fp32 accumulation
+
+
+@pytest.mark.parametrize('B,C1,k', [(1, 64, 15), (3, 64, 15), (37, 64, 11), (700, 64, 15), (5, 32, 5), (9, 16, 11), (150, 8, 15), (8, 24, 1)])
+def test_onehot_conv_fwd_tc(B, C1, k):
+    """K1 forward through the in-smem one-hot Toeplitz operand with exactly split (hi/mid/lo bf16) weights vs the oracle's
+    gather-sum of the fp32 weights; BatchNorm statistics of the bf16-rounded outputs."""
+    import torch
+    from embrace_b200 import _native as N_
+    lib = N_.lib()
+    rs = np.random.RandomState(B * 17 + C1 + k)
+    bases = rs.randint(0, 4, size=(B, 256)).astype(np.uint8)
+    W = rs.standard_normal((C1, 4, k)).astype(np.float32)
+    bias = rs.standard_normal(C1).astype(np.float32)
+    ref = O.onehot_conv_fwd(bases, W.astype(np.float64), bias.astype(np.float64)).transpose(0, 2, 1)      # [B, L, C]
+    tb, tw, tbias = torch.from_numpy(bases).cuda(), torch.from_numpy(W).cuda(), torch.from_numpy(bias).cuda()
+    y = torch.full((B, 256, C1), float('nan'), dtype=torch.bfloat16, device='cuda')
+    stats = torch.zeros(2, C1, dtype=torch.float64, device='cuda')
+    N_.check(lib.emb_k_onehot_conv_fwd_tc(C.c_void_p(tb.data_ptr()), C.c_void_p(tw.data_ptr()), C.c_void_p(tbias.data_ptr()), B, C1, k,
+                                          C.c_void_p(y.data_ptr()), C.c_void_p(stats.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    got = y.float().cpu().numpy().astype(np.float64)
+    assert np.isfinite(got).all()
+    # the fp32 sum is exact to ~1e-5 of the weight scale; the output is then rounded to bf16 once
+    assert np.abs(got - ref).max() <= 2.0 ** -8 * np.abs(ref).max() + 1e-6
+    near = np.abs(got - q(ref)) > 0                     # differs from the correctly rounded value only at rounding ties / 1-ulp flips
+    assert near.mean() < 5e-4, near.mean()
+    st = stats.cpu().numpy()
+    np.testing.assert_allclose(st[0], got.sum(axis=(0, 1)), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(st[1], (got * got).sum(axis=(0, 1)), rtol=1e-5, atol=1e-3)
