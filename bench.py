@@ -134,6 +134,9 @@ def main():
     ap.add_argument('--ref-batch', type=int, default=256, help='batch of the bounded CPU sample')
     ap.add_argument('--cpu-baseline', type=int, default=1)
     ap.add_argument('--graph', type=int, default=1, help='replay the train step as one CUDA graph (single GPU)')
+    ap.add_argument('--dp-graph', type=int, default=int(os.environ.get('EMB_DP_GRAPH', '0')),
+                    help='N > 1: capture the data-parallel step with its NCCL collectives into one CUDA graph (1: one gradient '
+                         'all-reduce after the backward pass, 2: early slices on a side stream); 0 = host-driven collectives')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else max(args.warmup, 1)
 
@@ -179,7 +182,7 @@ def main():
     dp = None
     if world > 1:
         from embrace_b200.dp import DataParallel
-        dp = DataParallel(eng, args.batch, rank, world)
+        dp = DataParallel(eng, args.batch, rank, world, graph=bool(args.dp_graph))
         assert (dp.lo, dp.hi) == (lo, lo + B)
 
     def step_device(i):
@@ -275,7 +278,7 @@ def main():
         'config': {'workload': f'EmbraceNet arch {args.arch} full train step (fwd+loss+bwd+Adam), global batch {args.batch}, '
                                f'F={F}, 256-bp bases (BASELINE configs[2])',
                    'arch': args.arch, 'global_batch': args.batch, 'per_gpu_batch': B, 'in_features': F,
-                   'optimizer': 'adam+L2', 'precision': args.precision, 'tensor_core': eng.tensor_core, 'cuda_graph': bool(world == 1 and args.graph),
+                   'optimizer': 'adam+L2', 'precision': args.precision, 'tensor_core': eng.tensor_core, 'cuda_graph': bool(args.graph if world == 1 else args.dp_graph),
                    'parallelism': f'dp{world}' if world > 1 else 'single',
                    'l2': f'per-step working set (activations+gradients, ~{eng.ws_bytes / 1e9:.1f} GB) >> 126 MB L2; '
                          f'inputs rotate over {NBUF} resident batches',
@@ -300,6 +303,8 @@ def main():
                                           f'port of the reference, {r["seconds"]:.1f} s of CPU work)'}
     print(json.dumps(line), flush=True)
     if world > 1:
+        if dp is not None:
+            dp.close()        # graphs that captured NCCL collectives must be destroyed before their communicator
         dist.destroy_process_group()
 
 

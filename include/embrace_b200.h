@@ -216,7 +216,11 @@ int emb_profile_read(EmbEngine* e, double* ms_out, double* flops_out, int64_t* l
 int emb_set_tensor_core(EmbEngine* e, int32_t on);
 /* on: emb_train_step (no replayed draws, no data-parallel hooks) captures the whole step -- forward, loss, backward and
  * the optimizer kernel -- into a CUDA graph the second time a batch size is seen and replays it afterwards (inputs are
- * staged into engine-owned buffers; step-dependent scalars live in device memory).  off: destroys the cached graphs. */
+ * staged into engine-owned buffers; step-dependent scalars live in device memory).  off: destroys the cached graphs.
+ * on = 2 (data parallel, opt-in): the step is captured WITH its hooks -- the all-reduce callback (SyncBN sums) and the phase
+ * hook are invoked during capture on the capture stream, so collectives the host enqueues there (NCCL) become graph nodes;
+ * the phase hook is called a second time (phase = 2) after the backward pass, where the host completes its gradient
+ * all-reduce before the captured optimizer kernel; the global positive count travels through a device slot. */
 int emb_set_graph(EmbEngine* e, int32_t on);
 
 /* ---- data-parallel hooks (SyncBN / global loss weights) --------------------------------------

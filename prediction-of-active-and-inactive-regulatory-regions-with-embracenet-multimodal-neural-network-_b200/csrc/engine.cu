@@ -139,6 +139,8 @@ struct EmbEngine {
     // CUDA-graph replay of the whole train step (emb_set_graph): one instantiated graph per batch size
     struct StepGraph { int B; int has_opt; int opt_kind; int64_t kernels; cudaGraphExec_t exec; };
     bool graph_on = false;
+    bool graph_coll = false;         // emb_set_graph(2): the data-parallel hooks (SyncBN / gradient all-reduce callbacks) are captured too
+    int64_t* gpos_dev = nullptr;     // global positive count of the batch for the captured loss kernel (stream-ordered copy per step)
     std::vector<StepGraph> graphs;
     std::vector<int> graph_seen;     // batch sizes that already ran once eagerly (lazy initialisation happens there)
     bool capturing = false;
@@ -1365,6 +1367,7 @@ void emb_destroy(EmbEngine* e) {
     if (!e) return;
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+    if (e->gpos_dev) cudaFree(e->gpos_dev);
     if (e->gstream) { cudaStreamDestroy(e->gstream); cudaEventDestroy(e->gev_in); cudaEventDestroy(e->gev_out); }
     if (e->copy_stream) {
         cudaStreamDestroy(e->copy_stream);
@@ -1556,7 +1559,8 @@ int emb_loss_ce_weighted(EmbEngine* e, const float* logits, const int32_t* label
     if (!logits || !labels) return set_error(EMB_E_ARG, "null logits/labels");
     const bool sharded = e->global_batch > 0 && e->global_pos >= 0;
     ce_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, labels, B, sharded ? e->global_pos : -1, sharded ? e->global_batch : -1,
-                                                         dlogits_out, e->rec, e->rec_count, EmbEngine::MAX_REC);
+                                                         dlogits_out, e->rec, e->rec_count, EmbEngine::MAX_REC,
+                                                         sharded && e->graph_coll ? e->gpos_dev : nullptr);
     EMB_CHECK_LAUNCH();
     LAUNCHED(e);
     return EMB_OK;
@@ -1598,6 +1602,8 @@ int emb_opt_step(EmbEngine* e, const EmbOptConfig* cfg, void* stream) {
 int emb_set_graph(EmbEngine* e, int32_t on) {
     if (!e) return set_error(EMB_E_ARG, "null engine");
     e->graph_on = on != 0;
+    e->graph_coll = on == 2;
+    if (e->graph_coll && !e->gpos_dev) EMB_CUDA_OK(cudaMalloc(&e->gpos_dev, sizeof(int64_t)));
     if (!on) {
         for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
         e->graphs.clear();
@@ -1626,6 +1632,7 @@ static int train_step_graph(EmbEngine* e, const float* x_ffnn, const uint8_t* ba
         EMB_CUDA_OK(cudaMemcpyAsync(e->in_bases, bases, (size_t)B * SEQ_LEN, cudaMemcpyDeviceToDevice, st));
     if (labels != e->in_labels) EMB_CUDA_OK(cudaMemcpyAsync(e->in_labels, labels, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     if (cfg && (rc = opt_step_prepare(e, cfg, st))) return rc;
+    if (e->graph_coll && e->global_pos >= 0) EMB_CUDA_OK(cudaMemcpyAsync(e->gpos_dev, &e->global_pos, sizeof(int64_t), cudaMemcpyHostToDevice, st));
     const int has_opt = cfg ? 1 : 0, kind = cfg ? cfg->kind : -1;
     EmbEngine::StepGraph* g = nullptr;
     for (auto& c : e->graphs) if (c.B == B && c.has_opt == has_opt && c.opt_kind == kind) g = &c;
@@ -1636,6 +1643,7 @@ static int train_step_graph(EmbEngine* e, const float* x_ffnn, const uint8_t* ba
         rc = forward_impl(e, e->in_x, e->in_bases, nullptr, B, true, nullptr, e->logits, st);
         if (!rc) rc = emb_loss_ce_weighted(e, e->logits, e->in_labels, B, e->dlogits, (void*)st);
         if (!rc) rc = backward_impl(e, e->dlogits, st);
+        if (!rc && e->graph_coll && e->phase_hook && e->phase_hook(e->phase_user, 2, (void*)st)) rc = set_error(EMB_E_STATE, "phase hook (2) failed");
         if (!rc && cfg) rc = opt_step_launch(e, st);
         e->capturing = false;
         cudaGraph_t graph = nullptr;
@@ -1663,19 +1671,22 @@ int emb_train_step(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, cons
     int rc = check_ready(e, B, true);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (e->graph_on && !draws && !e->allreduce && !e->phase_hook && !e->prof_on && e->global_batch < 0) {
+    if (e->graph_on && !draws && !e->prof_on && (e->graph_coll || (!e->allreduce && !e->phase_hook && e->global_batch < 0))) {
         // the first step of a batch size runs eagerly (one-time initialisation such as function attributes happens there)
         bool seen = false;
         for (int b : e->graph_seen) seen |= b == B;
         if (seen) return train_step_graph(e, x_ffnn, bases, labels, B, cfg, st);
         e->graph_seen.push_back(B);
     }
+    if (e->graph_coll && e->global_pos >= 0) EMB_CUDA_OK(cudaMemcpyAsync(e->gpos_dev, &e->global_pos, sizeof(int64_t), cudaMemcpyHostToDevice, st));
     rc = forward_impl(e, x_ffnn, bases, nullptr, B, true, draws, e->logits, st);
     if (rc) return rc;
     rc = emb_loss_ce_weighted(e, e->logits, labels, B, e->dlogits, stream);
     if (rc) return rc;
     rc = backward_impl(e, e->dlogits, st);
     if (rc) return rc;
+    // graph-with-collectives mode: the host finishes its gradient all-reduce inside the step (phase 2), before the optimizer
+    if (e->graph_on && e->graph_coll && e->phase_hook && e->phase_hook(e->phase_user, 2, stream)) return set_error(EMB_E_STATE, "phase hook (2) failed");
     if (cfg) rc = emb_opt_step(e, cfg, stream);
     return rc;
 }

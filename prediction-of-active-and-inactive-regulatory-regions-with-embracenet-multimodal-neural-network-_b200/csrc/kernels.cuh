@@ -350,7 +350,7 @@ struct StepMetricsDev { float loss; int tp, fp, fn, tn; };
 __global__ void __launch_bounds__(1024)
 ce_loss_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, int B,
                int64_t n_pos_global, int64_t n_global, float* __restrict__ dlogits, StepMetricsDev* __restrict__ rec_base,
-               int* __restrict__ rec_count, int max_rec) {
+               int* __restrict__ rec_count, int max_rec, const int64_t* __restrict__ n_pos_global_dev = nullptr) {
     __shared__ int s_cnt[5];
     __shared__ float s_red[32];
     __shared__ float s_w[3];
@@ -363,7 +363,7 @@ ce_loss_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lab
     if ((t & 31) == 0 && npos) atomicAdd(&s_cnt[4], npos);
     __syncthreads();
     if (t == 0) {
-        double pos = n_global >= 0 ? (double)n_pos_global : (double)s_cnt[4];
+        double pos = n_global >= 0 ? (double)(n_pos_global_dev ? *n_pos_global_dev : n_pos_global) : (double)s_cnt[4];
         double tot = n_global >= 0 ? (double)n_global : (double)B;
         double neg = tot - pos;
         double pos_inv = pos != 0 ? 1.0 / pos : 0.0, neg_inv = neg != 0 ? 1.0 / neg : 0.0;

@@ -38,7 +38,7 @@ def merge_step_metrics(records, group=None):
 class DataParallel:
     """Wraps an Engine whose rows are this rank's shard of the global batch."""
 
-    def __init__(self, engine, global_batch, rank=None, world=None, group=None, overlap=True):
+    def __init__(self, engine, global_batch, rank=None, world=None, group=None, overlap=True, graph=False):
         self.engine, self.group = engine, group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
@@ -52,12 +52,26 @@ class DataParallel:
         self.cnn_lo, self.cnn_hi = engine.arena_range(pc)
         self.overlap = overlap and dist.get_backend(group) == 'nccl' and self.cnn_hi > self.cnn_lo
         self._pending = []
+        # graph=True (opt-in, NCCL only): the whole step -- SyncBN all-reduces, both parts of the gradient all-reduce and the
+        # optimizer kernel -- is captured into ONE CUDA graph by the engine (emb_set_graph(2)); the callbacks below then run
+        # during capture only, on the capture stream, and every later step is a single graph launch.
+        self.graph = bool(graph) and dist.get_backend(group) == 'nccl'
+        if self.graph and int(graph) < 2:
+            self.overlap = False            # graph=1: one all-reduce of the whole arena after the backward pass; graph=2: early slices
         if self.overlap:
             self.comm_stream = torch.cuda.Stream(device=engine.device)
+        if self.overlap or self.graph:
             engine.set_phase_hook(self._grads_ready)
+        if self.graph:
+            engine.set_graph(True, collectives=True)
 
     def _grads_ready(self, phase):
         g = self.engine.grads
+        if phase == 2:                      # graph mode: after the backward pass, before the optimizer kernel
+            self._finish_gradients()
+            return
+        if not self.overlap:
+            return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.engine.device))
         with torch.cuda.stream(self.comm_stream):
@@ -66,19 +80,38 @@ class DataParallel:
                 if hi > lo:
                     self._pending.append(dist.all_reduce(g[lo:hi], group=self.group, async_op=True))
 
+    def close(self):
+        """Graph mode: destroy the captured step graphs BEFORE the process group goes away -- NCCL keeps a communicator alive
+        (and `destroy_process_group` blocks) for as long as a CUDA graph that captured its collectives exists."""
+        if self.graph:
+            torch.cuda.synchronize(self.engine.device)
+            self.engine.set_graph(False)
+            self.graph = False
+
     def broadcast_parameters(self, src=0):
         dist.broadcast(self.engine.params, src, group=self.group)
         dist.broadcast(self.engine.buffers, src, group=self.group)
 
-    def train_step(self, x_local, bases_local, y_local, n_pos_global, cfg):
+    def _finish_gradients(self):
         eng = self.engine
-        eng.set_global_positives(n_pos_global)
-        eng.train_step(x_local, bases_local, y_local, None)       # forward + loss + backward (SyncBN inside)
         if self.overlap:
             dist.all_reduce(eng.grads[self.cnn_lo:self.cnn_hi], group=self.group)     # the CNN slice, after its backward
             for w in self._pending:
                 w.wait()                                            # the current stream waits for the early slices
             self._pending = []
+            if self.graph:                  # the side stream forked into the capture at phase 1: join it back
+                ev = torch.cuda.Event()
+                ev.record(self.comm_stream)
+                torch.cuda.current_stream(eng.device).wait_event(ev)
         else:
             dist.all_reduce(eng.grads, group=self.group)           # the gradient all-reduce
+
+    def train_step(self, x_local, bases_local, y_local, n_pos_global, cfg):
+        eng = self.engine
+        eng.set_global_positives(n_pos_global)
+        if self.graph:
+            eng.train_step(x_local, bases_local, y_local, cfg)    # one call = one graph launch (collectives and optimizer inside)
+            return
+        eng.train_step(x_local, bases_local, y_local, None)       # forward + loss + backward (SyncBN inside)
+        self._finish_gradients()
         eng.opt_step(cfg)

@@ -4,6 +4,7 @@ PyTorch is plumbing here: it owns the device memory (flat fp32 parameter / gradi
 and the workspace) and the stream; every computation is a call through the C ABI with raw device
 pointers.  There is deliberately no fallback: no GPU or no built library -> EmbError.
 """
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -65,6 +66,7 @@ class Engine:
             tensor_core = precision == 'bf16'
         self.set_tensor_core(tensor_core)
         self._keep = None
+        self._ext_streams = {}
 
     def __del__(self):
         try:
@@ -118,9 +120,11 @@ class Engine:
         N.check(self.lib.emb_set_tensor_core(self._h, 1 if on else 0))
         self.tensor_core = bool(on)
 
-    def set_graph(self, on=True):
-        """Replay the whole train step as one CUDA graph (captured the second time a batch size is seen)."""
-        N.check(self.lib.emb_set_graph(self._h, 1 if on else 0))
+    def set_graph(self, on=True, collectives=False):
+        """Replay the whole train step as one CUDA graph (captured the second time a batch size is seen).
+        collectives=True (data parallel, opt-in): the all-reduce / phase callbacks are invoked DURING capture with torch's
+        current stream switched to the capture stream, so the NCCL collectives they enqueue become nodes of the graph."""
+        N.check(self.lib.emb_set_graph(self._h, (2 if collectives else 1) if on else 0))
         self.graph = bool(on)
 
     def set_shard(self, row_offset, global_batch):
@@ -128,6 +132,16 @@ class Engine:
 
     def set_global_positives(self, n_pos):
         N.check(self.lib.emb_set_global_positives(self._h, int(n_pos)))
+
+    def _on_stream(self, stream):
+        """torch's current stream := the stream the engine is enqueuing on (its own capture stream in graph mode)."""
+        stream = int(stream or 0)
+        if stream == torch.cuda.current_stream(self.device).cuda_stream:
+            return contextlib.nullcontext()
+        ext = self._ext_streams.get(stream)
+        if ext is None:
+            ext = self._ext_streams[stream] = torch.cuda.ExternalStream(stream, device=self.device)
+        return torch.cuda.stream(ext)
 
     def set_allreduce(self, fn):
         """fn(tensor_float64) -> None performs an in-place SUM all-reduce of a device tensor (SyncBN statistics)."""
@@ -140,7 +154,8 @@ class Engine:
                 t = views.get(key)
                 if t is None:
                     t = views[key] = self._ws_view[key[0]:key[0] + count * 8].view(torch.float64)
-                fn(t)
+                with self._on_stream(stream):
+                    fn(t)
                 return 0
             except Exception as ex:           # never unwind through C
                 print('allreduce callback failed:', ex)
@@ -152,7 +167,8 @@ class Engine:
         """fn(phase) -> None is called from inside backward once the non-CNN gradients are final (phase 1)."""
         def cb(user, phase, stream):
             try:
-                fn(int(phase))
+                with self._on_stream(stream):
+                    fn(int(phase))
                 return 0
             except Exception as ex:           # never unwind through C
                 print('phase hook failed:', ex)
