@@ -91,23 +91,25 @@ class Compare_Models_Result():
         return output.float().cpu()
 
     def print_model_difference(self, p_val=0.05):
-        """visual.py:298-325: a comparison model counts as different when p < p_val in at least two folds."""
-        self.counter_dict = defaultdict(lambda: defaultdict(lambda: defaultdict(lambda: defaultdict(lambda: 0))))
-        for task in self.pval_dict.keys():
-            for cell_line in self.pval_dict[task].keys():
-                for fold in self.pval_dict[task][cell_line].keys():
-                    for b_model in self.pval_dict[task][cell_line][fold].keys():
-                        for c_model in self.pval_dict[task][cell_line][fold][b_model].keys():
-                            self.counter_dict[task][cell_line][b_model][c_model] += \
-                                0 if self.pval_dict[task][cell_line][fold][b_model][c_model] >= p_val else 1
-        for task in self.counter_dict.keys():
+        """visual.py:298-325: a comparison model counts as different from a base model when p < p_val in at least two folds.
+        Fills `counter_dict[task][cell_line][base][comparison]` (number of significant folds) and prints the verdicts."""
+        counts = {}
+        for task, cells in self.pval_dict.items():
+            for cell, folds in cells.items():
+                for per_base in folds.values():
+                    for base, others in per_base.items():
+                        slot = counts.setdefault(task, {}).setdefault(cell, {}).setdefault(base, {})
+                        for other, p in others.items():
+                            slot[other] = slot.get(other, 0) + (0 if p >= p_val else 1)     # as the reference: a NaN p-value counts as different
+        self.counter_dict = counts
+        for task, cells in counts.items():
             print(f'\n\n================ TASK: {task} ================')
-            for cell_line in self.counter_dict[task].keys():
-                print(f'\n\n{cell_line}')
-                for b_model in self.counter_dict[task][cell_line].keys():
-                    print(f'\n\nBASE MODEL: {b_model}\n')
-                    for c_model in self.counter_dict[task][cell_line][b_model].keys():
-                        print(f'{c_model} ===> different: {self.counter_dict[task][cell_line][b_model][c_model] >= 2}')
+            for cell, bases in cells.items():
+                print(f'\n\n{cell}')
+                for base, others in bases.items():
+                    print(f'\n\nBASE MODEL: {base}\n')
+                    for other, n_sig in others.items():
+                        print(f'{other} ===> different: {n_sig >= 2}')
 
     def __call__(self, device, base_model='EmbraceNetMultimodal', comparison_models=['FFNN', 'CNN', 'ConcatNetMultimodal'],
                  augmentation_base_model=True, n_folds=3, cell_lines=CELL_LINES, tasks=TASKS, pval_dict=None, data=None):

@@ -134,3 +134,16 @@ def test_compare_models_result_matches_reference(tmp_path):
         assert c3('cuda', pval_dict=pv) is pv
     finally:
         os.chdir(cwd)
+
+
+def test_print_model_difference_counts_like_the_reference(capsys):
+    """visual.py:298-325: significant (p < 0.05, or NaN: the reference tests `p >= p_val`) in at least two folds -> different."""
+    from embrace_b200.BIOINF_tesi.visual import Compare_Models_Result
+    c = Compare_Models_Result()
+    pv = {'t': {'A549': {'1': {'E': {'FFNN': 0.01, 'CNN': 0.5, 'X': float('nan')}},
+                         '2': {'E': {'FFNN': 0.04, 'CNN': 0.01, 'X': float('nan')}},
+                         '3': {'E': {'FFNN': 0.9, 'CNN': 0.2, 'X': 0.7}}}}}
+    assert c('cuda', pval_dict=pv) is pv
+    assert c.counter_dict['t']['A549']['E'] == {'FFNN': 2, 'CNN': 1, 'X': 2}
+    out = capsys.readouterr().out
+    assert 'FFNN ===> different: True' in out and 'CNN ===> different: False' in out and 'BASE MODEL: E' in out
