@@ -249,6 +249,11 @@ def main():
             eng.flush_host()                 # the last step's record is read inside the timed region too
     ms_e2e = timed(e2e_loop, args.steps)
     final = eng.metrics_read(4)
+    if dp is not None:
+        from embrace_b200.dp import merge_step_metrics
+        final = final[-1:] or [dict(loss=0.0, tp=0, fp=0, fn=0, tn=0)]      # the same shape on every rank, whatever was recorded
+        final = merge_step_metrics(final)        # every rank holds its share of the globally normalised loss: report the sum
+        dp.close()                               # graphs that captured NCCL collectives must be destroyed before their communicator
 
     if rank != 0:
         if world > 1:
@@ -303,8 +308,6 @@ def main():
                                           f'port of the reference, {r["seconds"]:.1f} s of CPU work)'}
     print(json.dumps(line), flush=True)
     if world > 1:
-        if dp is not None:
-            dp.close()        # graphs that captured NCCL collectives must be destroyed before their communicator
         dist.destroy_process_group()
 
 
