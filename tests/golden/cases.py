@@ -41,6 +41,15 @@ CASES = {
                          B=6, seed=95, steps=2),
 }
 
+# The benchmark architectures themselves (L = largest point of the search space = bench.py's workload, W = widest
+# docking, M = the 4-conv-layer real trial).  Pinned on the CPU only (test_oracle_golden.py); the GPU suites compare the
+# engine with the oracle on these shapes (test_benchmark_archs_tensor_core_full_step).
+BENCH_CASES = {
+    'archL': dict(spec=ARCH_L, B=3, seed=201, steps=1, force_modal=[False], lr=1e-3, wd=1e-3),
+    'archW': dict(spec=ARCH_W, B=4, seed=211, steps=1, force_modal=[True], lr=1e-3, wd=1e-3),
+    'archM': dict(spec=ARCH_M, B=4, seed=221, steps=2, force_modal=[None, False], lr=1e-3, wd=1e-3),
+}
+
 
 def make_inputs(spec, B, seed):
     """x_ffnn fp64 holding fp32-representable U[0,1) values (features are MinMax-scaled,

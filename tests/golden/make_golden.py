@@ -22,7 +22,7 @@ sys.path.insert(0, HERE)
 
 from oracle import embracenet_oracle as O      # noqa: E402
 import ref_harness as RH                       # noqa: E402
-from cases import CASES, make_inputs, compress  # noqa: E402
+from cases import CASES, BENCH_CASES, make_inputs, compress  # noqa: E402
 
 
 def run_case(M, name, case):
@@ -223,7 +223,11 @@ if __name__ == '__main__':
     assert RH.reference_available(), 'needs /root/reference'
     M = RH.import_reference()
     torch.set_num_threads(4)
-    for name, case in CASES.items():
+    if len(sys.argv) > 1 and sys.argv[1] == 'bench':       # only the benchmark-architecture cases (added later)
+        for name, case in BENCH_CASES.items():
+            run_case(M, name, case)
+        sys.exit(0)
+    for name, case in {**CASES, **BENCH_CASES}.items():
         run_case(M, name, case)
     notrain_fixture(M)
     multinomial_fixture()
