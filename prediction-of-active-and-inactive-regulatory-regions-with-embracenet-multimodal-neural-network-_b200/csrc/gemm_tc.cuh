@@ -132,6 +132,8 @@ struct TcParams {
     int taps_per_cta;       // multi-tap wgrad: this many taps accumulate side by side in TMEM from ONE staged operand pair;
                             // tap t reads the B tile through a descriptor shifted by (tap - pad) rows of 128 bytes
     int tap_pad;
+    int fuse_taps;          // multi-tap wgrad with n_tile == 64 (experimental, EMB_WGRAD_FUSE_TAPS): this many taps per tcgen05.mma -- the 64-wide
+                            // N blocks of ONE instruction are the same B tile 128 bytes (one row = one tap) apart, i.e. LBO = 128
     int grid_m, grid_n, grid_z, total_tiles;
 };
 
@@ -484,6 +486,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const int tap0 = tap_z * multi;
                         const int nt = min(multi, p.n_taps - tap0);
                         const uint64_t da0 = ((uint64_t)da_hi << 32) | (da_lbo | ((sa & 0x3FFFFu) >> 4));
+                        if (p.fuse_taps > 1) {
+                            for (int tt = 0; tt < nt; tt += p.fuse_taps) {
+                                const int g = min(p.fuse_taps, nt - tt);
+                                const uint32_t sbt = sb + p.b.dst_off + (uint32_t)((tap0 + tt - p.tap_pad) * 128);
+                                const uint64_t db0 = ((uint64_t)db_hi << 32) | ((8u << 16) | ((sbt & 0x3FFFFu) >> 4));        // LBO = 128 bytes
+                                const uint32_t idg = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(g * 64 >> 3) << 17);               // N = g * 64
+                                const uint32_t d_t = d_tmem + (uint32_t)(tt * p.n_tile);
+                                for (int s2 = 0; s2 < k_steps; ++s2)
+                                    tc_mma_f16(d_t, da0 + (uint64_t)(s2 * a_kstep), db0 + (uint64_t)(s2 * b_kstep), idg, (it | s2) ? 1u : 0u);
+                            }
+                        } else
                         for (int tt = 0; tt < nt; ++tt) {
                             const uint32_t sbt = sb + p.b.dst_off + (uint32_t)((tap0 + tt - p.tap_pad) * 128);
                             const uint64_t db0 = ((uint64_t)db_hi << 32) | (db_lbo | ((sbt & 0x3FFFFu) >> 4));
@@ -804,6 +817,7 @@ inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int
             const int want = tc_wgrad_taps() > 1 ? tc_wgrad_taps() : 512 / n_tile;
             p.taps_per_cta = std::max(1, std::min(std::min(pr.taps, want), 512 / n_tile));
             p.tap_pad = 0;
+            p.fuse_taps = (n_tile == 64 && p.b.boxes == 1 && getenv("EMB_WGRAD_FUSE_TAPS")) ? std::min(4, p.taps_per_cta) : 1;
             p.tap_in_z = 1; p.n_taps = pr.taps; p.n_off_per_tap = pr.wgrad_tap_stride > 0 ? pr.wgrad_tap_stride : pr.Cin;
             p.n_logical = pr.taps * pr.Cin;
             p.zero_smem = 1;

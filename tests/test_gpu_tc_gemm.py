@@ -1,6 +1,7 @@
 """The tcgen05/TMEM/TMA GEMM kernel (and the SIMT kernel it replaces) against numpy on bf16-rounded inputs,
 for every GEMM-shaped op of the step: Linear fwd/dgrad/wgrad, Conv1d implicit GEMM fwd/dgrad/wgrad."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -152,3 +153,19 @@ def test_onehot_conv_fwd_tc(B, C1, k):
     st = stats.cpu().numpy()
     np.testing.assert_allclose(st[0], got.sum(axis=(0, 1)), rtol=1e-5, atol=1e-3)
     np.testing.assert_allclose(st[1], (got * got).sum(axis=(0, 1)), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.skipif(not os.environ.get('EMB_EXPERIMENTAL'), reason='unverified round-2 candidate: run with EMB_EXPERIMENTAL=1')
+@pytest.mark.parametrize('B,L,Cin,Cout,k', [(64, 124, 64, 96, 15), (16, 58, 64, 128, 11), (9, 25, 64, 64, 5)])
+def test_conv_wgrad_fused_taps(B, L, Cin, Cout, k):
+    """Multi-tap wgrad with up to four taps per tcgen05.mma (EMB_WGRAD_FUSE_TAPS: the 64-wide N blocks of one instruction are
+    the same staged tile one row apart, LBO = 128 bytes) must equal the one-MMA-per-tap form."""
+    rs = np.random.RandomState(B + L + Cin + Cout + k + 7)
+    g, x = rs.standard_normal((B, L, Cout)), rs.standard_normal((B, L, Cin))
+    _, dW, _ = O.conv1d_bwd(np.transpose(q(x), (0, 2, 1)), np.zeros((Cout, Cin, k)), np.transpose(q(g), (0, 2, 1)))
+    os.environ['EMB_WGRAD_FUSE_TAPS'] = '1'
+    try:
+        got = run(5, 1, g, x, (Cout, Cin, k), B=B, L=L, Cin=Cin, Cout=Cout, taps=k)
+    finally:
+        del os.environ['EMB_WGRAD_FUSE_TAPS']
+    check(got, dW, ('conv wgrad, fused taps', B, L, Cin, Cout, k))
