@@ -207,8 +207,9 @@ inline int onehot_conv_wgrad_tc(const uint8_t* bases, const bf16* dy, float* dw,
 //              kernels compute it (a two-term split left 0.2 % of the bf16-rounded outputs one ulp off, enough to re-route
 //              max-pool gradients downstream); resident in shared memory for the whole kernel (32 KB).
 // 16 tcgen05.mma (128 positions x 64 channels x 16; 8 per weight matrix) per half sample, one TMEM accumulator per half; two sets
-// of four epilogue warps (one set per half: the kernel is bound by the latency of this epilogue chain, not by the MMAs) add the bias, round to bf16, stage their 32 x 64 tile in shared memory in the 128B-swizzle pattern and hand it
-// to a TMA tensor store (4 KB per request), and accumulate the layer-0 BatchNorm statistics from the staged (rounded) values.
+// of four epilogue warps (one set per half: the kernel is bound by the latency of this epilogue chain, not by the MMAs) add the
+// bias, round to bf16, stage their 32 x 64 tile in shared memory in the 128B-swizzle pattern and hand it to a TMA tensor store
+// (4 KB per request), and accumulate the layer-0 BatchNorm statistics from the staged (rounded) values.
 // Every output byte is written to HBM once, which is the only compulsory traffic of this op (the lookup kernels were bound
 // by their 5 shared-memory table reads per output).
 //
@@ -234,7 +235,7 @@ onehot_conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_y, const uint8
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* tiles = smem;                                          // [8 epilogue warps][32 rows][128 B], 128B-swizzled
-    uint8_t* wsm = tiles + 8 * OHF_TILE_BYTES;                  // W' in the un-swizzled K-major core-matrix layout
+    uint8_t* wsm = tiles + 8 * OHF_TILE_BYTES;                      // W'1, W'2 in the un-swizzled K-major core-matrix layout
     uint8_t* stages = wsm + OHF_W_BYTES;                            // [stage]{rows[272][16 B], codes[256]}
     float* sbias = (float*)(stages + OHF_STAGES * OHF_STAGE);       // [64]
     float* sred = sbias + 64;                                       // [8 warps][64 channels][2]
@@ -249,7 +250,7 @@ onehot_conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_y, const uint8
     const int n_mine = (int)blockIdx.x < B ? (B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     for (int i = threadIdx.x; i < OHF_STAGES * OHF_STAGE / 16; i += OHF_THREADS) ((uint4*)stages)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < 64 * 64; i += OHF_THREADS) {       // one (channel, tap, base) weight -> its hi and lo slots
+    for (int i = threadIdx.x; i < 64 * 64; i += OHF_THREADS) {       // one (channel, tap, base) weight -> its hi, mid and lo slots
         const int o = i >> 6, t = (i >> 2) & 15, c = i & 3;
         float v = (o < C1 && t < k) ? w[((size_t)o * 4 + c) * k + t] : 0.f;
         const bf16 hi = __float2bfloat16_rn(v);
