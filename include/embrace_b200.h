@@ -118,6 +118,14 @@ int emb_abi_version(void);
 /* number of sm_100 devices visible (0 = none: compute entry points will fail) */
 int emb_device_count(void);
 
+/* Process-wide tuning switches (A/B measurements, verification fall-backs).  Each is read once from the environment
+ * variable of the same upper-case name with an EMB_ prefix at first use and can be changed here; none is consulted on a
+ * launch path through getenv.  Names: k1_pairs, k1_lookup, no_onehot_wgrad_tc, epi_stats, no_tma_k2, prof_dump, conv_reuse,
+ * conv_debug, conv_no_resident, conv_tps1, min_kiters, wgrad_taps, wgrad_ntile, wgrad_fuse_taps, deterministic, k2_wide
+ * (csrc/common.cuh: struct Tuning documents each).  Changing one after a CUDA graph was captured does not alter that graph. */
+int emb_set_option(const char* name, int32_t value);
+int emb_get_option(const char* name, int32_t* value_out);
+
 /* ---- lifetime ------------------------------------------------------------------------------
  * emb_create plans the layer shapes (utils.py:143-153 size_out_convolution chain), the parameter
  * table and the workspace for batches up to max_batch.  No device memory is touched. */
@@ -233,6 +241,28 @@ int emb_set_allreduce(EmbEngine* e, EmbAllreduceFn fn, void* user);
  * those slices of the gradient arena there, overlapped with the rest of the backward pass.  Return 0 on success. */
 typedef int (*EmbPhaseFn)(void* user, int32_t phase, void* stream);
 int emb_set_phase_hook(EmbEngine* e, EmbPhaseFn fn, void* user);
+
+/* ---- data parallelism over NVLink peer memory (csrc/dp_peer.cuh) ------------------------------
+ * One process per GPU; rows of the global batch are partitioned (emb_set_shard).  After emb_dp_attach every exchange of
+ * the train step is a kernel of this library: SyncBN sums and the global positive count travel as one-shot pushes into
+ * every rank's communication block inside the finalize / loss kernels, and emb_opt_step (also inside emb_train_step and
+ * its CUDA graph) becomes reduce-scatter(gradients, peer loads) -> optimizer on this rank's slice -> all-gather(parameters,
+ * peer stores) in one kernel.  No NCCL call and no host callback remains on the step.  Replaces what
+ * torch.nn.parallel.DistributedDataParallel + SyncBatchNorm would add around fit_multimodal's loop body
+ * (training_models_multimodal.py:132-162); the reference itself is single-device.
+ *   comm[q]   rank q's communication block (emb_dp_comm_bytes() bytes, 128-byte aligned, ZEROED before the first attach)
+ *   params[q], grads[q]   rank q's parameter / gradient arenas (entry [rank] = the arenas this engine is bound to)
+ * as pointers valid in THIS process (emb_ipc_export / emb_ipc_open map a peer process's memory; engines sharing a process
+ * pass their pointers directly).  world <= 8.  Every rank must run the same sequence of training steps. */
+int64_t emb_dp_comm_bytes(void);
+int emb_dp_attach(EmbEngine* e, int32_t rank, int32_t world, void* const* comm, float* const* params, float* const* grads);
+int emb_dp_detach(EmbEngine* e);
+/* tests / the split emb_backward + emb_opt_step use: leaves the SUMMED gradient in every rank's gradient arena */
+int emb_dp_allreduce_grads(EmbEngine* e, void* stream);
+/* CUDA IPC plumbing: handle (64 bytes) + byte offset of dev_ptr inside its cudaMalloc allocation; emb_ipc_open maps it into
+ * this process on the current device (peer access enabled lazily) and caches the mapping per handle. */
+int emb_ipc_export(const void* dev_ptr, void* handle_out, int64_t* offset_out);
+int emb_ipc_open(const void* handle, int64_t offset, void** dev_ptr_out);
 
 /* ---- single-kernel entry points (unit tests and micro-benchmarks) ----------------------------*/
 /* K1: Conv1d(4->C1,k) over one-hot input as a gather-sum (CNN_pre.py:39 with in_channels=4).

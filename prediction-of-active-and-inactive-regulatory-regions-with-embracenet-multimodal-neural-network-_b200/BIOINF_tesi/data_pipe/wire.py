@@ -89,23 +89,36 @@ class DeviceLoader:
     def __len__(self):
         return self.n_len
 
+    @property
+    def input_size(self):
+        """Feature width without starting an iteration (utils.get_input_size reads this)."""
+        return int((self.data.x if self.modality == 'FFNN' else self.data.codes).shape[1])
+
     def __iter__(self):
         src = self.data.x if self.modality == 'FFNN' else self.data.codes
-        for idx in self.plan():
+        for idx in self.plan(self.modality):
             ix = torch.as_tensor(idx, dtype=torch.int64, device=self.data.device)
             yield src.index_select(0, ix), self.data.y.index_select(0, ix).reshape(-1, 1)
 
 
 class _Plan:
-    """Materialises one epoch's index batches once and serves the same list to both modality loaders."""
+    """Materialises one epoch's index batches once and serves the same list to both modality loaders.
+
+    Which epoch an iteration belongs to is decided by WHO has already started it, not by counting calls: a modality that
+    starts iterating while the current epoch was already started by that same modality opens a new epoch; the other
+    modality joins the epoch that is open.  A loader iterated on its own (get_input_size over the reference's DataLoader
+    does that, training_models_multimodal.py:313) therefore cannot shift the two modalities against each other -- in the
+    reference it does (each DataLoader owns a sampler whose index lists are shuffled in place per __iter__), and rows of
+    sample i then meet sequences of sample j with the label assert still passing; that mis-pairing is NOT reproduced."""
 
     def __init__(self, make):
-        self.make, self.epoch, self.users = make, None, 0
+        self.make, self.epoch, self.started = make, None, set()
 
-    def __call__(self):
-        if self.users % 2 == 0:
+    def __call__(self, who=None):
+        if self.epoch is None or who is None or who in self.started:
             self.epoch = list(self.make())
-        self.users += 1
+            self.started = set()
+        self.started.add(who)
         return self.epoch
 
 

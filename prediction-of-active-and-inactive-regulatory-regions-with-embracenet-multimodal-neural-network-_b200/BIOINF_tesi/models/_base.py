@@ -121,16 +121,37 @@ class EngineModule(nn.Module):
         return self
 
     def _engine_for(self, x_ffnn, bases):
+        """The engine whose workspace holds a batch of this size.  The first engine is sized with 12.5 % + 8 rows of slack
+        (BalancePos_BatchSampler batches differ by a row or two and arrive shuffled).  A batch that still does not fit
+        re-creates the engine over the same parameter / optimizer arenas: the metric records of the running epoch are
+        carried over on the host (metrics_read() prepends them), the optimizer step count is kept, and the new engine's
+        generator is keyed by a seed derived from the resize count, so its dropout / selection draws do not replay the
+        old engine's."""
         B = (x_ffnn if x_ffnn is not None else bases).shape[0]
         if self._engine is None or B > self._engine.max_batch:
-            cap = max(B, 256)
             old = self._engine
-            state = old.opt_state() if old is not None else None
-            self._engine = Engine(self.spec, cap, precision=self._precision, device=self._dev, seed=self._seed, arenas=self._arenas)
+            cap = max(B + B // 8 + 8, 256)
+            state, seed = None, self._seed
+            if old is not None:
+                state = old.opt_state()
+                self._carry_records = getattr(self, '_carry_records', []) + old.metrics_read()
+                self._resizes = getattr(self, '_resizes', 0) + 1
+                seed = (self._seed + 0x9E3779B97F4A7C15 * self._resizes) & 0xFFFFFFFFFFFFFFFF
+            self._engine = Engine(self.spec, cap, precision=self._precision, device=self._dev, seed=seed, arenas=self._arenas)
             if state is not None:
                 self._engine.set_opt_state(*state)
             del old
         return self._engine
+
+    def metrics_reset(self):
+        self._carry_records = []
+        if self._engine is not None:
+            self._engine.metrics_reset()
+
+    def metrics_read(self):
+        """Per-batch records since the last reset, including those an engine resize carried over."""
+        rec = list(getattr(self, '_carry_records', []))
+        return rec + (self._engine.metrics_read() if self._engine is not None else [])
 
     def _publish_grads(self):
         own = dict(self.named_parameters())
@@ -184,9 +205,9 @@ class EngineModule(nn.Module):
         call: forward(is_training=True), class-weighted CE, backward, optimizer step; loss and confusion counts are
         appended to the device-side metric records."""
         xf, bases, y = self._batch_inputs(x_ffnn, x_cnn, target)
-        eng = self._engine_for(xf, bases)
         if reset_metrics:
-            eng.metrics_reset()
+            self.metrics_reset()
+        eng = self._engine_for(xf, bases)
         self._forward_token += 1
         eng.train_step(xf, bases, y, opt_cfg, draws=draws)
         self._bump_batches_tracked()
@@ -195,9 +216,9 @@ class EngineModule(nn.Module):
     def eval_batch(self, x_ffnn, x_cnn, target, draws=None, reset_metrics=False):
         """model.eval() forward + the same loss/metric record, no gradient (training_models_multimodal.py:167-192)."""
         xf, bases, y = self._batch_inputs(x_ffnn, x_cnn, target)
-        eng = self._engine_for(xf, bases)
         if reset_metrics:
-            eng.metrics_reset()
+            self.metrics_reset()
+        eng = self._engine_for(xf, bases)
         logits = eng.forward(xf, bases, training=False, draws=draws)
         eng.loss(logits, y, want_grad=False)
         return logits

@@ -62,14 +62,14 @@ def run_epochs(model, batches_train, batches_test, n_train, n_test, cfg, num_epo
             d = draws_train(epoch - 1, bi) if draws_train else None
             model.train_batch(x1, x2, target, cfg, draws=d, reset_metrics=not started)
             started = True
-        train_loss, AUPRC_train, _ = _epoch_metrics(model.engine.metrics_read() if started else [], n_train)
+        train_loss, AUPRC_train, _ = _epoch_metrics(model.metrics_read() if started else [], n_train)
         model.eval()
         started = False
         for bi, (x1, x2, target) in enumerate(batches_test()):
             d = draws_test(epoch - 1, bi) if draws_test else None
             model.eval_batch(x1, x2, target, draws=d, reset_metrics=not started)
             started = True
-        test_loss, AUPRC_test, F1_test = _epoch_metrics(model.engine.metrics_read() if started else [], n_test)
+        test_loss, AUPRC_test, F1_test = _epoch_metrics(model.metrics_read() if started else [], n_test)
         AUPRC_train_scores.append(AUPRC_train)
         AUPRC_test_scores.append(AUPRC_test)
         F1_scores.append(F1_test)
@@ -81,6 +81,24 @@ def run_epochs(model, batches_train, batches_test, n_train, n_test, cfg, num_epo
             print('Early stopping the training')
             break
     return AUPRC_train_scores, AUPRC_test_scores, F1_scores
+
+
+def paired_batches(loader):
+    """zip(loader['FFNN'], loader['CNN']) with the reference's two asserts (training_models_multimodal.py:136-137): equal
+    batch lengths and `torch.eq(target, _).all()`.  For device-resident targets the label comparison is accumulated in a
+    device flag and read ONCE when the epoch's iteration ends (no per-batch sync); host targets are compared at once."""
+    flag = None
+    for (x_1, target), (x_2, t2) in zip(loader['FFNN'], loader['CNN']):
+        assert len(x_1) == len(x_2)
+        if torch.is_tensor(target) and target.is_cuda:
+            bad = (target.reshape(-1) != torch.as_tensor(t2).reshape(-1).to(target.device)).any()
+            flag = bad if flag is None else (flag | bad)
+        else:
+            assert torch.equal(torch.as_tensor(target).reshape(-1), torch.as_tensor(t2).reshape(-1).cpu()), \
+                'FFNN and CNN loaders disagree on the labels of a batch'
+        yield x_1, x_2, target
+    if flag is not None and bool(flag):
+        raise AssertionError('FFNN and CNN loaders disagree on the labels of a batch (loaders out of step?)')
 
 
 def fit_multimodal(model, train_loader, test_loader, device, cell_line, task, optimizer=None, num_epochs=100, patience=4, delta=0,
@@ -100,13 +118,7 @@ def fit_multimodal(model, train_loader, test_loader, device, cell_line, task, op
     model = model.double().to(device)            # accepted and ignored: fp32 master weights on the GPU
 
     def pairs(loader):
-        def it():
-            for (x_1, target), (x_2, t2) in zip(loader['FFNN'], loader['CNN']):
-                assert len(x_1) == len(x_2)
-                if not (torch.is_tensor(target) and target.is_cuda):      # the reference's assert, without forcing a device sync
-                    assert torch.equal(torch.as_tensor(target).reshape(-1), torch.as_tensor(t2).reshape(-1).cpu())
-                yield x_1, x_2, target
-        return it
+        return lambda: paired_batches(loader)
     scores = run_epochs(model, pairs(train_loader), pairs(test_loader), len(train_loader['FFNN']), len(test_loader['FFNN']), cfg,
                         num_epochs, patience, delta, verbose, draws_train, draws_test)
     if checkpoint_path:
@@ -202,17 +214,15 @@ class Param_Search_Multimodal():
         for epoch in range(1, self.num_epochs + 1):
             self.model.train()
             started = False
-            for (x_1, target), (x_2, _t) in zip(self.train_loader['FFNN'], self.train_loader['CNN']):
-                assert len(x_1) == len(x_2)
+            for x_1, x_2, target in paired_batches(self.train_loader):
                 self.model.train_batch(x_1, x_2, target, cfg, reset_metrics=not started)
                 started = True
             self.model.eval()
             started = False
-            for (x_1, target), (x_2, _t) in zip(self.test_loader['FFNN'], self.test_loader['CNN']):
-                assert len(x_1) == len(x_2)
+            for x_1, x_2, target in paired_batches(self.test_loader):
                 self.model.eval_batch(x_1, x_2, target, reset_metrics=not started)
                 started = True
-            _, AUPRC_test, _ = _epoch_metrics(self.model.engine.metrics_read() if started else [], n_test)
+            _, AUPRC_test, _ = _epoch_metrics(self.model.metrics_read() if started else [], n_test)
             trial.report(AUPRC_test, epoch)
             if trial.should_prune():
                 raise hpo.TrialPruned()

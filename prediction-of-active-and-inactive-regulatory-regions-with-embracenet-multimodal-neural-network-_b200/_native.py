@@ -62,6 +62,8 @@ SIGNATURES = {
     'emb_last_error': (C.c_char_p, []),
     'emb_abi_version': (C.c_int, []),
     'emb_device_count': (C.c_int, []),
+    'emb_set_option': (C.c_int, [C.c_char_p, C.c_int32]),
+    'emb_get_option': (C.c_int, [C.c_char_p, C.POINTER(C.c_int32)]),
     'emb_create': (C.c_int, [C.POINTER(EmbArchSpec), C.c_int32, C.c_int32, C.POINTER(_P)]),
     'emb_destroy': (None, [_P]),
     'emb_param_count': (C.c_int64, [_P]),
@@ -94,6 +96,12 @@ SIGNATURES = {
     'emb_set_graph': (C.c_int, [_P, C.c_int32]),
     'emb_profile_gemm': (C.c_int, [_P, C.c_int32]),
     'emb_profile_read': (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    'emb_dp_comm_bytes': (C.c_int64, []),
+    'emb_dp_attach': (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    'emb_dp_detach': (C.c_int, [_P]),
+    'emb_dp_allreduce_grads': (C.c_int, [_P, _P]),
+    'emb_ipc_export': (C.c_int, [_P, _P, C.POINTER(C.c_int64)]),
+    'emb_ipc_open': (C.c_int, [_P, C.c_int64, C.POINTER(_P)]),
     'emb_set_allreduce': (C.c_int, [_P, ALLREDUCE_FN, _P]),
     'emb_set_phase_hook': (C.c_int, [_P, PHASE_FN, _P]),
     'emb_k_onehot_conv_fwd': (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
@@ -146,6 +154,17 @@ def lib():
             fn.argtypes = args
         _lib = l
     return _lib
+
+
+def set_option(name, value):
+    """Process-wide tuning switch of the library (include/embrace_b200.h: emb_set_option)."""
+    check(lib().emb_set_option(name.encode(), int(value)))
+
+
+def get_option(name):
+    v = C.c_int32()
+    check(lib().emb_get_option(name.encode(), C.byref(v)))
+    return v.value
 
 
 def check(rc):

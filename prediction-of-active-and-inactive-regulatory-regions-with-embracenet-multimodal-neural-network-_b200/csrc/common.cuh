@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <stdlib.h>
+#include <string.h>
 
 namespace emb {
 
@@ -31,6 +33,58 @@ int set_error(int code, const char* fmt, ...);
             return emb::set_error(-3, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),   \
                                   __FILE__, __LINE__);                                              \
     } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Tuning switches.  Read ONCE per process from the environment (first use), never on the launch path; every switch can
+// also be set through the ABI (emb_set_option(name, value), include/embrace_b200.h lists them).  All default to the
+// production configuration; the non-default values exist for A/B measurements and as verification fall-backs.
+// ---------------------------------------------------------------------------------------------
+struct Tuning {
+    int k1_pairs = 0;            // EMB_K1_PAIRS            K1 lookup forward: tap-pair tables instead of tap-triple tables
+    int k1_lookup = 0;           // EMB_K1_LOOKUP           K1 forward as the shared-memory gather-sum even in bf16 mode (no tensor core)
+    int no_onehot_wgrad_tc = 0;  // EMB_NO_ONEHOT_WGRAD_TC  K1 backward as the position-list histogram
+    int epi_stats = 0;           // EMB_EPI_STATS           BatchNorm statistics inside the conv GEMM epilogue (no separate pass)
+    int no_tma_k2 = 0;           // EMB_NO_TMA_K2           pooling backward without the bulk-copy kernels / arg-max codes
+    int prof_dump = 0;           // EMB_PROF_DUMP           emb_profile_read prints one line per timed GEMM launch
+    int conv_reuse = 1;          // EMB_CONV_REUSE          0: every conv on the per-tap kernel, 1: tap-reuse kernel where it applies
+    int conv_debug = 0;          // EMB_CONV_DEBUG          tap-reuse kernel: skip loads / MMAs / epilogue (timing experiments)
+    int conv_no_resident = 0;    // EMB_CONV_NO_RESIDENT    tap-reuse kernel: always stream the weights
+    int conv_tps1 = 0;           // EMB_CONV_TPS1           tap-reuse kernel: one tap per streamed weight stage
+    int min_kiters = 8;          // EMB_MIN_KITERS          split-K: minimum K blocks per CTA
+    int wgrad_taps = 0;          // EMB_WGRAD_TAPS          conv wgrad taps per CTA (0: as many as TMEM holds, 1: per-tap kernel)
+    int wgrad_ntile = 128;       // EMB_WGRAD_NT            conv wgrad N tile
+    int wgrad_fuse_taps = 0;     // EMB_WGRAD_FUSE_TAPS     conv wgrad with Cin = 64: up to four taps per tcgen05.mma
+    int deterministic = 0;       // EMB_DETERMINISTIC       fixed-order reductions: no split-K, one CTA per reduction column block
+    int k2_wide = 1;             // EMB_K2_WIDE             8-channel (16-byte) forward pooling kernel where C % 8 == 0
+};
+struct TuningName { const char* env; const char* name; int Tuning::*field; };
+inline const TuningName* tuning_names(int* n) {
+    static const TuningName t[] = {
+        {"EMB_K1_PAIRS", "k1_pairs", &Tuning::k1_pairs}, {"EMB_K1_LOOKUP", "k1_lookup", &Tuning::k1_lookup},
+        {"EMB_NO_ONEHOT_WGRAD_TC", "no_onehot_wgrad_tc", &Tuning::no_onehot_wgrad_tc}, {"EMB_EPI_STATS", "epi_stats", &Tuning::epi_stats},
+        {"EMB_NO_TMA_K2", "no_tma_k2", &Tuning::no_tma_k2}, {"EMB_PROF_DUMP", "prof_dump", &Tuning::prof_dump},
+        {"EMB_CONV_REUSE", "conv_reuse", &Tuning::conv_reuse}, {"EMB_CONV_DEBUG", "conv_debug", &Tuning::conv_debug},
+        {"EMB_CONV_NO_RESIDENT", "conv_no_resident", &Tuning::conv_no_resident}, {"EMB_CONV_TPS1", "conv_tps1", &Tuning::conv_tps1},
+        {"EMB_MIN_KITERS", "min_kiters", &Tuning::min_kiters}, {"EMB_WGRAD_TAPS", "wgrad_taps", &Tuning::wgrad_taps},
+        {"EMB_WGRAD_NT", "wgrad_ntile", &Tuning::wgrad_ntile}, {"EMB_WGRAD_FUSE_TAPS", "wgrad_fuse_taps", &Tuning::wgrad_fuse_taps},
+        {"EMB_DETERMINISTIC", "deterministic", &Tuning::deterministic}, {"EMB_K2_WIDE", "k2_wide", &Tuning::k2_wide},
+    };
+    *n = (int)(sizeof t / sizeof t[0]);
+    return t;
+}
+inline Tuning& tuning() {
+    static Tuning t = [] {
+        Tuning v;
+        int n = 0;
+        const TuningName* names = tuning_names(&n);
+        for (int i = 0; i < n; ++i) {
+            const char* e = getenv(names[i].env);
+            if (e) v.*(names[i].field) = (*e == 0) ? 1 : atoi(e);       // an empty value means "on"
+        }
+        return v;
+    }();
+    return t;
+}
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }

@@ -283,7 +283,7 @@ tc_conv_reuse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
 }
 
-inline int tc_conv_mode() { static int v = getenv("EMB_CONV_REUSE") ? atoi(getenv("EMB_CONV_REUSE")) : 1; return v; }
+inline int tc_conv_mode() { return tuning().conv_reuse; }
 
 // Is the tap-reuse kernel applicable / preferable for this conv problem?  (fwd and dgrad only)
 inline bool tc_conv_reuse_ok(const TcProblem& pr) {
@@ -301,11 +301,9 @@ inline bool tc_conv_reuse_ok(const TcProblem& pr) {
 inline int tc_conv_reuse(const TcProblem& pr, const Epilogue& ep, cudaStream_t st) {
     int rc = tc_init();
     if (rc) return rc;
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (first_on_device(0)) {
         cudaError_t err = cudaFuncSetAttribute(tc_conv_reuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_max_smem());
         if (err != cudaSuccess) return set_error(-3, "cudaFuncSetAttribute(tc_conv_reuse_kernel): %s", cudaGetErrorString(err));
-        attr_done = true;
     }
     TcConvParams p = {};
     const bool dgrad = pr.kind == TC_CONV_DGRAD;
@@ -341,7 +339,7 @@ inline int tc_conv_reuse(const TcProblem& pr, const Epilogue& ep, cudaStream_t s
     p.idesc = make_idesc(0, dgrad ? 1 : 0, p.n_tile);
     p.acc_stride = p.n_tile <= 32 ? 32 : p.n_tile <= 64 ? 64 : p.n_tile <= 128 ? 128 : 256;
     p.tmem_cols = 2 * p.acc_stride;
-    p.debug = getenv("EMB_CONV_DEBUG") ? atoi(getenv("EMB_CONV_DEBUG")) : 0;
+    p.debug = tuning().conv_debug;
     const int stats_bytes = ep.bn_stats ? round_up(8 * N * 4, 128) : 0;      // [4 epilogue warps][2][N] floats
     const int budget = tc_max_smem() - 2048 - stats_bytes - TCV_A_SLOTS * p.a_slot_bytes;
     int all_b = p.taps * p.n_chunks * p.b_slot_bytes;
@@ -357,10 +355,10 @@ inline int tc_conv_reuse(const TcProblem& pr, const Epilogue& ep, cudaStream_t s
             all_b = all_tail;
         }
     }
-    p.b_resident = (p.grid_n == 1 && all_b <= budget && !getenv("EMB_CONV_NO_RESIDENT")) ? 1 : 0;
+    p.b_resident = (p.grid_n == 1 && all_b <= budget && !tuning().conv_no_resident) ? 1 : 0;
     if (!p.b_resident) p.b_tail = 0;
     p.tps = 1;
-    if (!p.b_resident && !getenv("EMB_CONV_TPS1"))
+    if (!p.b_resident && !tuning().conv_tps1)
         for (int t : {5, 3, 2})               // the largest group that still leaves three stages in flight
             if (t <= p.taps && budget / (t * p.b_slot_bytes) >= 3 && t * p.b_slot_bytes <= 64 * 1024) { p.tps = t; break; }
     p.b_stages = std::min(TCV_MAX_B_STAGES, budget / (p.tps * p.b_slot_bytes));

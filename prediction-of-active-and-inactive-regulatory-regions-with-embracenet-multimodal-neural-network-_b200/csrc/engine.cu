@@ -23,6 +23,7 @@
 #include "conv_tc.cuh"
 #include "onehot_wgrad_tc.cuh"
 #include "probe.cuh"
+#include "dp_peer.cuh"
 
 namespace emb {
 
@@ -83,6 +84,7 @@ using namespace emb;
 struct EmbEngine {
     EmbArchSpec spec;
     int max_batch, prec, esize;      // esize: bytes per activation element
+    int device = -1;                 // CUDA ordinal of the bound memory; every entry makes it current (emb_bind records it)
     bool use_tc = false;
     std::vector<Tensor> tensors;
     int64_t n_params = 0, n_buffers = 0;
@@ -136,6 +138,13 @@ struct EmbEngine {
     EmbPhaseFn phase_hook = nullptr;
     void* phase_user = nullptr;
     int64_t launches = 0;
+    // peer-memory data parallelism (emb_dp_attach, csrc/dp_peer.cuh): SyncBN / loss-weight / gradient exchanges as kernels
+    bool dp_on = false;
+    DpCtx dp{};
+    DpArenas dp_ar{};
+    unsigned int* dp_epoch = nullptr;      // device counter of training steps (workspace)
+    int64_t* dp_gpos = nullptr;            // device slot: global positive count of the current step (workspace)
+    int64_t dp_lo = 0, dp_hi = 0;          // this rank's slice of the parameter arena (optimizer state and work are sharded)
     // CUDA-graph replay of the whole train step (emb_set_graph): one instantiated graph per batch size
     struct StepGraph { int B; int has_opt; int opt_kind; int64_t kernels; cudaGraphExec_t exec; };
     bool graph_on = false;
@@ -468,6 +477,8 @@ int64_t carve(EmbEngine* e, char* base) {
     e->rec_count = bp.take<int>(1);
     e->rec = bp.take<StepMetricsDev>(EmbEngine::MAX_REC);
     e->opt_scalars = bp.take<OptScalars>(1);
+    e->dp_epoch = bp.take<unsigned int>(1);
+    e->dp_gpos = bp.take<int64_t>(1);
     e->logits = bp.take<float>(Bm * 2);
     e->dlogits = bp.take<float>(Bm * 2);
     e->probs = bp.take<float>(Bm);
@@ -802,7 +813,7 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
                 // vectorised gather-sum; BatchNorm statistics of layer 0 are accumulated by the same kernel
                 const int n_tp = (c.k + 1) / 2, n_tr = (c.k + 2) / 3;
                 const size_t smem3 = (size_t)(n_tr * 125 * c.cout + c.cout + 32 * groups * 16) * sizeof(float) + SEQ_LEN + 2 * c.pad + 32;
-                if (smem3 <= (size_t)tc_max_smem() && B >= 32 && (1024 % groups) == 0 && !getenv("EMB_K1_PAIRS")) {
+                if (smem3 <= (size_t)tc_max_smem() && B >= 32 && (1024 % groups) == 0 && !tuning().k1_pairs) {
                     // tap-triple tables (160 KB for 64 channels, k = 15): one persistent 1024-thread CTA per SM
                     onehot_conv_fwd_triple_kernel<T><<<std::min(B, tc_num_sms()), 1024, smem3, st>>>(bases, e->params + c.w, e->params + c.b, (T*)c.y,
                                                                                                    training ? c.stats : nullptr, B, c.cout, c.k, c.ld);
@@ -833,7 +844,7 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
                 TcProblem pr = {};
                 pr.kind = TC_CONV_FWD; pr.a = (const bf16*)pr_.a; pr.lda = pr_.ld; pr.b = c.wc; pr.ldb = round_up(c.cin, 8);
                 pr.M = B * c.Lc; pr.N = c.cout; pr.B = B; pr.L = c.Lc; pr.Cin = c.cin; pr.Cout = c.cout; pr.taps = c.k; pr.pad = c.pad;
-                if (training && c.cout <= 512 && getenv("EMB_EPI_STATS")) {
+                if (training && c.cout <= 512 && tuning().epi_stats) {
                     ep.bn_stats = c.stats;         // BatchNorm batch statistics accumulated by the GEMM epilogue: no separate pass over y
                     stats_done = true;
                 }
@@ -856,21 +867,25 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
                 EMB_CHECK_LAUNCH();
                 LAUNCHED(e);
             }
-            if (e->allreduce) {
+            if (e->allreduce && !e->dp_on) {
                 int rc = e->allreduce(e->allreduce_user, c.stats, 2 * c.cout, st);
                 if (rc) return set_error(EMB_E_STATE, "allreduce callback failed (%d)", rc);
             }
         }
         double n = (double)(e->global_batch > 0 ? e->global_batch : B) * c.Lc;
-        bn_finalize_kernel<<<cdiv(c.cout, 128), 128, 0, st>>>(c.stats, e->params + c.gamma, e->params + c.beta, e->buffers + c.rm,
-                                                              e->buffers + c.rv, c.scale, c.shift, c.mean, c.rstd, n, c.cout, training ? 1 : 0);
+        if (training && e->dp_on)      // SyncBN: the all-reduce of the partial sums happens inside the finalize kernel (peer memory)
+            bn_finalize_dp_kernel<<<1, 256, 0, st>>>(e->dp, (int)i, c.stats, e->params + c.gamma, e->params + c.beta, e->buffers + c.rm,
+                                                     e->buffers + c.rv, c.scale, c.shift, c.mean, c.rstd, n, c.cout);
+        else
+            bn_finalize_kernel<<<cdiv(c.cout, 128), 128, 0, st>>>(c.stats, e->params + c.gamma, e->params + c.beta, e->buffers + c.rm,
+                                                                  e->buffers + c.rv, c.scale, c.shift, c.mean, c.rstd, n, c.cout, training ? 1 : 0);
         EMB_CHECK_LAUNCH();
         LAUNCHED(e);
         size_t total = (size_t)B * c.Lp * c.cout;
         float p = training ? c.drop : 0.f;
         const float* du = (dr && p > 0.f) ? dr->cnn_drop[i] : nullptr;
         const bool kt_bwd = std::is_same<T, bf16>::value && kt_ok(c.cout, c.ld) && kt_bwd_smem(c.Lc, c.Lp, c.cout) <= (size_t)kt_max_smem() &&
-                            !getenv("EMB_NO_TMA_K2");    // the backward will consume the arg-max codes
+                            !tuning().no_tma_k2;    // the backward will consume the arg-max codes
         if (even) {
             const int blocks = cdiv((size_t)B * (c.cout / 2), 256);
 #define EMB_K2_FWD(MODE)                                                                                                          \
@@ -903,7 +918,7 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
         const int64_t R = (int64_t)B * c.Lc;
         const bool even = (c.cout % 2) == 0;
         const bool kt = std::is_same<T, bf16>::value && kt_ok(c.cout, c.ld) && kt_bwd_smem(c.Lc, c.Lp, c.cout) <= (size_t)kt_max_smem() &&
-                        !getenv("EMB_NO_TMA_K2");
+                        !tuning().no_tma_k2;
         PoolBwdArgs ka = {};
         if (kt) {
             // pass 1 of 2: the BatchNorm reductions only; dz is recomputed (not stored) by pass 2 below
@@ -930,13 +945,17 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
             EMB_CHECK_LAUNCH();
             LAUNCHED(e);
         }
-        if (e->allreduce) {
+        if (e->dp_on) {
+            bn_bwd_finalize_dp_kernel<<<1, 256, 0, st>>>(e->dp, EMB_MAX_CNN + i, c.bstats, e->grads + c.gamma, e->grads + c.beta, c.cout);
+            EMB_CHECK_LAUNCH();
+            LAUNCHED(e);
+        } else if (e->allreduce) {
             int rc = e->allreduce(e->allreduce_user, c.bstats, 2 * c.cout, st);
             if (rc) return set_error(EMB_E_STATE, "allreduce callback failed (%d)", rc);
         }
         // under data parallelism the all-reduced statistics are already global: only the first shard contributes
-        // them to the gradient arena (which the host then sum-reduces across ranks)
-        if (!e->allreduce || e->row_offset == 0) {
+        // them to the gradient arena (which is then sum-reduced across ranks)
+        if (!e->dp_on && (!e->allreduce || e->row_offset == 0)) {
             bn_bwd_finalize_kernel<<<cdiv(c.cout, 128), 128, 0, st>>>(c.bstats, e->grads + c.gamma, e->grads + c.beta, c.cout);
             EMB_CHECK_LAUNCH();
             LAUNCHED(e);
@@ -1039,6 +1058,8 @@ int cnn_backward(EmbEngine* e, int B, cudaStream_t st) {
 int check_ready(EmbEngine* e, int B, bool need_grads) {
     if (!e) return set_error(EMB_E_ARG, "null engine");
     if (!e->params || !e->ws) return set_error(EMB_E_STATE, "emb_bind() has not been called");
+    int cur = -1;
+    if (e->device >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != e->device) EMB_CUDA_OK(cudaSetDevice(e->device));
     if (need_grads && (!e->grads)) return set_error(EMB_E_STATE, "no gradient arena bound");
     if (B < 1 || B > e->max_batch) return set_error(EMB_E_ARG, "batch %d outside [1, %d]", B, e->max_batch);
     return EMB_OK;
@@ -1052,6 +1073,11 @@ int forward_impl(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const 
     e->last_B = B;
     e->last_training = training;
     e->last_bases = bases;
+    if (training && e->dp_on) {
+        dp_epoch_advance_kernel<<<1, 1, 0, st>>>(e->dp_epoch);        // one epoch per training step: the exchange kernels' flag value
+        EMB_CHECK_LAUNCH();
+        LAUNCHED(e);
+    }
     if ((rc = refresh_wcache(e, st))) return rc;
     if (training && e->zero_fwd_bytes) EMB_CUDA_OK(cudaMemsetAsync(e->zero_fwd, 0, e->zero_fwd_bytes, st));
     const Act* ffnn_last = nullptr;
@@ -1335,6 +1361,24 @@ extern "C" {
 const char* emb_last_error(void) { return g_last_error.c_str(); }
 int emb_abi_version(void) { return EMB_ABI_VERSION; }
 
+int emb_set_option(const char* name, int32_t value) {
+    if (!name) return set_error(EMB_E_ARG, "null option name");
+    int n = 0;
+    const TuningName* names = tuning_names(&n);
+    for (int i = 0; i < n; ++i)
+        if (!strcmp(name, names[i].name) || !strcmp(name, names[i].env)) { tuning().*(names[i].field) = value; return EMB_OK; }
+    return set_error(EMB_E_ARG, "unknown option '%s'", name);
+}
+
+int emb_get_option(const char* name, int32_t* value_out) {
+    if (!name || !value_out) return set_error(EMB_E_ARG, "null argument");
+    int n = 0;
+    const TuningName* names = tuning_names(&n);
+    for (int i = 0; i < n; ++i)
+        if (!strcmp(name, names[i].name) || !strcmp(name, names[i].env)) { *value_out = tuning().*(names[i].field); return EMB_OK; }
+    return set_error(EMB_E_ARG, "unknown option '%s'", name);
+}
+
 int emb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -1420,13 +1464,18 @@ int emb_bind(EmbEngine* e, float* params, float* grads, float* buffers, float* o
         if (!params || !workspace) return set_error(EMB_E_ARG, "params and workspace must both be given");
         if (workspace_bytes < e->ws_bytes) return set_error(EMB_E_ARG, "workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)e->ws_bytes);
         if (((uintptr_t)workspace & 255) || ((uintptr_t)params & 15)) return set_error(EMB_E_ARG, "workspace must be 256-byte and params 16-byte aligned");
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, workspace) == cudaSuccess && pa.type == cudaMemoryTypeDevice) EMB_CUDA_OK(cudaSetDevice(pa.device));
         e->params = params; e->grads = grads; e->buffers = buffers; e->opt_m = opt_m; e->opt_v = opt_v; e->ws = (char*)workspace;
     }
+    EMB_CUDA_OK(cudaGetDevice(&e->device));
     carve(e, e->ws);
     if (e->prec == EMB_PREC_BF16) { int rcw = build_wcache_table(e); if (rcw) return rcw; }
     RngState rs{e->seed, 0};
     EMB_CUDA_OK(cudaMemcpy(e->rng, &rs, sizeof rs, cudaMemcpyHostToDevice));
     EMB_CUDA_OK(cudaMemset(e->rec_count, 0, sizeof(int)));
+    EMB_CUDA_OK(cudaMemset(e->dp_epoch, 0, sizeof(unsigned int)));
+    e->dp.epoch = e->dp_epoch;
     cudaFuncSetAttribute(pool_bn_bwd_stage1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SEQ_LEN * 32 * 4);
     cudaFuncSetAttribute(pool_bn_bwd_stage1_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SEQ_LEN * 32 * 4);
     cudaFuncSetAttribute(onehot_conv_bwd_lists_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (SEQ_LEN + 16) * 64 * 4 + 512);
@@ -1479,6 +1528,106 @@ int emb_set_phase_hook(EmbEngine* e, EmbPhaseFn fn, void* user) {
     return EMB_OK;
 }
 
+// ---- data parallelism over peer memory (csrc/dp_peer.cuh) ------------------------------------------------------------------
+static int dp_reduce_launch(EmbEngine* e, cudaStream_t st, int do_opt, int write_grads);
+int64_t emb_dp_comm_bytes(void) { return (int64_t)sizeof(DpComm); }
+
+int emb_dp_attach(EmbEngine* e, int32_t rank, int32_t world, void* const* comm, float* const* params, float* const* grads) {
+    int rc = check_ready(e, 1, true);
+    if (rc) return rc;
+    if (world < 1 || world > DP_MAX_WORLD || rank < 0 || rank >= world) return set_error(EMB_E_ARG, "bad rank/world %d/%d (world <= %d)", rank, world, DP_MAX_WORLD);
+    if (!comm || !params || !grads) return set_error(EMB_E_ARG, "null pointer table");
+    if (params[rank] != e->params || grads[rank] != e->grads) return set_error(EMB_E_ARG, "entry [rank] must be this engine's own arenas");
+    for (auto& c : e->cnn)
+        if (2 * c.cout > DP_SLOT_DOUBLES) return set_error(EMB_E_UNSUPPORTED, "data parallel SyncBN supports up to %d channels", DP_SLOT_DOUBLES / 2);
+    if (e->cnn.size() > (size_t)EMB_MAX_CNN) return set_error(EMB_E_UNSUPPORTED, "too many conv layers");
+    e->dp.rank = rank; e->dp.world = world; e->dp.epoch = e->dp_epoch;
+    for (int q = 0; q < world; ++q) {
+        if (!comm[q] || !params[q] || !grads[q]) return set_error(EMB_E_ARG, "null pointer for rank %d", q);
+        if (((uintptr_t)comm[q] & 127) || ((uintptr_t)params[q] & 15) || ((uintptr_t)grads[q] & 15)) return set_error(EMB_E_ARG, "misaligned peer pointer (rank %d)", q);
+        e->dp.comm[q] = (DpComm*)comm[q];
+        e->dp_ar.params[q] = params[q];
+        e->dp_ar.grads[q] = grads[q];
+    }
+    // contiguous, 16-byte aligned slices of the arena: rank r owns [r * per, (r + 1) * per)
+    const int64_t n = round_up64(e->n_params, 4);
+    const int64_t per = round_up64((n + world - 1) / world, 4);
+    e->dp_lo = std::min<int64_t>(n, (int64_t)rank * per);
+    e->dp_hi = std::min<int64_t>(n, e->dp_lo + per);
+    // a fresh group starts at epoch 0 with clean flags on every member (the caller zeroes the comm blocks before attaching)
+    EMB_CUDA_OK(cudaMemset(e->dp_epoch, 0, sizeof(unsigned int)));
+    for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);       // graphs captured before attaching do not contain the exchanges
+    e->graphs.clear();
+    e->graph_seen.clear();
+    e->dp_on = world > 1;
+    return EMB_OK;
+}
+
+int emb_dp_detach(EmbEngine* e) {
+    if (!e) return set_error(EMB_E_ARG, "null engine");
+    e->dp_on = false;
+    for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+    e->graphs.clear();
+    e->graph_seen.clear();
+    return EMB_OK;
+}
+
+int emb_dp_allreduce_grads(EmbEngine* e, void* stream) {
+    int rc = check_ready(e, 1, true);
+    if (rc) return rc;
+    if (!e->dp_on) return EMB_OK;
+    return dp_reduce_launch(e, (cudaStream_t)stream, 0, 1);
+}
+
+// CUDA IPC plumbing for the peer pointers (one process per GPU).  The handle names the ALLOCATION that contains dev_ptr
+// (PyTorch's caching allocator packs tensors into larger cudaMalloc blocks), *offset_out the position inside it.
+int emb_ipc_export(const void* dev_ptr, void* handle_out, int64_t* offset_out) {
+    if (!dev_ptr || !handle_out || !offset_out) return set_error(EMB_E_ARG, "null argument");
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+    static RangeFn range_fn = nullptr;
+    if (!range_fn) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+            return set_error(EMB_E_CUDA, "cuMemGetAddressRange not available");
+        range_fn = (RangeFn)fn;
+    }
+    if (range_fn(&base, &size, (CUdeviceptr)dev_ptr) != CUDA_SUCCESS) return set_error(EMB_E_CUDA, "cuMemGetAddressRange failed");
+    cudaIpcMemHandle_t h;
+    cudaError_t err = cudaIpcGetMemHandle(&h, (void*)base);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(EMB_E_CUDA, "cudaIpcGetMemHandle: %s (memory must come from cudaMalloc: no expandable segments / cudaMallocAsync)", cudaGetErrorString(err));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    memcpy(handle_out, &h, 64);
+    *offset_out = (int64_t)((CUdeviceptr)dev_ptr - base);
+    return EMB_OK;
+}
+
+int emb_ipc_open(const void* handle, int64_t offset, void** dev_ptr_out) {
+    if (!handle || !dev_ptr_out) return set_error(EMB_E_ARG, "null argument");
+    struct Opened { char h[64]; int dev; void* base; };
+    static std::vector<Opened> opened;                         // a handle can be opened once per process and device: cache the mapping
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (auto& o : opened)
+        if (o.dev == dev && !memcmp(o.h, handle, 64)) { *dev_ptr_out = (char*)o.base + offset; return EMB_OK; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* base = nullptr;
+    cudaError_t err = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) { cudaGetLastError(); return set_error(EMB_E_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(err)); }
+    Opened o;
+    memcpy(o.h, handle, 64);
+    o.dev = dev; o.base = base;
+    opened.push_back(o);
+    *dev_ptr_out = (char*)base + offset;
+    return EMB_OK;
+}
+
 int emb_set_tensor_core(EmbEngine* e, int32_t on) {
     if (!e) return set_error(EMB_E_ARG, "null engine");
     if (on && e->prec != EMB_PREC_BF16) return set_error(EMB_E_UNSUPPORTED, "tensor-core GEMMs need EMB_PREC_BF16");
@@ -1520,7 +1669,7 @@ int emb_profile_read(EmbEngine* e, double* ms_out, double* flops_out, int64_t* l
         float t = 0;
         EMB_CUDA_OK(cudaEventElapsedTime(&t, e->prof_ev[i], e->prof_ev[i + 1]));
         ms += t;
-        if (getenv("EMB_PROF_DUMP") && i / 2 < e->prof_flops_each.size())
+        if (tuning().prof_dump && i / 2 < e->prof_flops_each.size())
             fprintf(stderr, "gemm %3zu  %9.1f us  %8.2f GFLOP  %7.1f TFLOP/s\n", i / 2, t * 1e3, e->prof_flops_each[i / 2] / 1e9,
                     e->prof_flops_each[i / 2] / (t * 1e-3) / 1e12);
     }
@@ -1557,6 +1706,17 @@ int emb_loss_ce_weighted(EmbEngine* e, const float* logits, const int32_t* label
     int rc = check_ready(e, B, false);
     if (rc) return rc;
     if (!logits || !labels) return set_error(EMB_E_ARG, "null logits/labels");
+    if (e->dp_on && e->last_training && e->global_batch > 0) {
+        // data parallel: the class weights come from the GLOBAL positive count, exchanged over peer memory by a one-CTA kernel
+        dp_count_positives_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(e->dp, labels, B, e->dp_gpos);
+        EMB_CHECK_LAUNCH();
+        LAUNCHED(e);
+        ce_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, labels, B, 0, e->global_batch, dlogits_out, e->rec, e->rec_count,
+                                                             EmbEngine::MAX_REC, e->dp_gpos);
+        EMB_CHECK_LAUNCH();
+        LAUNCHED(e);
+        return EMB_OK;
+    }
     const bool sharded = e->global_batch > 0 && e->global_pos >= 0;
     ce_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, labels, B, sharded ? e->global_pos : -1, sharded ? e->global_batch : -1,
                                                          dlogits_out, e->rec, e->rec_count, EmbEngine::MAX_REC,
@@ -1583,7 +1743,25 @@ static int opt_step_prepare(EmbEngine* e, const EmbOptConfig* cfg, cudaStream_t 
     EMB_CUDA_OK(cudaMemcpyAsync(e->opt_scalars, &h, sizeof h, cudaMemcpyHostToDevice, st));
     return EMB_OK;
 }
+// data parallel: reduce-scatter of the gradient arenas + optimizer on this rank's slice + all-gather of the parameters
+static int dp_reduce_launch(EmbEngine* e, cudaStream_t st, int do_opt, int write_grads) {
+    dp_barrier_kernel<<<1, 32, 0, st>>>(e->dp, DP_SYNC_GRADS_READY);          // every rank's backward pass has finished
+    EMB_CHECK_LAUNCH();
+    const int64_t n4 = (e->dp_hi - e->dp_lo) / 4;
+    if (n4 > 0) {
+        const int grid = (int)std::min<int64_t>(tc_num_sms() * 4, cdiv(n4, 256));
+        dp_reduce_opt_kernel<<<grid, 256, 0, st>>>(e->dp.rank, e->dp.world, e->dp_ar, e->opt_m, e->opt_v, e->opt_scalars, (long long)e->dp_lo,
+                                                   (long long)e->dp_hi, do_opt, write_grads);
+        EMB_CHECK_LAUNCH();
+    }
+    dp_barrier_kernel<<<1, 32, 0, st>>>(e->dp, DP_SYNC_PARAMS_DONE);          // everybody's stores have landed; my gradients are free again
+    EMB_CHECK_LAUNCH();
+    e->launches += 3;
+    return EMB_OK;
+}
+
 static int opt_step_launch(EmbEngine* e, cudaStream_t st) {
+    if (e->dp_on) return dp_reduce_launch(e, st, 1, 0);
     int grid = std::min<int64_t>(148 * 8, cdiv(e->n_params, 256));
     opt_step_kernel<<<grid, 256, 0, st>>>(e->params, e->grads, e->opt_m, e->opt_v, e->opt_scalars, (size_t)e->n_params);
     EMB_CHECK_LAUNCH();
@@ -1671,7 +1849,7 @@ int emb_train_step(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, cons
     int rc = check_ready(e, B, true);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (e->graph_on && !draws && !e->prof_on && (e->graph_coll || (!e->allreduce && !e->phase_hook && e->global_batch < 0))) {
+    if (e->graph_on && !draws && !e->prof_on && (e->graph_coll || e->dp_on || (!e->allreduce && !e->phase_hook && e->global_batch < 0))) {
         // the first step of a batch size runs eagerly (one-time initialisation such as function attributes happens there)
         bool seen = false;
         for (int b : e->graph_seen) seen |= b == B;

@@ -615,24 +615,41 @@ inline EncodeTiledFn& encode_fn() { static EncodeTiledFn f = nullptr; return f; 
 inline int& tc_max_smem() { static int v = 0; return v; }
 inline int& tc_num_sms() { static int v = 148; return v; }
 // conv wgrad tiling (tunable for experiments): taps accumulated per CTA (<=1: one tap per CTA) and the N tile
-inline int tc_min_kiters() { static int v = getenv("EMB_MIN_KITERS") ? atoi(getenv("EMB_MIN_KITERS")) : 8; return v; }
-inline int tc_wgrad_taps() { static int v = getenv("EMB_WGRAD_TAPS") ? atoi(getenv("EMB_WGRAD_TAPS")) : 0; return v; }   // 0: as many taps as TMEM holds; 1: per-tap kernel
-inline int tc_wgrad_ntile() { static int v = getenv("EMB_WGRAD_NT") ? atoi(getenv("EMB_WGRAD_NT")) : 128; return v; }
+inline int tc_min_kiters() { return tuning().min_kiters; }
+inline int tc_wgrad_taps() { return tuning().wgrad_taps; }   // 0: as many taps as TMEM holds; 1: per-tap kernel
+inline int tc_wgrad_ntile() { return tuning().wgrad_ntile; }
+
+// true the first time it is called for (slot, current device): cudaFuncSetAttribute is per device
+inline bool first_on_device(int slot) {
+    static bool done[8][64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return true;
+    if (done[slot][dev]) return false;
+    done[slot][dev] = true;
+    return true;
+}
 
 inline int tc_init() {
-    if (encode_fn()) return 0;
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-    if (err != cudaSuccess || !fn) return set_error(-3, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(err));
-    encode_fn() = (EncodeTiledFn)fn;
-    int dev = 0, smem = 0;
+    // per device: cudaFuncSetAttribute applies to the current device's instance of the kernel
+    static bool done[64] = {};
+    int dev = 0;
     cudaGetDevice(&dev);
+    if (encode_fn() && dev >= 0 && dev < 64 && done[dev]) return 0;
+    if (!encode_fn()) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (err != cudaSuccess || !fn) return set_error(-3, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(err));
+        encode_fn() = (EncodeTiledFn)fn;
+    }
+    int smem = 0;
     cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     tc_max_smem() = smem;
     cudaDeviceGetAttribute(&tc_num_sms(), cudaDevAttrMultiProcessorCount, dev);
-    err = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t err = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return set_error(-3, "cudaFuncSetAttribute(tc_gemm_kernel): %s", cudaGetErrorString(err));
+    if (dev >= 0 && dev < 64) done[dev] = true;
     return 0;
 }
 
@@ -817,7 +834,7 @@ inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int
             const int want = tc_wgrad_taps() > 1 ? tc_wgrad_taps() : 512 / n_tile;
             p.taps_per_cta = std::max(1, std::min(std::min(pr.taps, want), 512 / n_tile));
             p.tap_pad = 0;
-            p.fuse_taps = (n_tile == 64 && p.b.boxes == 1 && getenv("EMB_WGRAD_FUSE_TAPS")) ? std::min(4, p.taps_per_cta) : 1;
+            p.fuse_taps = (n_tile == 64 && p.b.boxes == 1 && tuning().wgrad_fuse_taps) ? std::min(4, p.taps_per_cta) : 1;
             p.tap_in_z = 1; p.n_taps = pr.taps; p.n_off_per_tap = pr.wgrad_tap_stride > 0 ? pr.wgrad_tap_stride : pr.Cin;
             p.n_logical = pr.taps * pr.Cin;
             p.zero_smem = 1;

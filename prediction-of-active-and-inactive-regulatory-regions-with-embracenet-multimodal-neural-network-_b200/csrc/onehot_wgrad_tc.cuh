@@ -169,18 +169,16 @@ onehot_conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const ui
 
 inline bool onehot_wgrad_tc_ok(const void* dy, const uint8_t* bases, int C1, int k, int ld) {
     return C1 >= 8 && C1 <= 64 && (C1 % 8) == 0 && ld == C1 && k >= 1 && k <= 15 && (k & 1) && !((uintptr_t)dy & 15) && !((uintptr_t)bases & 15) &&
-           !getenv("EMB_NO_ONEHOT_WGRAD_TC");
+           !tuning().no_onehot_wgrad_tc;
 }
 
 // dw[C1][4][k] += ... (fp32 atomics; the caller zeroes it).  dy: [B, 256, ld] bf16.
 inline int onehot_conv_wgrad_tc(const uint8_t* bases, const bf16* dy, float* dw, int B, int C1, int k, int ld, cudaStream_t st) {
     int rc = tc_init();
     if (rc) return rc;
-    static bool attr = false;
-    if (!attr) {
+    if (first_on_device(1)) {
         cudaError_t e = cudaFuncSetAttribute(onehot_conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OHW_SMEM);
         if (e != cudaSuccess) return set_error(-3, "cudaFuncSetAttribute(onehot_conv_wgrad_tc_kernel): %s", cudaGetErrorString(e));
-        attr = true;
     }
     CUtensorMap map;
     rc = make_map(&map, dy, C1, SEQ_LEN, B, ld, (int64_t)SEQ_LEN * ld, 64, SEQ_LEN, 1);
@@ -405,7 +403,7 @@ onehot_conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_y, const uint8
 
 inline bool onehot_fwd_tc_ok(const void* y, const uint8_t* bases, int C1, int k, int ld) {
     return C1 >= 8 && C1 <= 64 && (C1 % 8) == 0 && ld == C1 && k >= 1 && k <= 15 && (k & 1) && !((uintptr_t)y & 15) && !((uintptr_t)bases & 15) &&
-           !getenv("EMB_K1_LOOKUP");
+           !tuning().k1_lookup;
 }
 
 // y: [B, 256, ld] bf16; stats (nullable): [2][C1] doubles, accumulated (sum, sum of squares of the rounded outputs).
@@ -413,11 +411,9 @@ inline int onehot_conv_fwd_tc(const uint8_t* bases, const float* w, const float*
                               cudaStream_t st) {
     int rc = tc_init();
     if (rc) return rc;
-    static bool attr = false;
-    if (!attr) {
+    if (first_on_device(2)) {
         cudaError_t e = cudaFuncSetAttribute(onehot_conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OHF_SMEM);
         if (e != cudaSuccess) return set_error(-3, "cudaFuncSetAttribute(onehot_conv_fwd_tc_kernel): %s", cudaGetErrorString(e));
-        attr = true;
     }
     CUtensorMap map;
     rc = make_map(&map, y, C1, SEQ_LEN, B, ld, (int64_t)SEQ_LEN * ld, 64, 32, 1);

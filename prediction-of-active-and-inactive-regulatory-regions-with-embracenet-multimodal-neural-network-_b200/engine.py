@@ -239,6 +239,12 @@ class Engine:
         N.check(self.lib.emb_forward_infer(self._h, _ptr(x_ffnn), _ptr(bases), _ptr(av), B, dref, _ptr(logits), _ptr(probs), self.stream))
         return (logits, probs) if want_probs else logits
 
+    def infer(self, x_ffnn, bases, availabilities, probs_out):
+        """Eval-mode forward of device-resident rows straight into `probs_out` ([B] fp32 device tensor): no allocation, no copy."""
+        B = (x_ffnn if x_ffnn is not None else bases).shape[0]
+        N.check(self.lib.emb_forward_infer(self._h, _ptr(x_ffnn), _ptr(bases), _ptr(availabilities), B, None, None, _ptr(probs_out), self.stream))
+        return probs_out
+
     def loss(self, logits, labels, want_grad=True):
         B = logits.shape[0]
         labels = labels.to(device=self.device, dtype=torch.int32).contiguous().view(-1)

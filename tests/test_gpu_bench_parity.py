@@ -1,0 +1,221 @@
+"""Parity of the BENCHMARKED configuration at its own size (BASELINE configs[2]: arch L, batch 8192, bf16 tensor-core path).
+
+One full train step with replayed draws -- forward, weighted CE, backward, Adam -- through the C ABI against
+oracle/torch_port.py, i.e. the reference's own PyTorch-CPU library calls in fp64 (EmbraceNetMultimodal.py:159-193,
+training_models_multimodal.py:132-162).  At these sizes every big GEMM has far more than 148 tiles, so the persistent
+multi-tile loops, the conv3 packing, split-K tails and the pooling kernels' grids run in the regime bench.py times.
+
+What is asserted (measured values are written to gpurun_out/parity_bench_<precision>_<B>.json):
+  selection indices          bit-exact
+  logits                     max-norm and relative L2 error vs the fp64 reference
+  loss                       relative
+  every parameter gradient   relative L2 error and max-norm error per tensor (conv biases behind BatchNorm are analytically
+                             zero: compared in absolute terms against the weight-gradient scale)
+  BatchNorm running stats    max-norm
+  post-Adam parameters       the engine's update vs the fp64 Adam rule applied to the ENGINE's gradients (Adam normalises per
+                             element, so gradient noise must be kept out of this check)
+Tolerances: fp32/SIMT engine 2e-4 / 5e-4 (logits / gradients, max-norm); bf16 tensor-core engine: logits 2e-2 max-norm and
+5e-3 L2, gradients 2e-2 L2 and 6e-2 max-norm -- bf16 storage of every activation (2^-9 relative each) against an fp64
+reference; the batch sum averages the rounding noise of the rows, so the L2 figures are the meaningful ones.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import embracenet_oracle as O
+from tests.golden.cases import ARCH_L, ARCH_S, make_inputs
+from tests.test_gpu_parity import to_archspec, nerr, l2err
+
+pytestmark = pytest.mark.gpu
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+
+TOL = {
+    'fp32': dict(logits_max=2e-4, logits_l2=1e-4, loss=2e-5, grad_l2=5e-4, grad_max=1e-3, bn=1e-5),
+    'bf16': dict(logits_max=2e-2, logits_l2=5e-3, loss=2e-3, grad_l2=2e-2, grad_max=6e-2, bn=2e-3),
+}
+
+
+def big_step(spec, B, precision, tensor_core, seed=700, lr=1e-3, wd=1e-3, tag=''):
+    import torch
+    from embrace_b200 import Engine
+    from oracle import torch_port as TP
+    tol = TOL[precision]
+    P = O.init_params(spec, seed)
+    P = {k: (v.astype(np.float32).astype(np.float64) if v.dtype == np.float64 else v) for k, v in P.items()}   # fp32-representable weights
+    x, bases, y = make_inputs(spec, B, seed + 1)
+    draws = O.make_draws(spec, B, seed + 2, force_modal=True)        # modality dropout on: rows keep one random modality
+
+    # ---- the reference's CPU path, fp64 --------------------------------------------------------------------------
+    torch.set_num_threads(os.cpu_count() or 1)
+    st = TP.TrainState(spec, {k: v.copy() for k, v in P.items()}, 'adam', lr=lr, wd=wd)
+    loss_ref, logits_ref, idx_ref = st.step(torch.from_numpy(x), torch.from_numpy(O.onehot_from_bases(bases)), y, draws)
+    logits_ref = logits_ref.numpy()
+    grads_ref = {k: v.grad.detach().numpy() for k, v in st.T.items() if not O.is_buffer(k)}
+    bufs_ref = {k: v.detach().numpy() for k, v in st.T.items() if k.endswith(('running_mean', 'running_var'))}
+
+    # ---- the engine ------------------------------------------------------------------------------------------------
+    eng = Engine(to_archspec(spec), max_batch=B, precision=precision, tensor_core=tensor_core)
+    eng.load_numpy(P)
+    eng.metrics_reset()
+    logits = eng.forward(torch.from_numpy(x.astype(np.float32)), torch.from_numpy(bases), training=True, draws=draws)
+    dlogits = eng.loss(logits, torch.from_numpy(y))
+    eng.backward(dlogits)
+    got_logits = logits.cpu().numpy()
+    grads = eng.grads_numpy()
+    idx = eng.last_selection(B).cpu().numpy()
+    m = eng.metrics_read()
+    rep = dict(B=B, precision=precision, tensor_core=bool(tensor_core), launches=int(eng.launch_count),
+               logits_max=nerr(got_logits, logits_ref), logits_l2=l2err(got_logits, logits_ref),
+               loss=abs(m[0]['loss'] - loss_ref) / max(1.0, abs(loss_ref)), loss_ref=float(loss_ref), loss_got=float(m[0]['loss']),
+               idx_mismatches=int((idx != idx_ref.numpy()).sum()), grads={})
+    worst_l2 = worst_max = 0.0
+    for k, gr in grads_ref.items():
+        wk = k[:-4] + 'weight'
+        if k.endswith('.bias') and grads_ref[wk].ndim == 3:
+            rep['grads'][k] = dict(abs=float(np.abs(grads[k] - gr).max()), wscale=float(np.abs(grads_ref[wk]).max()))
+            continue
+        e2, em = l2err(grads[k], gr), nerr(grads[k], gr)
+        rep['grads'][k] = dict(l2=e2, max=em)
+        worst_l2, worst_max = max(worst_l2, e2), max(worst_max, em)
+    rep['grad_l2_worst'], rep['grad_max_worst'] = worst_l2, worst_max
+    # optimizer: the engine's update against the fp64 rule on the engine's own gradients
+    P_exp = {k: v.copy() for k, v in P.items()}
+    O.opt_step(P_exp, grads, O.opt_init(P, 'adam'), lr, wd)
+    eng.opt_step(eng.opt_config('adam', lr=lr, weight_decay=wd))
+    got_P = eng.params_numpy()
+    rep['bn'] = max(nerr(got_P[k], v) for k, v in bufs_ref.items()) if bufs_ref else 0.0
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, f'parity_bench_{tag or precision}_{B}.json'), 'w') as f:
+        json.dump(rep, f, indent=1)
+    print(json.dumps({k: v for k, v in rep.items() if k != 'grads'}))
+
+    assert rep['idx_mismatches'] == 0, 'modality selection must be bit-exact'
+    assert np.isfinite(got_logits).all()
+    assert rep['logits_max'] <= tol['logits_max'] and rep['logits_l2'] <= tol['logits_l2'], rep
+    assert rep['loss'] <= tol['loss'], rep
+    for k, r in rep['grads'].items():
+        if 'abs' in r:
+            assert r['abs'] <= (1e-4 if precision == 'fp32' else 5e-2) * max(r['wscale'], 1.0), (k, r)
+        else:
+            assert r['l2'] <= tol['grad_l2'] and r['max'] <= tol['grad_max'], (k, r)
+    assert rep['bn'] <= tol['bn'], rep['bn']
+    for k in grads_ref:
+        amp = 1.2e-7 * max(np.abs(grads[k]).max(), wd * np.abs(P_exp[k]).max()) / 1e-8
+        bound = 2e-6 * np.abs(P_exp[k]).max() + lr * min(1.0, 1e-4 + amp)
+        assert np.abs(got_P[k] - P_exp[k]).max() <= bound, ('adam', k)
+    return rep
+
+
+def test_arch_L_fp32_engine_matches_reference_at_batch_2048():
+    """The verification (fp32 / SIMT) engine against the fp64 reference path at a batch far beyond the golden cases: pins the
+    reference port and the engine to each other at scale before the bf16 comparison below is read."""
+    big_step(ARCH_L, 2048, 'fp32', False)
+
+
+@pytest.mark.parametrize('B', [2048, 8192])
+def test_arch_L_bf16_tensor_core_matches_reference_at_benchmark_batch(B):
+    """bench.py's workload itself: arch L, bf16, tcgen05 GEMMs, batch 8192 (and the 4-GPU shard size 2048)."""
+    big_step(ARCH_L, B, 'bf16', True)
+
+
+def test_arch_S_bf16_tensor_core_matches_reference_at_batch_8192():
+    big_step(ARCH_S, 8192, 'bf16', True, tag='archS_bf16')
+
+
+def test_adamw_matches_decoupled_rule():
+    """EMB_OPT_ADAMW (north_star's fused AdamW; the reference itself runs coupled L2): two steps of the engine's kernel against
+    O.opt_step(decoupled=True) driven by the engine's own gradients."""
+    import torch
+    from embrace_b200 import Engine
+    spec, B = ARCH_S, 64
+    P = O.init_params(spec, 5)
+    P = {k: (v.astype(np.float32).astype(np.float64) if v.dtype == np.float64 else v) for k, v in P.items()}
+    x, bases, y = make_inputs(spec, B, 6)
+    eng = Engine(to_archspec(spec), max_batch=B, precision='fp32', tensor_core=False)
+    eng.load_numpy(P)
+    lr, wd = 3e-3, 5e-2
+    cfg = eng.opt_config('adamw', lr=lr, weight_decay=wd)
+    P_exp = {k: v.copy() for k, v in P.items()}
+    st = O.opt_init(P_exp, 'adam')
+    for step in range(2):
+        draws = O.make_draws(spec, B, 900 + step, force_modal=False)
+        logits = eng.forward(torch.from_numpy(x.astype(np.float32)), torch.from_numpy(bases), training=True, draws=draws)
+        eng.backward(eng.loss(logits, torch.from_numpy(y)))
+        grads = eng.grads_numpy()
+        eng.opt_step(cfg)
+        O.opt_step(P_exp, grads, st, lr, wd, decoupled=True)
+        got = eng.params_numpy()
+        for k in grads:
+            amp = 1.2e-7 * np.abs(grads[k]).max() / 1e-8
+            bound = 2e-6 * np.abs(P_exp[k]).max() + lr * min(1.0, 1e-4 + amp)
+            assert np.abs(got[k] - P_exp[k]).max() <= bound, (step, k)
+        # the decoupled rule must actually differ from coupled L2 at this weight decay
+        if step == 0:
+            P_c = {k: v.copy() for k, v in P.items()}
+            O.opt_step(P_c, grads, O.opt_init(P_c, 'adam'), lr, wd, decoupled=False)
+            assert max(np.abs(P_c[k] - P_exp[k]).max() for k in grads) > 10 * lr * 1e-4
+        for k in P_exp:                       # keep the oracle's buffers in step with the engine's (BatchNorm running stats)
+            if O.is_buffer(k) and k in got:
+                P_exp[k] = got[k]
+
+
+def test_training_curve_auprc_parity_bf16_tensor_core_large_batch():
+    """AUPRC parity after training on the PRODUCTION path (north_star: within 0.002): bf16 storage + tcgen05 GEMMs at batch
+    1024, arch S, against the reference's fp64 CPU path (oracle/torch_port.py) with the same replayed draws; ranking AUPRC
+    (sklearn average_precision_score of the score z1 - z0) and the reference's hard-prediction AUPRC (utils.py:80-86) on
+    16 384 held-out rows."""
+    import torch
+    from sklearn.metrics import average_precision_score
+    from oracle import torch_port as TP
+    from embrace_b200 import Engine
+    spec = ARCH_S
+    rs = np.random.RandomState(3)
+    N, B, steps = 8192, 1024, 40
+    F = spec['F']
+
+    def data(n):
+        x = rs.random_sample((n, F)).astype(np.float32).astype(np.float64)
+        bases = rs.randint(0, 4, size=(n, 256)).astype(np.uint8)
+        motif = np.array([0, 2, 2, 1, 3, 0], dtype=np.uint8)
+        y = (rs.random_sample(n) < 1 / (1 + np.exp(-(6 * (x[:, :4].mean(1) - 0.5) - 1.0)))).astype(np.int64)
+        for i in np.nonzero(y)[0]:
+            if rs.random_sample() < 0.7:
+                pos = rs.randint(0, 250)
+                bases[i, pos:pos + 6] = motif
+        return x, bases, y
+    xtr, btr, ytr = data(N)
+    xte, bte, yte = data(16384)
+    P = O.init_params(spec, 17)
+    P = {k: (v.astype(np.float32).astype(np.float64) if v.dtype == np.float64 else v) for k, v in P.items()}
+    torch.set_num_threads(os.cpu_count() or 1)
+    st = TP.TrainState(spec, {k: v.copy() for k, v in P.items()}, 'adam', lr=3e-3, wd=1e-4)
+    eng = Engine(to_archspec(spec), max_batch=16384, precision='bf16', tensor_core=True)
+    eng.load_numpy(P)
+    cfg = eng.opt_config('adam', lr=3e-3, weight_decay=1e-4)
+    for s in range(steps):
+        lo = (s * B) % N
+        xb, bb, yb = xtr[lo:lo + B], btr[lo:lo + B], ytr[lo:lo + B]
+        draws = O.make_draws(spec, B, 5000 + s)
+        st.step(torch.from_numpy(xb), torch.from_numpy(O.onehot_from_bases(bb)), yb, draws)
+        eng.train_step(torch.from_numpy(xb.astype(np.float32)), torch.from_numpy(bb), torch.from_numpy(yb), cfg, draws=draws)
+    u = np.random.RandomState(9).random_sample((len(yte), spec['C']))
+    with torch.no_grad():
+        Tt = {k: v.detach() for k, v in st.T.items()}
+        ref_logits, _ = TP.forward(spec, Tt, torch.from_numpy(xte), torch.from_numpy(O.onehot_from_bases(bte)), {'embrace_u': u}, training=False)
+    ref_logits = ref_logits.numpy()
+    got_logits = eng.forward(torch.from_numpy(xte.astype(np.float32)), torch.from_numpy(bte), training=False,
+                             draws={'embrace_u': u, 'modal_u0': 0.0}).cpu().numpy()
+    s_ref, s_got = ref_logits[:, 1] - ref_logits[:, 0], got_logits[:, 1] - got_logits[:, 0]
+    rank_ref, rank_got = average_precision_score(yte, s_ref), average_precision_score(yte, s_got)
+    hard_ref, hard_got = O.auprc_hard(ref_logits, yte), O.auprc_hard(got_logits, yte)
+    rep = dict(rank_ref=rank_ref, rank_got=rank_got, hard_ref=hard_ref, hard_got=hard_got, base_rate=float(yte.mean()),
+               flipped_predictions=int(((s_ref > 0) != (s_got > 0)).sum()), launches=int(eng.launch_count))
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, 'auprc_parity_bf16_tc.json'), 'w') as f:
+        json.dump(rep, f, indent=1)
+    print(json.dumps(rep))
+    assert rank_ref > yte.mean() + 0.05, 'the planted signal must be learnable'
+    assert abs(rank_ref - rank_got) <= 0.002
+    assert abs(hard_ref - hard_got) <= 0.002

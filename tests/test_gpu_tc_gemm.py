@@ -163,9 +163,10 @@ def test_conv_wgrad_fused_taps(B, L, Cin, Cout, k):
     rs = np.random.RandomState(B + L + Cin + Cout + k + 7)
     g, x = rs.standard_normal((B, L, Cout)), rs.standard_normal((B, L, Cin))
     _, dW, _ = O.conv1d_bwd(np.transpose(q(x), (0, 2, 1)), np.zeros((Cout, Cin, k)), np.transpose(q(g), (0, 2, 1)))
-    os.environ['EMB_WGRAD_FUSE_TAPS'] = '1'
+    from embrace_b200 import _native as N
+    N.set_option('wgrad_fuse_taps', 1)
     try:
         got = run(5, 1, g, x, (Cout, Cin, k), B=B, L=L, Cin=Cin, Cout=Cout, taps=k)
     finally:
-        del os.environ['EMB_WGRAD_FUSE_TAPS']
+        N.set_option('wgrad_fuse_taps', 0)
     check(got, dW, ('conv wgrad, fused taps', B, L, Cin, Cout, k))
