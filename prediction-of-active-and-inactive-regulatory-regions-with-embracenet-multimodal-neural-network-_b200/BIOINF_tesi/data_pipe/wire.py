@@ -95,8 +95,13 @@ class DeviceLoader:
         return int((self.data.x if self.modality == 'FFNN' else self.data.codes).shape[1])
 
     def __iter__(self):
+        # NOT a generator: the epoch ticket is taken when iter() is called, which is what lets _Plan see that zip() opened
+        # both modality loaders back to back
+        return self._batches(self.plan.open(self.modality))
+
+    def _batches(self, ticket):
         src = self.data.x if self.modality == 'FFNN' else self.data.codes
-        for idx in self.plan(self.modality):
+        for idx in self.plan.batches(ticket):
             ix = torch.as_tensor(idx, dtype=torch.int64, device=self.data.device)
             yield src.index_select(0, ix), self.data.y.index_select(0, ix).reshape(-1, 1)
 
@@ -104,22 +109,42 @@ class DeviceLoader:
 class _Plan:
     """Materialises one epoch's index batches once and serves the same list to both modality loaders.
 
-    Which epoch an iteration belongs to is decided by WHO has already started it, not by counting calls: a modality that
-    starts iterating while the current epoch was already started by that same modality opens a new epoch; the other
-    modality joins the epoch that is open.  A loader iterated on its own (get_input_size over the reference's DataLoader
-    does that, training_models_multimodal.py:313) therefore cannot shift the two modalities against each other -- in the
-    reference it does (each DataLoader owns a sampler whose index lists are shuffled in place per __iter__), and rows of
-    sample i then meet sequences of sample j with the label assert still passing; that mis-pairing is NOT reproduced."""
+    Two iterators share an epoch exactly when they were OPENED back to back -- iter() on one modality's loader, then iter()
+    on the other's, before the first produced a batch -- which is what `zip(loader['FFNN'], loader['CNN'])` does
+    (training_models_multimodal.py:136).  Any other iterator (a loader walked on its own, e.g. get_input_size over the
+    reference's DataLoader, :313) gets an epoch of its own and cannot shift the two modalities against each other.  In the
+    reference it does: each DataLoader owns a sampler whose index lists are shuffled in place per __iter__, so after one
+    solo pass features of sample i meet the sequence of sample j while the label assert still passes (positives are paired
+    with positives); that mis-pairing is deliberately NOT reproduced."""
+
+    class _Ticket:
+        __slots__ = ('modality', 'epoch', 'started')
+
+        def __init__(self, modality):
+            self.modality, self.epoch, self.started = modality, None, False
 
     def __init__(self, make):
-        self.make, self.epoch, self.started = make, None, set()
+        self.make, self.pending = make, None
 
-    def __call__(self, who=None):
-        if self.epoch is None or who is None or who in self.started:
-            self.epoch = list(self.make())
-            self.started = set()
-        self.started.add(who)
-        return self.epoch
+    def open(self, modality):
+        t = _Plan._Ticket(modality)
+        p = self.pending
+        if p is not None and not p.started and p.modality != modality and p.epoch is None:
+            p.epoch = t.epoch = [None]              # one shared cell, filled by whichever side asks for its batches first
+            self.pending = None
+        else:
+            self.pending = t
+        return t
+
+    def batches(self, ticket):
+        ticket.started = True
+        if self.pending is ticket:
+            self.pending = None
+        if ticket.epoch is None:
+            ticket.epoch = [None]
+        if ticket.epoch[0] is None:
+            ticket.epoch[0] = list(self.make())
+        return ticket.epoch[0]
 
 
 def build_loaders(data: PackedDataset, batch_size=100, training=True, random_state=789):

@@ -1541,6 +1541,17 @@ int emb_dp_attach(EmbEngine* e, int32_t rank, int32_t world, void* const* comm, 
     for (auto& c : e->cnn)
         if (2 * c.cout > DP_SLOT_DOUBLES) return set_error(EMB_E_UNSUPPORTED, "data parallel SyncBN supports up to %d channels", DP_SLOT_DOUBLES / 2);
     if (e->cnn.size() > (size_t)EMB_MAX_CNN) return set_error(EMB_E_UNSUPPORTED, "too many conv layers");
+    {   // CUDA loads kernels lazily, and loading one may synchronise the context: a kernel that is first launched while an
+        // exchange kernel of this device is waiting for a peer ON THE SAME DEVICE (the single-GPU test) would deadlock.  Load now.
+        cudaFuncAttributes fa;
+        EMB_CUDA_OK(cudaFuncGetAttributes(&fa, dp_epoch_advance_kernel));
+        EMB_CUDA_OK(cudaFuncGetAttributes(&fa, dp_barrier_kernel));
+        EMB_CUDA_OK(cudaFuncGetAttributes(&fa, bn_finalize_dp_kernel));
+        EMB_CUDA_OK(cudaFuncGetAttributes(&fa, bn_bwd_finalize_dp_kernel));
+        EMB_CUDA_OK(cudaFuncGetAttributes(&fa, dp_count_positives_kernel));
+        EMB_CUDA_OK(cudaFuncGetAttributes(&fa, dp_reduce_opt_kernel));
+        EMB_CUDA_OK(cudaFuncGetAttributes(&fa, ce_loss_kernel));
+    }
     e->dp.rank = rank; e->dp.world = world; e->dp.epoch = e->dp_epoch;
     for (int q = 0; q < world; ++q) {
         if (!comm[q] || !params[q] || !grads[q]) return set_error(EMB_E_ARG, "null pointer for rank %d", q);

@@ -18,14 +18,15 @@ FWD = [('ffnn0 fwd', LIN(B, 256, 562)), ('ffnn1 fwd', LIN(B, 128, 256)), ('ffnn2
        ('conv1 fwd', CONV(124, 64, 96)), ('conv2 fwd', CONV(58, 96, 256)), ('conv3 fwd', CONV(25, 256, 512)),
        ('docking_0 fwd', LIN(B, 1024, 32)), ('docking_1 fwd + embrace select', LIN(B, 1024, 4096)),
        ('post0 fwd', LIN(B, 512, 1024)), ('post1 fwd', LIN(B, 256, 512))]
-BWD = [('post1 dgrad', LIN(B, 256, 512)), ('post1 wgrad', LIN(B, 256, 512)), ('post0 dgrad', LIN(B, 512, 1024)), ('post0 wgrad', LIN(B, 512, 1024)),
-       ('docking_0 dgrad', LIN(B, 1024, 32)), ('docking_0 wgrad', LIN(B, 1024, 32)),
-       ('docking_1 dgrad', LIN(B, 1024, 4096)), ('docking_1 wgrad', LIN(B, 1024, 4096)),
-       ('ffnn3 dgrad', LIN(B, 32, 64)), ('ffnn3 wgrad', LIN(B, 32, 64)), ('ffnn2 dgrad', LIN(B, 64, 128)), ('ffnn2 wgrad', LIN(B, 64, 128)),
-       ('ffnn1 dgrad', LIN(B, 128, 256)), ('ffnn1 wgrad', LIN(B, 128, 256)), ('ffnn0 wgrad', LIN(B, 256, 562)),
+# backward launch order (engine.cu backward_impl / cnn_backward_t): for every layer the WEIGHT gradient is launched first, then the
+# data gradient (round 1 printed these two labels swapped); the 2-logit head runs on its own dot-product kernels, outside this class
+BWD = [('post1 wgrad', LIN(B, 256, 512)), ('post1 dgrad', LIN(B, 256, 512)), ('post0 wgrad', LIN(B, 512, 1024)), ('post0 dgrad + embrace bwd', LIN(B, 512, 1024)),
+       ('docking_0 wgrad', LIN(B, 1024, 32)), ('docking_0 dgrad', LIN(B, 1024, 32)),
+       ('docking_1 wgrad', LIN(B, 1024, 4096)), ('docking_1 dgrad', LIN(B, 1024, 4096)),
+       ('ffnn3 wgrad', LIN(B, 32, 64)), ('ffnn3 dgrad', LIN(B, 32, 64)), ('ffnn2 wgrad', LIN(B, 64, 128)), ('ffnn2 dgrad', LIN(B, 64, 128)),
+       ('ffnn1 wgrad', LIN(B, 128, 256)), ('ffnn1 dgrad', LIN(B, 128, 256)), ('ffnn0 wgrad', LIN(B, 256, 562)),
        ('conv3 wgrad', CONV(25, 256, 512)), ('conv3 dgrad', CONV(25, 256, 512)), ('conv2 wgrad', CONV(58, 96, 256)),
        ('conv2 dgrad', CONV(58, 96, 256)), ('conv1 wgrad', CONV(124, 64, 96)), ('conv1 dgrad', CONV(124, 64, 96))]
-
 
 def main(path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -37,8 +38,9 @@ def main(path):
     recs = load(path)
     T = 'gpu__time_duration.sum'
     firsts = [i for i, d in enumerate(recs) if d['name'].startswith('wcache_fused_kernel')]
-    lo = [i for i in firsts if i + 78 <= len(recs)][-1]                # the last complete step of the capture
-    step = recs[lo:lo + 78]
+    assert len(firsts) >= 2, 'need at least one complete step (two weight-cache refreshes) in the capture'
+    lo, hi = firsts[-2], firsts[-1]                                    # the last complete step of the capture
+    step = recs[lo:hi]
     gemms = [d for d in step if d['name'] in GEMM]
     assert len(gemms) == len(FWD) + len(BWD), len(gemms)
     print(f'peaks: {tf_peak:.0f} TFLOP/s bf16 (sustained, measured), {bw_peak:.0f} GB/s HBM (measured)\n')

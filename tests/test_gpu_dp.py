@@ -67,7 +67,7 @@ def test_dp2_on_one_device_equals_large_batch(precision, tc, GB):
         e.metrics_reset()
         engines.append(e)
         streams.append(torch.cuda.Stream(device=dev))
-        inputs.append((torch.from_numpy(x[lo:hi].astype(np.float32)).to(dev), torch.from_numpy(bases[lo:hi]).to(dev), torch.from_numpy(y[lo:hi]).to(dev)))
+        inputs.append((torch.from_numpy(x[lo:hi].astype(np.float32)).to(dev), torch.from_numpy(bases[lo:hi]).to(dev), torch.from_numpy(y[lo:hi].astype(np.int32)).to(dev)))
     blocks = attach_local(engines, GB)
     torch.cuda.synchronize()
     cfgs = [e.opt_config('adam', lr=lr, weight_decay=wd) for e in engines]
@@ -153,7 +153,7 @@ def test_dp_selection_is_partition_invariant_on_one_device():
     ins = []
     for r in range(3):
         lo, hi = shard_rows(GB, r, 3)
-        ins.append((torch.from_numpy(x[lo:hi].astype(np.float32)).to(dev), torch.from_numpy(bases[lo:hi]).to(dev), torch.from_numpy(y[lo:hi]).to(dev)))
+        ins.append((torch.from_numpy(x[lo:hi].astype(np.float32)).to(dev), torch.from_numpy(bases[lo:hi]).to(dev), torch.from_numpy(y[lo:hi].astype(np.int32)).to(dev)))
     for e, st, (tx, tb, ty) in zip(engines, streams, ins):
         with torch.cuda.stream(st):
             e.train_step(tx, tb, ty, e.opt_config('adam', lr=1e-3, weight_decay=1e-3))
@@ -188,7 +188,7 @@ def _worker(rank, world, port, q, comm, precision, tc, GB, steps):
         cfg = eng.opt_config('adam', lr=1e-3, weight_decay=1e-3)
         lo, hi = dp.lo, dp.hi
         tx, tb, ty = (torch.from_numpy(x[lo:hi].astype(np.float32)).to(dev), torch.from_numpy(bases[lo:hi]).to(dev),
-                      torch.from_numpy(y[lo:hi]).to(dev))
+                      torch.from_numpy(y[lo:hi].astype(np.int32)).to(dev))
         eng.metrics_reset()
         for _ in range(steps):
             dp.train_step(tx, tb, ty, int(y.sum()), cfg)

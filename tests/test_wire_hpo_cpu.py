@@ -71,6 +71,56 @@ def test_loaders_stay_in_lock_step_and_cover_the_data():
             assert max(pos) - min(pos) <= 1
 
 
+def test_loaders_stay_paired_after_a_solo_iteration():
+    """Param_Search_Multimodal._build calls get_input_size(train_loader['FFNN']) once per trial
+    (training_models_multimodal.py:313 in the reference), which iterates ONE loader on its own.  The two modality loaders
+    must still hand out the same rows afterwards, in every later epoch, whichever of them is started first."""
+    from embrace_b200.BIOINF_tesi.models.utils.utils import get_input_size
+    from embrace_b200.BIOINF_tesi.models.utils.training_models_multimodal import paired_batches
+    rs = np.random.RandomState(1)
+    n = 1000
+    x = rs.random_sample((n, 5)).astype(np.float32)
+    codes = rs.randint(0, 4, (n, 256)).astype(np.uint8)
+    x[:, 0] = np.arange(n)                                  # row identity travels in the features ...
+    codes[:, 0] = np.arange(n) % 4                          # ... and in the sequences
+    codes[:, 1] = (np.arange(n) // 4) % 4
+    codes[:, 2] = (np.arange(n) // 16) % 4
+    codes[:, 3] = (np.arange(n) // 64) % 4
+    codes[:, 4] = (np.arange(n) // 256) % 4
+    y = (rs.random_sample(n) < 0.15).astype(int)
+    data = PackedDataset(x, codes, y, device='cpu')
+
+    def row_of_codes(c):
+        c = c.numpy().astype(np.int64)
+        return c[:, 0] + 4 * c[:, 1] + 16 * c[:, 2] + 64 * c[:, 3] + 256 * c[:, 4]
+    for training in (True, False):
+        L = build_loaders(data, batch_size=100, training=training)
+        assert get_input_size(L['FFNN']) == 5                # answered from the tensor shape: no iteration is started
+        for _, _ in L['FFNN']:                               # a genuine solo iteration (what the reference's DataLoader would see)
+            break
+        for order in (('FFNN', 'CNN'), ('CNN', 'FFNN'), ('FFNN', 'CNN')):
+            seen = 0
+            for (a, ta), (b, tb) in zip(L[order[0]], L[order[1]]):
+                xa, cb = (a, b) if order[0] == 'FFNN' else (b, a)
+                assert torch.equal(ta, tb)
+                assert np.array_equal(xa[:, 0].numpy().astype(np.int64), row_of_codes(cb)), 'features and sequences of different samples were paired'
+                seen += len(xa)
+            assert seen == n
+        list(L['CNN'])                                       # a solo pass over the other modality
+        for x1, x2, t in paired_batches(L):
+            assert np.array_equal(x1[:, 0].numpy().astype(np.int64), row_of_codes(x2))
+
+
+def test_paired_batches_raises_when_labels_disagree():
+    from embrace_b200.BIOINF_tesi.models.utils.training_models_multimodal import paired_batches
+    a = [(torch.zeros(3, 2), torch.tensor([[1], [0], [0]]))]
+    b = [(torch.zeros(3, 4, 256), torch.tensor([[1], [1], [0]]))]
+    with pytest.raises(AssertionError):
+        list(paired_batches({'FFNN': a, 'CNN': b}))
+    ok = list(paired_batches({'FFNN': a, 'CNN': [(b[0][0], a[0][1])]}))
+    assert len(ok) == 1
+
+
 # ---- sweep substrate -----------------------------------------------------------------------------------
 def _space(trial):
     a = trial.suggest_int('n', 1, 4)
