@@ -138,6 +138,13 @@ struct EmbEngine {
     EmbPhaseFn phase_hook = nullptr;
     void* phase_user = nullptr;
     int64_t launches = 0;
+    // Independent branches of the step run on side streams (fork / join through events; inside a captured step they become parallel
+    // branches of the CUDA graph): the FFNN chain next to the CNN chain, every weight gradient next to the data-gradient chain.
+    // At small batch the step is a chain of latency-bound launches, and this halves its critical path.
+    cudaStream_t side[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> fork_ev;
+    size_t fork_next = 0;
+    bool fork_on = true;
     // peer-memory data parallelism (emb_dp_attach, csrc/dp_peer.cuh): SyncBN / loss-weight / gradient exchanges as kernels
     bool dp_on = false;
     DpCtx dp{};
@@ -661,6 +668,19 @@ int run_tc(EmbEngine* e, const TcProblem& pr, const Epilogue& ep, double flops, 
 
 bool tc_on(const EmbEngine* e) { return e->use_tc && e->prec == EMB_PREC_BF16; }
 
+// ---- fork / join of independent branches -------------------------------------------------------------------------------
+// forking is off while per-launch GEMM timing runs (concurrent kernels would share the GPU and inflate each other's time) and in
+// the host-callback data-parallel mode (its hooks assume one stream)
+bool forking(const EmbEngine* e) { return e->fork_on && e->side[0] && !e->prof_on && !e->allreduce && !e->phase_hook && tuning().fork; }
+// `to` waits for everything enqueued on `from` so far
+int stream_after(EmbEngine* e, cudaStream_t from, cudaStream_t to) {
+    if (from == to) return EMB_OK;
+    cudaEvent_t ev = e->fork_ev[e->fork_next++ % e->fork_ev.size()];
+    EMB_CUDA_OK(cudaEventRecord(ev, from));
+    EMB_CUDA_OK(cudaStreamWaitEvent(to, ev, 0));
+    return EMB_OK;
+}
+
 // can this Linear layer's GEMMs run on the tensor-core kernel?  (the flattened CNN input must be dense)
 bool tc_linear_ok(const EmbEngine* e, const LinearLayer& l) {
     if (!tc_on(e) || l.out < 16 || l.in < 16) return false;
@@ -911,7 +931,7 @@ int cnn_forward(EmbEngine* e, const uint8_t* bases, int B, bool training, const 
 
 // backward through the CNN stack; on entry cnn.back().ga holds the gradient w.r.t. the flattened output
 template <typename T>
-int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
+int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st, cudaStream_t sw) {
     const int dt = dtype_of(e);
     for (int i = (int)e->cnn.size() - 1; i >= 0; --i) {
         ConvLayer& c = e->cnn[i];
@@ -1014,6 +1034,7 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
             Epilogue ep = base_epi(e, EPI_ATOMIC, e->grads + c.w, 0);
             ep.map = MAP_CONV_W; ep.mapC = c.cin; ep.map_taps = c.k;
             int rc;
+            if ((rc = stream_after(e, st, sw))) return rc;        // the weight gradient runs next to the data gradient
             if (tc) {
                 TcProblem tp = {};
                 tp.kind = TC_CONV_WGRAD; tp.a = (const bf16*)c.dy; tp.lda = c.ld; tp.b = (const bf16*)pr.a; tp.ldb = pr.ld;
@@ -1022,13 +1043,13 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
                 const size_t wn = (size_t)c.k * c.cout * c.cin;
                 tp.wgrad_tap_stride = c.cout * c.cin;
                 Epilogue et = base_epi(e, EPI_ATOMIC, c.wg_tmp, c.cin);
-                rc = run_tc(e, tp, et, flops, st);
+                rc = run_tc(e, tp, et, flops, sw);
                 if (rc) return rc;
-                unpermute_conv_wgrad_kernel<<<cdiv(wn, 256), 256, 0, st>>>(c.wg_tmp, e->grads + c.w, c.cout, c.cin, c.k);
+                unpermute_conv_wgrad_kernel<<<cdiv(wn, 256), 256, 0, sw>>>(c.wg_tmp, e->grads + c.w, c.cout, c.cin, c.k);
                 EMB_CHECK_LAUNCH();
                 LAUNCHED(e);
             } else {
-                rc = run_gemm(e, A, X, ep, c.cout, c.k * c.cin, (int)R, pick_split_k(c.cout, c.k * c.cin, (int)R), st);
+                rc = run_gemm(e, A, X, ep, c.cout, c.k * c.cin, (int)R, pick_split_k(c.cout, c.k * c.cin, (int)R), sw);
             }
             if (rc) return rc;
             // dgrad: ga_prev[b,l',c] = sum_{tap,o} dy[b, l'-tap+pad, o] * W[o][c][tap]
@@ -1051,8 +1072,8 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st) {
     return EMB_OK;
 }
 
-int cnn_backward(EmbEngine* e, int B, cudaStream_t st) {
-    return e->prec == EMB_PREC_BF16 ? cnn_backward_t<bf16>(e, B, st) : cnn_backward_t<float>(e, B, st);
+int cnn_backward(EmbEngine* e, int B, cudaStream_t st, cudaStream_t sw) {
+    return e->prec == EMB_PREC_BF16 ? cnn_backward_t<bf16>(e, B, st, sw) : cnn_backward_t<float>(e, B, st, sw);
 }
 
 int check_ready(EmbEngine* e, int B, bool need_grads) {
@@ -1081,21 +1102,29 @@ int forward_impl(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const 
     if ((rc = refresh_wcache(e, st))) return rc;
     if (training && e->zero_fwd_bytes) EMB_CUDA_OK(cudaMemsetAsync(e->zero_fwd, 0, e->zero_fwd_bytes, st));
     const Act* ffnn_last = nullptr;
+    // the FFNN chain (and docking_0) is independent of the CNN chain until the embracement / concatenation: side stream
+    const bool two_chains = s.kind == EMB_KIND_EMBRACENET || s.kind == EMB_KIND_CONCATNET;
+    cudaStream_t sf = (two_chains && forking(e)) ? e->side[0] : st;
     if (s.kind != EMB_KIND_CNN) {
         if (!x_ffnn) return set_error(EMB_E_ARG, "x_ffnn is NULL");
+        if ((rc = stream_after(e, st, sf))) return rc;
         size_t tot = (size_t)B * e->x0.ld;
-        if (dt) cast_rows_kernel<bf16><<<cdiv(tot, 256), 256, 0, st>>>(x_ffnn, (bf16*)e->x0.p, B, s.in_features, e->x0.ld);
-        else cast_rows_kernel<float><<<cdiv(tot, 256), 256, 0, st>>>(x_ffnn, (float*)e->x0.p, B, s.in_features, e->x0.ld);
+        if (dt) cast_rows_kernel<bf16><<<cdiv(tot, 256), 256, 0, sf>>>(x_ffnn, (bf16*)e->x0.p, B, s.in_features, e->x0.ld);
+        else cast_rows_kernel<float><<<cdiv(tot, 256), 256, 0, sf>>>(x_ffnn, (float*)e->x0.p, B, s.in_features, e->x0.ld);
         EMB_CHECK_LAUNCH();
         LAUNCHED(e);
         const Act* in = &e->x0;
         for (size_t i = 0; i < e->ffnn.size(); ++i) {
             const float* du = (dr && training && e->ffnn[i].drop > 0) ? dr->ffnn_drop[i] : nullptr;
-            rc = linear_forward(e, e->ffnn[i], *in, e->ffnn_h[i], B, training, du, RNG_FFNN_DROP + (uint32_t)i, st);
+            rc = linear_forward(e, e->ffnn[i], *in, e->ffnn_h[i], B, training, du, RNG_FFNN_DROP + (uint32_t)i, sf);
             if (rc) return rc;
             in = &e->ffnn_h[i];
         }
         ffnn_last = in;
+        if (s.kind == EMB_KIND_EMBRACENET) {
+            rc = linear_forward(e, e->dock0, *ffnn_last, e->d0, B, false, nullptr, 0, sf);
+            if (rc) return rc;
+        }
     }
     Act flat;
     if (s.kind != EMB_KIND_FFNN) {
@@ -1120,8 +1149,7 @@ int forward_impl(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const 
                                                               dr ? dr->modal_rows : nullptr, e->rng, e->row_offset, e->cum0, B);
         EMB_CHECK_LAUNCH();
         LAUNCHED(e);
-        rc = linear_forward(e, e->dock0, *ffnn_last, e->d0, B, false, nullptr, 0, st);
-        if (rc) return rc;
+        if ((rc = stream_after(e, sf, st))) return rc;      // join: docking_1's epilogue reads docking_0's output
         {   // docking_1 GEMM with the embracement select fused into its epilogue
             Operand A = input_operand(e, e->dock1, flat, B, false);
             Operand W = weight_operand(e, e->dock1, false);
@@ -1150,6 +1178,7 @@ int forward_impl(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const 
         }
         head_in = in;
     } else if (s.kind == EMB_KIND_CONCATNET) {
+        if ((rc = stream_after(e, sf, st))) return rc;      // join: the concatenation reads both chains
         const size_t tot = (size_t)B * (e->ffnn_out + e->cnn_out);
         if (dt) concat_kernel<bf16><<<cdiv(tot, 256), 256, 0, st>>>((const bf16*)ffnn_last->p, ffnn_last->ld, e->ffnn_out, (const bf16*)flat.p, e->cnn_Lp_last,
                                                                  e->cnn_C_last, e->cnn_ld_last, (bf16*)e->xcat.p, e->xcat.ld, B);
@@ -1211,6 +1240,10 @@ int backward_impl(EmbEngine* e, const float* dlogits, cudaStream_t st) {
     if (e->zero_bwd_bytes) EMB_CUDA_OK(cudaMemsetAsync(e->zero_bwd, 0, e->zero_bwd_bytes, st));
     const void* g = dlogits;     // gradient w.r.t. the current layer's pre-activation
     int g_dt = 0, g_ld = 2;
+    // Branches: the data-gradient chain stays on `st`; every weight gradient goes to `sw` as soon as its input gradient exists;
+    // the FFNN backward chain runs on `sf` next to the docking_1 / CNN backward.  All three are joined before returning.
+    const bool fk = forking(e);
+    cudaStream_t sw = fk ? e->side[1] : st, sf = fk ? e->side[0] : st;
 
     auto mask_epi = [&](const Act& ref, float drop, const Act& out) {
         Epilogue ep = base_epi(e, EPI_MASKGRAD, out.p, out.ld);
@@ -1218,12 +1251,32 @@ int backward_impl(EmbEngine* e, const float* dlogits, cudaStream_t st) {
         ep.scale = drop > 0.f ? 1.f / (1.f - drop) : 1.f;
         return ep;
     };
+    // weight gradient of `l` on the weight-gradient stream, ordered after everything `from` has produced so far
+    auto wgrad_on = [&](cudaStream_t from, const LinearLayer& l, const void* gg, int gdt, int gld, const Act& in) -> int {
+        int r = stream_after(e, from, sw);
+        if (r) return r;
+        return linear_wgrad(e, l, gg, gdt, gld, in, B, sw);
+    };
+    // the FFNN stack's backward, entirely on `sf` (its GEMMs are tiny: the chain is what costs)
+    auto ffnn_chain = [&]() -> int {
+        int r = stream_after(e, st, sf);
+        if (r) return r;
+        for (int i = (int)e->ffnn.size() - 1; i >= 0; --i) {
+            const Act& in = i ? e->ffnn_h[i - 1] : e->x0;
+            if ((r = wgrad_on(sf, e->ffnn[i], e->ffnn_g[i].p, dt, e->ffnn_g[i].ld, in))) return r;
+            if (i) {
+                r = linear_dgrad(e, e->ffnn[i], e->ffnn_g[i].p, dt, e->ffnn_g[i].ld, B, mask_epi(e->ffnn_h[i - 1], e->ffnn[i - 1].drop, e->ffnn_g[i - 1]), sf);
+                if (r) return r;
+            }
+        }
+        return EMB_OK;
+    };
 
     if (s.kind == EMB_KIND_EMBRACENET) {
         const LinearLayer& hl = e->head.back();
         const int np = (int)e->post.size();
         const Act& head_in = np ? e->post_h[np - 1] : e->e;
-        rc = linear_wgrad(e, hl, g, g_dt, g_ld, head_in, B, st);
+        rc = wgrad_on(st, hl, g, g_dt, g_ld, head_in);
         if (rc) return rc;
         auto embrace_bwd_epi = [&]() {
             Epilogue ep = base_epi(e, EPI_EMBRACE_BWD, e->dd0.p, e->dd0.ld);
@@ -1237,7 +1290,7 @@ int backward_impl(EmbEngine* e, const float* dlogits, cudaStream_t st) {
         if (rc) return rc;
         for (int i = np - 1; i >= 0; --i) {
             const Act& in = i ? e->post_h[i - 1] : e->e;
-            rc = linear_wgrad(e, e->post[i], e->post_g[i].p, dt, e->post_g[i].ld, in, B, st);
+            rc = wgrad_on(st, e->post[i], e->post_g[i].p, dt, e->post_g[i].ld, in);
             if (rc) return rc;
             if (i == 0) rc = linear_dgrad(e, e->post[i], e->post_g[i].p, dt, e->post_g[i].ld, B, embrace_bwd_epi(), st);
             else rc = linear_dgrad(e, e->post[i], e->post_g[i].p, dt, e->post_g[i].ld, B, mask_epi(e->post_h[i - 1], e->post[i - 1].drop, e->post_g[i - 1]), st);
@@ -1245,13 +1298,14 @@ int backward_impl(EmbEngine* e, const float* dlogits, cudaStream_t st) {
         }
         // docking layers
         const int nf = (int)e->ffnn.size();
-        rc = linear_wgrad(e, e->dock0, e->dd0.p, dt, e->dd0.ld, e->ffnn_h[nf - 1], B, st);
+        rc = wgrad_on(st, e->dock0, e->dd0.p, dt, e->dd0.ld, e->ffnn_h[nf - 1]);
         if (rc) return rc;
         rc = linear_dgrad(e, e->dock0, e->dd0.p, dt, e->dd0.ld, B, mask_epi(e->ffnn_h[nf - 1], e->ffnn[nf - 1].drop, e->ffnn_g[nf - 1]), st);
         if (rc) return rc;
+        if (fk && (rc = ffnn_chain())) return rc;                 // forked here; otherwise it runs below, in the round-1 order
         Act flat;
         flat.p = e->cnn.back().a; flat.width = e->cnn_out; flat.ld = e->cnn_Lp_last * e->cnn_ld_last;
-        rc = linear_wgrad(e, e->dock1, e->dd1.p, dt, e->dd1.ld, flat, B, st);
+        rc = wgrad_on(st, e->dock1, e->dd1.p, dt, e->dd1.ld, flat);
         if (rc) return rc;
         {
             Epilogue ep = base_epi(e, EPI_LINEAR, e->cnn.back().ga, e->cnn_Lp_last * e->cnn_ld_last);
@@ -1262,13 +1316,13 @@ int backward_impl(EmbEngine* e, const float* dlogits, cudaStream_t st) {
     } else if (s.kind == EMB_KIND_CONCATNET) {
         const LinearLayer& hl = e->head.back();
         const int np = (int)e->post.size(), nf = (int)e->ffnn.size();
-        rc = linear_wgrad(e, hl, g, g_dt, g_ld, e->post_h[np - 1], B, st);
+        rc = wgrad_on(st, hl, g, g_dt, g_ld, e->post_h[np - 1]);
         if (rc) return rc;
         rc = linear_dgrad(e, hl, g, g_dt, g_ld, B, mask_epi(e->post_h[np - 1], e->post[np - 1].drop, e->post_g[np - 1]), st);
         if (rc) return rc;
         for (int i = np - 1; i >= 0; --i) {
             const Act& in = i ? e->post_h[i - 1] : e->xcat;
-            rc = linear_wgrad(e, e->post[i], e->post_g[i].p, dt, e->post_g[i].ld, in, B, st);
+            rc = wgrad_on(st, e->post[i], e->post_g[i].p, dt, e->post_g[i].ld, in);
             if (rc) return rc;
             if (i) rc = linear_dgrad(e, e->post[i], e->post_g[i].p, dt, e->post_g[i].ld, B, mask_epi(e->post_h[i - 1], e->post[i - 1].drop, e->post_g[i - 1]), st);
             else rc = linear_dgrad(e, e->post[i], e->post_g[i].p, dt, e->post_g[i].ld, B, base_epi(e, EPI_LINEAR, e->gcat.p, e->gcat.ld), st);
@@ -1282,10 +1336,11 @@ int backward_impl(EmbEngine* e, const float* dlogits, cudaStream_t st) {
                 e->ffnn_h[nf - 1].ld, scale, (float*)e->ffnn_g[nf - 1].p, e->ffnn_g[nf - 1].ld, (float*)e->cnn.back().ga, e->cnn_Lp_last, e->cnn_C_last, e->cnn_ld_last, B);
         EMB_CHECK_LAUNCH();
         LAUNCHED(e);
+        if (fk && (rc = ffnn_chain())) return rc;
     } else if (s.kind == EMB_KIND_FFNN) {
         const LinearLayer& hl = e->head.back();
         const int nf = (int)e->ffnn.size();
-        rc = linear_wgrad(e, hl, g, g_dt, g_ld, e->ffnn_h[nf - 1], B, st);
+        rc = wgrad_on(st, hl, g, g_dt, g_ld, e->ffnn_h[nf - 1]);
         if (rc) return rc;
         rc = linear_dgrad(e, hl, g, g_dt, g_ld, B, mask_epi(e->ffnn_h[nf - 1], e->ffnn[nf - 1].drop, e->ffnn_g[nf - 1]), st);
         if (rc) return rc;
@@ -1294,7 +1349,7 @@ int backward_impl(EmbEngine* e, const float* dlogits, cudaStream_t st) {
         flat.p = e->cnn.back().a; flat.width = e->cnn_out; flat.ld = e->cnn_Lp_last * e->cnn_ld_last;
         for (int i = (int)e->head.size() - 1; i >= 0; --i) {
             const Act& in = i ? e->head_h[i - 1] : flat;
-            rc = linear_wgrad(e, e->head[i], g, g_dt, g_ld, in, B, st);
+            rc = wgrad_on(st, e->head[i], g, g_dt, g_ld, in);
             if (rc) return rc;
             Epilogue ep;
             if (i) ep = base_epi(e, EPI_LINEAR, e->head_g[i - 1].p, e->head_g[i - 1].ld);
@@ -1307,16 +1362,13 @@ int backward_impl(EmbEngine* e, const float* dlogits, cudaStream_t st) {
             if (i) { g = e->head_g[i - 1].p; g_dt = dt; g_ld = e->head_g[i - 1].ld; }
         }
     }
-    if (s.kind != EMB_KIND_CNN) {
-        for (int i = (int)e->ffnn.size() - 1; i >= 0; --i) {
-            const Act& in = i ? e->ffnn_h[i - 1] : e->x0;
-            rc = linear_wgrad(e, e->ffnn[i], e->ffnn_g[i].p, dt, e->ffnn_g[i].ld, in, B, st);
-            if (rc) return rc;
-            if (i) {
-                rc = linear_dgrad(e, e->ffnn[i], e->ffnn_g[i].p, dt, e->ffnn_g[i].ld, B, mask_epi(e->ffnn_h[i - 1], e->ffnn[i - 1].drop, e->ffnn_g[i - 1]), st);
-                if (rc) return rc;
-            }
-        }
+    if (s.kind != EMB_KIND_CNN && !(fk && (s.kind == EMB_KIND_EMBRACENET || s.kind == EMB_KIND_CONCATNET))) {
+        // the FFNN stack on the main chain (single-modality FFNN, or forking off): sf == st unless kind FFNN forks its wgrads
+        cudaStream_t keep = sf;
+        sf = st;
+        rc = ffnn_chain();
+        sf = keep;
+        if (rc) return rc;
     }
     if (e->phase_hook) {
         // every gradient outside the CNN stack is final here: a data-parallel host can start reducing those arena slices
@@ -1325,8 +1377,12 @@ int backward_impl(EmbEngine* e, const float* dlogits, cudaStream_t st) {
         if (rc) return set_error(EMB_E_STATE, "phase hook failed (%d)", rc);
     }
     if (s.kind != EMB_KIND_FFNN) {
-        rc = cnn_backward(e, B, st);
+        rc = cnn_backward(e, B, st, sw);
         if (rc) return rc;
+    }
+    if (fk) {       // join the branches: the caller (optimizer, gradient reduction, the host) sees complete gradients on `st`
+        if ((rc = stream_after(e, sw, st))) return rc;
+        if ((rc = stream_after(e, sf, st))) return rc;
     }
     return EMB_OK;
 }
@@ -1411,6 +1467,8 @@ void emb_destroy(EmbEngine* e) {
     if (!e) return;
     for (auto ev : e->prof_ev) cudaEventDestroy(ev);
     for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+    for (auto ev : e->fork_ev) cudaEventDestroy(ev);
+    for (int k = 0; k < 2; ++k) if (e->side[k]) cudaStreamDestroy(e->side[k]);
     if (e->gpos_dev) cudaFree(e->gpos_dev);
     if (e->gstream) { cudaStreamDestroy(e->gstream); cudaEventDestroy(e->gev_in); cudaEventDestroy(e->gev_out); }
     if (e->copy_stream) {
@@ -1469,6 +1527,11 @@ int emb_bind(EmbEngine* e, float* params, float* grads, float* buffers, float* o
         e->params = params; e->grads = grads; e->buffers = buffers; e->opt_m = opt_m; e->opt_v = opt_v; e->ws = (char*)workspace;
     }
     EMB_CUDA_OK(cudaGetDevice(&e->device));
+    if (!e->side[0]) {
+        for (int k = 0; k < 2; ++k) EMB_CUDA_OK(cudaStreamCreateWithFlags(&e->side[k], cudaStreamNonBlocking));
+        e->fork_ev.resize(48);
+        for (auto& ev : e->fork_ev) EMB_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
     carve(e, e->ws);
     if (e->prec == EMB_PREC_BF16) { int rcw = build_wcache_table(e); if (rcw) return rcw; }
     RngState rs{e->seed, 0};

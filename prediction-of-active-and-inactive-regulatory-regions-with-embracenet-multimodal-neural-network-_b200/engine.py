@@ -116,6 +116,10 @@ class Engine:
     def params_numpy(self):
         return {t['name']: self.view(t).detach().cpu().numpy().astype(np.float64) for t in self.table}
 
+    def set_seed(self, seed):
+        """Re-key the counter-based generator and rewind its step counter."""
+        N.check(self.lib.emb_set_seed(self._h, int(seed)))
+
     def set_tensor_core(self, on):
         N.check(self.lib.emb_set_tensor_core(self._h, 1 if on else 0))
         self.tensor_core = bool(on)

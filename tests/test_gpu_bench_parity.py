@@ -10,9 +10,12 @@ Two references, both test infrastructure (oracle/torch_port.py):
   bf16emu  the same library calls with values rounded to bfloat16 at exactly the points where EMB_PREC_BF16 STORES a tensor
            (activations, activation gradients, GEMM weight operands) and wide arithmetic everywhere else -- "the engine with
            exact arithmetic".  It is pinned to the numpy oracle's own emulation on the CPU (test_oracle_golden.py).
-The bf16 engine is held to bf16emu tightly (a kernel bug in the many-tile regime shows there) and to fp64 loosely: what
-separates bf16emu from fp64 is the precision contract itself, not the kernels, and the report states both distances side by
-side.  Finding (r2, arch L and S, batch 2048..8192, at initialisation): bf16 storage alone moves the logits by 7e-3 (L2) and
+What separates bf16emu from fp64 is the precision contract itself, not the kernels; what separates the engine from bf16emu
+is fp32 instead of exact accumulation, which the contract amplifies (tests/test_bf16_contract_cpu.py measures that
+sensitivity on the CPU: a 1e-6 relative perturbation of the stored activations moves the emulation's own logits by 3e-3 and
+its CNN gradients by 5 %).  The report states all three distances side by side; kernel bugs in the many-tile regime are
+caught by the fp32 engine against fp64 at batch 2048 (2e-6), by tests/test_gpu_big_tiles.py (GEMMs alone, 2e-4) and by
+the bit-exact selection.  Finding (r2, arch L and S, batch 2048..8192, at initialisation): bf16 storage alone moves the logits by 7e-3 (L2) and
 the parameter gradients by 0.5 % (head) to 20 % (first conv layers) relative L2 against fp64, independent of batch size and
 of whether the labels carry signal -- the numpy emulation shows the same numbers at batch 256..1024; the gradient of a
 freshly initialised network is a difference of near-equal class means, and every stored tensor carries 2^-9 relative rounding.
@@ -42,7 +45,8 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 # engine precision -> reference -> bounds
 TOL = {
     'fp32': {'fp64': dict(logits_max=2e-4, logits_l2=1e-4, loss=2e-5, grad_l2=3e-3, grad_max=1e-2, cos=0.99999, bn=1e-5)},
-    'bf16': {'bf16emu': dict(logits_max=1e-2, logits_l2=3e-3, loss=1e-3, grad_l2=5e-2, grad_max=1e-1, cos=0.998, bn=1e-4),
+    # bf16emu bounds = about 3x the emulation's own sensitivity to a 1e-6 perturbation of what it stores (tests/test_bf16_contract_cpu.py)
+    'bf16': {'bf16emu': dict(logits_max=1.5e-2, logits_l2=8e-3, loss=1e-3, grad_l2=0.15, grad_max=0.25, cos=0.985, bn=1e-4),
              'fp64': dict(logits_max=3e-2, logits_l2=1.2e-2, loss=2e-3, grad_l2=0.30, grad_max=0.40, cos=0.95, bn=4e-3)},
 }
 

@@ -4,8 +4,10 @@ conv3 `whole samples per 128-row tile` packing at B >= 2048, ragged last tiles a
 (tests/test_gpu_tc_gemm.py covers small shapes on both back ends.)
 
 Reference: torch CPU fp32 library calls (nn.Linear / nn.Conv1d forward and their autograd formulas -- the ops the reference
-model is made of, FFNN_pre.py:33, CNN_pre.py:39) on the SAME bf16-rounded inputs; tolerance 2e-3 of the output maximum
-(fp32 accumulation order differs)."""
+model is made of, FFNN_pre.py:33, CNN_pre.py:39) on the SAME bf16-rounded inputs; tolerance 2e-4 of the output maximum:
+bf16 x bf16 products are exact in fp32, so only the accumulation (order, and the tensor core's internal alignment of the
+addends) separates the two -- which also shows that whatever distance the bf16 train step keeps from the exact-arithmetic
+bf16-storage emulation (tests/test_gpu_bench_parity.py) does not come from the GEMMs."""
 import ctypes as C
 
 import numpy as np
@@ -33,10 +35,23 @@ def run_tc(kind, a, b, out_shape, **dims):
     return out.cpu().numpy()
 
 
-def check(got, ref, what, tol=2e-3):
+def check(got, ref, what, tol=2e-4):
     assert np.isfinite(got).all(), what
     err = np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() / max(np.abs(ref).max(), 1e-30)
+    ERRS.append((str(what), float(err)))
     assert err < tol, (what, err)
+
+
+ERRS = []
+
+
+def teardown_module(module):
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, 'big_tiles_errors.json'), 'w') as f:
+        json.dump(ERRS, f, indent=1)
 
 
 def tiles(M, N, n_cap=256):
