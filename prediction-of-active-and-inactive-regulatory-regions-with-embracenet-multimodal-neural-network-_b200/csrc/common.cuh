@@ -56,6 +56,7 @@ struct Tuning {
     int wgrad_fuse_taps = 0;     // EMB_WGRAD_FUSE_TAPS     conv wgrad with Cin = 64: up to four taps per tcgen05.mma
     int deterministic = 0;       // EMB_DETERMINISTIC       fixed-order reductions: no split-K, one CTA per reduction column block
     int k2_wide = 1;             // EMB_K2_WIDE             8-channel (16-byte) forward pooling kernel where C % 8 == 0
+    int infer_fuse = 1;          // EMB_INFER_FUSE          eval forward: BatchNorm + ReLU + MaxPool in the conv GEMM epilogue (no pre-pooling tensor)
     int fork = 1;                // EMB_FORK                independent branches of the step on side streams (parallel graph branches)
 };
 struct TuningName { const char* env; const char* name; int Tuning::*field; };
@@ -69,7 +70,7 @@ inline const TuningName* tuning_names(int* n) {
         {"EMB_MIN_KITERS", "min_kiters", &Tuning::min_kiters}, {"EMB_WGRAD_TAPS", "wgrad_taps", &Tuning::wgrad_taps},
         {"EMB_WGRAD_NT", "wgrad_ntile", &Tuning::wgrad_ntile}, {"EMB_WGRAD_FUSE_TAPS", "wgrad_fuse_taps", &Tuning::wgrad_fuse_taps},
         {"EMB_DETERMINISTIC", "deterministic", &Tuning::deterministic}, {"EMB_K2_WIDE", "k2_wide", &Tuning::k2_wide},
-        {"EMB_FORK", "fork", &Tuning::fork},
+        {"EMB_FORK", "fork", &Tuning::fork}, {"EMB_INFER_FUSE", "infer_fuse", &Tuning::infer_fuse},
     };
     *n = (int)(sizeof t / sizeof t[0]);
     return t;

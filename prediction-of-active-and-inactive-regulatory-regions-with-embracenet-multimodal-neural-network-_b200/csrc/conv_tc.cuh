@@ -250,7 +250,7 @@ tc_conv_reuse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const int r = q * 32 + lane;
         const int grp = r / p.S, r_in = r - grp * p.S;
         const bool r_ok = grp < p.bt && r_in < p.L;
-        int acc = 0;
+        int acc = 0, pool_chunk = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int tile_n = tile % p.grid_n, tile_m = tile / p.grid_n;
@@ -261,6 +261,14 @@ tc_conv_reuse_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             const bool row_ok = r_ok && sample < p.Bn;
             const int n_base = tile_n * p.n_tile;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+            if (ep.mode == EPI_POOL) {
+                for (int c0 = 0; c0 < p.n_tile; c0 += 16, ++pool_chunk) {         // the two staging buffers alternate ACROSS tiles as well
+                    if (n_base + c0 >= p.N) break;                          // uniform over the four epilogue warps
+                    float v[16];
+                    tc_ld16(t_addr + (uint32_t)c0, v);
+                    tc_pool_chunk16(ep, s_stats + (pool_chunk & 1) * (128 * TC_POOL_ROW), r, v, n_base + c0, p.N, p.S, p.bt, tile_m * p.bt, p.Bn);
+                }
+            } else
             if (!(p.debug & 2)) for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
                 if (n_base + c0 >= p.N) break;
                 float v[16];
@@ -340,7 +348,8 @@ inline int tc_conv_reuse(const TcProblem& pr, const Epilogue& ep, cudaStream_t s
     p.acc_stride = p.n_tile <= 32 ? 32 : p.n_tile <= 64 ? 64 : p.n_tile <= 128 ? 128 : 256;
     p.tmem_cols = 2 * p.acc_stride;
     p.debug = tuning().conv_debug;
-    const int stats_bytes = ep.bn_stats ? round_up(8 * N * 4, 128) : 0;      // [4 epilogue warps][2][N] floats
+    const int stats_bytes = ep.mode == EPI_POOL ? TC_POOL_SCRATCH_BYTES      // staging tiles of the fused pooling epilogue
+                                                : ep.bn_stats ? round_up(8 * N * 4, 128) : 0;      // [4 epilogue warps][2][N] floats
     const int budget = tc_max_smem() - 2048 - stats_bytes - TCV_A_SLOTS * p.a_slot_bytes;
     int all_b = p.taps * p.n_chunks * p.b_slot_bytes;
     if (dgrad && p.k_steps_last < 4 && p.grid_n == 1 && all_b > budget) {

@@ -651,6 +651,7 @@ int run_gemm(EmbEngine* e, const Operand& A, const Operand& B, const Epilogue& e
 }
 
 int pick_split_k(int M, int N, int K) {
+    if (tuning().deterministic) return 1;          // one contributor per output element: the atomic accumulation has a fixed order
     int tiles = cdiv(M, SG_BM) * cdiv(N, SG_BN);
     int want = std::max(1, (148 * 4) / std::max(1, tiles));
     int maxk = std::max(1, K / 64);
@@ -760,7 +761,7 @@ int linear_wgrad(EmbEngine* e, const LinearLayer& l, const void* g, int g_dtype,
     int rc;
     if (l.out == 2 && g_dtype == 0 && g_ld == 2 && !l.perm_in) {
         // the 2-logit head: weight and bias gradient in one small kernel
-        const int rpb = 64;
+        const int rpb = tuning().deterministic ? B : 64;       // deterministic: one block owns the whole sum
         if (dtype_of(e)) head_wgrad_kernel<bf16><<<cdiv(B, rpb), 256, 0, st>>>((const float*)g, (const bf16*)in.p, in.ld, e->grads + l.w, e->grads + l.b, B, l.in, rpb);
         else head_wgrad_kernel<float><<<cdiv(B, rpb), 256, 0, st>>>((const float*)g, (const float*)in.p, in.ld, e->grads + l.w, e->grads + l.b, B, l.in, rpb);
         EMB_CHECK_LAUNCH();
@@ -787,7 +788,7 @@ int linear_wgrad(EmbEngine* e, const LinearLayer& l, const void* g, int g_dtype,
         rc = run_gemm(e, A, X, ep, l.out, l.in, B, pick_split_k(l.out, l.in, B), st);
     }
     if (rc) return rc;
-    dim3 grid(cdiv(l.out, 32), std::min(64, cdiv(B, 8)));
+    dim3 grid(cdiv(l.out, 32), tuning().deterministic ? 1 : std::min(64, cdiv(B, 8)));
     if (g_dtype) colsum_kernel<bf16><<<grid, dim3(32, 8), 0, st>>>((const bf16*)g, e->grads + l.b, B, l.out, g_ld);
     else colsum_kernel<float><<<grid, dim3(32, 8), 0, st>>>((const float*)g, e->grads + l.b, B, l.out, g_ld);
     EMB_CHECK_LAUNCH();
@@ -860,6 +861,22 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
             Epilogue ep = base_epi(e, EPI_LINEAR, c.y, c.ld);
             ep.bias = e->params + c.b;
             int rc;
+            if (!training && tc_conv_ok(e, c) && c.ld == c.cout && tuning().infer_fuse) {
+                // Inference: eval-mode BatchNorm (one scale / shift per channel from the running statistics) + ReLU + MaxPool run in
+                // the conv GEMM's epilogue on the tile, which holds whole samples: the pre-pooling conv output is never written.
+                bn_finalize_kernel<<<cdiv(c.cout, 128), 128, 0, st>>>(c.stats, e->params + c.gamma, e->params + c.beta, e->buffers + c.rm,
+                                                                      e->buffers + c.rv, c.scale, c.shift, c.mean, c.rstd, 1.0, c.cout, 0);
+                EMB_CHECK_LAUNCH();
+                LAUNCHED(e);
+                ep.mode = EPI_POOL;
+                ep.pool_scale = c.scale; ep.pool_shift = c.shift; ep.pool_out = c.a; ep.pool_Lp = c.Lp; ep.pool_ld = c.ld;
+                TcProblem pr = {};
+                pr.kind = TC_CONV_FWD; pr.a = (const bf16*)pr_.a; pr.lda = pr_.ld; pr.b = c.wc; pr.ldb = round_up(c.cin, 8);
+                pr.M = B * c.Lc; pr.N = c.cout; pr.B = B; pr.L = c.Lc; pr.Cin = c.cin; pr.Cout = c.cout; pr.taps = c.k; pr.pad = c.pad;
+                rc = run_tc(e, pr, ep, 2.0 * B * c.Lc * c.cout * c.k * c.cin, st);
+                if (rc) return rc;
+                continue;
+            }
             if (tc_conv_ok(e, c)) {
                 TcProblem pr = {};
                 pr.kind = TC_CONV_FWD; pr.a = (const bf16*)pr_.a; pr.lda = pr_.ld; pr.b = c.wc; pr.ldb = round_up(c.cin, 8);
@@ -939,12 +956,18 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st, cudaStream_t sw) {
         const bool even = (c.cout % 2) == 0;
         const bool kt = std::is_same<T, bf16>::value && kt_ok(c.cout, c.ld) && kt_bwd_smem(c.Lc, c.Lp, c.cout) <= (size_t)kt_max_smem() &&
                         !tuning().no_tma_k2;
+        // Conv bias gradient: sum(dy) is EXACTLY zero behind a training-mode BatchNorm (its backward subtracts the mean of dz and the
+        // xhat-weighted mean, which is what makes sum_n dy = 0).  The reference's fp64 autograd leaves ~1e-18 of rounding noise there,
+        // far below Adam's eps; summing it in fp32 leaves ~1e-9, which Adam's normalisation would turn into a random walk of the
+        // bias that the reference does not have.  The exact value is written instead (the arena was zeroed): nothing to accumulate.
+        float* const conv_dbias = nullptr;
+        const bool det = tuning().deterministic != 0;
         PoolBwdArgs ka = {};
         if (kt) {
             // pass 1 of 2: the BatchNorm reductions only; dz is recomputed (not stored) by pass 2 below
             ka.y = (const bf16*)c.y; ka.amax = c.amax; ka.ga = (const bf16*)c.ga; ka.scale = c.scale; ka.shift = c.shift;
             ka.mean = c.mean; ka.rstd = c.rstd; ka.gamma = e->params + c.gamma; ka.bstats_in = c.bstats; ka.bstats_out = c.bstats;
-            ka.dy = (bf16*)c.dy; ka.dbias = e->grads + c.b; ka.B = B; ka.Lc = c.Lc; ka.Lp = c.Lp; ka.C = c.cout; ka.drop_p = c.drop;
+            ka.dy = (bf16*)c.dy; ka.dbias = conv_dbias; ka.B = B; ka.Lc = c.Lc; ka.Lp = c.Lp; ka.C = c.cout; ka.drop_p = c.drop;
             ka.n = (double)(e->global_batch > 0 ? e->global_batch : B) * c.Lc;
             kt_segments(c.cout, c.Lc, 2, &ka.nseg, &ka.P);
             const size_t ksm = kt_bwd_smem(c.Lc, c.Lp, c.cout);
@@ -989,16 +1012,16 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st, cudaStream_t sw) {
             dim3 block(G, rpb);
             const int grid = (int)std::min<int64_t>(148 * 8, cdiv(R, rpb));
             bn_bwd_apply_v8_kernel<T><<<grid, block, (size_t)rpb * c.cout * sizeof(float), st>>>((const T*)c.y, (T*)c.dy, c.bstats, e->params + c.gamma,
-                                                                                                c.mean, c.rstd, e->grads + c.b, R, c.cout, c.ld, n);
+                                                                                                c.mean, c.rstd, conv_dbias, R, c.cout, c.ld, n);
         } else if (even) {
             const int gx = cdiv(c.cout / 2, 32);
             dim3 grid(gx, (unsigned)std::min<int64_t>(std::max(1, 148 * 8 / gx), cdiv(R, 8)));
             bn_bwd_apply_v2_kernel<T><<<grid, dim3(32, 8), 0, st>>>((const T*)c.y, (T*)c.dy, c.bstats, e->params + c.gamma, c.mean, c.rstd,
-                                                                    e->grads + c.b, R, c.cout, c.ld, n);
+                                                                    conv_dbias, R, c.cout, c.ld, n);
         } else {
             dim3 grid(cdiv(c.cout, 32), (unsigned)std::min<int64_t>(296, cdiv(R, 8)));
             bn_bwd_apply_kernel<T><<<grid, dim3(32, 8), 0, st>>>((const T*)c.y, (T*)c.dy, c.bstats, e->params + c.gamma, c.mean, c.rstd,
-                                                                 e->grads + c.b, R, c.cout, c.ld, n);
+                                                                 conv_dbias, R, c.cout, c.ld, n);
         }
         EMB_CHECK_LAUNCH();
         LAUNCHED(e);
@@ -1006,19 +1029,19 @@ int cnn_backward_t(EmbEngine* e, int B, cudaStream_t st, cudaStream_t sw) {
             // conv-0 dbias was already accumulated by the bn_bwd_apply kernel
             if (std::is_same<T, bf16>::value && tc_on(e) && onehot_wgrad_tc_ok(c.dy, e->last_bases, c.cout, c.k, c.ld)) {
                 // the weight gradient of the one-hot layer as ONE tensor-core contraction per 16 positions (onehot_wgrad_tc.cuh)
-                int rcw = onehot_conv_wgrad_tc(e->last_bases, (const bf16*)c.dy, e->grads + c.w, B, c.cout, c.k, c.ld, st);
+                int rcw = onehot_conv_wgrad_tc(e->last_bases, (const bf16*)c.dy, e->grads + c.w, B, c.cout, c.k, c.ld, st, det ? 1 : 0);
                 if (rcw) return rcw;
             } else if (even && (c.cout / 2) * c.k <= 1024) {
                 const int threads = round_up((c.cout / 2) * c.k, 32);
                 size_t smem = (size_t)(SEQ_LEN + 2 * c.pad) * c.cout * sizeof(float) + SEQ_LEN + 16;
-                int grid = std::min(B, 148 * 2);
+                int grid = det ? 1 : std::min(B, 148 * 2);
                 if (std::is_same<T, bf16>::value && (c.cout % 8) == 0) {
                     const size_t smem16 = (size_t)(SEQ_LEN + 2 * c.pad) * c.cout * sizeof(bf16) + SEQ_LEN + 16;
-                    onehot_conv_bwd_lists16_kernel<<<std::min(B, 148 * 2), threads, smem16, st>>>(e->last_bases, (const bf16*)c.dy, e->grads + c.w, B, c.cout, c.k, c.ld);
+                    onehot_conv_bwd_lists16_kernel<<<grid, threads, smem16, st>>>(e->last_bases, (const bf16*)c.dy, e->grads + c.w, B, c.cout, c.k, c.ld);
                 } else
                 onehot_conv_bwd_lists_kernel<T><<<grid, threads, smem, st>>>(e->last_bases, (const T*)c.dy, e->grads + c.w, B, c.cout, c.k, c.ld);
             } else {
-                int grid = std::min(B, 148 * 4);
+                int grid = det ? 1 : std::min(B, 148 * 4);
                 onehot_conv_bwd_kernel<T><<<grid, 256, 0, st>>>(e->last_bases, (const T*)c.dy, e->grads + c.w, nullptr, B, c.cout, c.k, c.ld);
             }
             EMB_CHECK_LAUNCH();
@@ -2124,7 +2147,7 @@ int emb_k_onehot_conv_wgrad_tc(const uint8_t* bases, const void* dy_bf16, int32_
     if (B < 1 || !onehot_wgrad_tc_ok(dy_bf16, bases, C1, k, C1)) return set_error(EMB_E_ARG, "bad shape or alignment");
     cudaStream_t st = (cudaStream_t)stream;
     EMB_CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)C1 * 4 * k * sizeof(float), st));
-    int rc = onehot_conv_wgrad_tc(bases, (const bf16*)dy_bf16, dw, B, C1, k, C1, st);
+    int rc = onehot_conv_wgrad_tc(bases, (const bf16*)dy_bf16, dw, B, C1, k, C1, st, 0);
     return rc ? rc : EMB_OK;
 }
 

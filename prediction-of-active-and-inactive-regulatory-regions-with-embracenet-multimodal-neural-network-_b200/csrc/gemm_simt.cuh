@@ -95,6 +95,7 @@ enum EpiMode : int {
     EPI_MASKGRAD = 2,     // out = ref > 0 ? acc * scale : 0              (dgrad through ReLU+Dropout)
     EPI_EMBRACE_BWD = 3,  // dd0/dd1 = acc masked by idx and e > 0
     EPI_ATOMIC = 4,       // atomicAdd(out_f32[map(m,n)], acc)            (wgrad, split-K)
+    EPI_POOL = 5,         // tensor-core conv forward, inference: eval BatchNorm + ReLU + MaxPool1d(10,2) on the tile, pooled rows out
 };
 enum OutMap : int { MAP_ROWMAJOR = 0, MAP_CONV_W = 1, MAP_W_PERM = 2 };
 
@@ -131,6 +132,11 @@ struct Epilogue {
     // tensor-core conv forward only: per-column sum / sum of squares of the STORED (bf16-rounded) outputs, i.e. the
     // BatchNorm batch statistics of the layer, accumulated in the epilogue ([N] sums then [N] sums of squares)
     double* bn_stats;
+    // EPI_POOL (tensor-core conv forward, eval mode): a[b, j, n] = max_{i<10} relu(bf16(acc + bias) * pool_scale[n] + pool_shift[n]) at l = 2j + i
+    const float* pool_scale;
+    const float* pool_shift;
+    void* pool_out;          // bf16 [B, pool_Lp, pool_ld]
+    int pool_Lp, pool_ld;
 };
 
 __device__ __forceinline__ void epilogue_apply(const Epilogue& ep, int m, int n, int M, int N, float acc) {

@@ -354,6 +354,54 @@ __device__ __forceinline__ void tc_bn_stats16(const Epilogue& ep, float* s_warp,
     __syncwarp();
 }
 
+// ---------------------------------------------------------------------------------------------
+// EPI_POOL: the inference forward never writes the pre-pooling conv output.  A conv tile holds WHOLE samples (rows = positions),
+// so BatchNorm (eval: one scale/shift per channel) + ReLU + MaxPool1d(10, 2) run on the tile: the 128 epilogue threads stage
+// relu(bn(.)) of a 16-column chunk in shared memory ([128 rows][20 floats]: the 80-byte row stride keeps the 16-byte stores of
+// a quarter warp on different banks), meet at a named barrier, and then produce the pooled rows -- thread = (pooled row,
+// channel pair), 10 reads each -- straight into the next layer's input.  Arithmetic and rounding points are those of the
+// unfused path (bf16 conv output, fp32 BatchNorm apply, one bf16 rounding of the pooled value), so both produce the same bits.
+// Two buffers alternate, so one barrier per chunk suffices.
+// ---------------------------------------------------------------------------------------------
+constexpr int TC_POOL_ROW = 20;
+constexpr int TC_POOL_SCRATCH_BYTES = 2 * 128 * TC_POOL_ROW * 4;
+
+__device__ __forceinline__ void tc_pool_chunk16(const Epilogue& ep, float* buf, int tid, const float* v, int n0, int N, int rows_per_sample,
+                                                int samples_in_tile, int sample0, int Bn) {
+    float z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int n = n0 + i;
+        float t = 0.f;
+        if (n < N) {
+            const float y = __bfloat162float(__float2bfloat16_rn(v[i] + (ep.bias ? __ldg(ep.bias + n) : 0.f)));
+            t = fmaxf(fmaf(y, __ldg(ep.pool_scale + n), __ldg(ep.pool_shift + n)), 0.f);
+        }
+        z[i] = t;
+    }
+    float4* dst = reinterpret_cast<float4*>(buf + tid * TC_POOL_ROW);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = make_float4(z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int Lp = ep.pool_Lp;
+    const int n_out = samples_in_tile * Lp * 8;
+    for (int o = tid; o < n_out; o += 128) {
+        const int cp = o & 7, pj = o >> 3;
+        const int g = pj / Lp, j = pj - g * Lp;
+        const int sample = sample0 + g, n = n0 + 2 * cp;
+        if (sample >= Bn || n >= N) continue;
+        const float* src = buf + (g * rows_per_sample + 2 * j) * TC_POOL_ROW + 2 * cp;
+        float2 m = *reinterpret_cast<const float2*>(src);
+#pragma unroll
+        for (int i = 1; i < 10; ++i) {
+            const float2 t = *reinterpret_cast<const float2*>(src + i * TC_POOL_ROW);
+            m.x = fmaxf(m.x, t.x);
+            m.y = fmaxf(m.y, t.y);
+        }
+        *reinterpret_cast<uint32_t*>((bf16*)ep.pool_out + ((size_t)sample * Lp + j) * ep.pool_ld + n) = pack_bf16x2(m.x, m.y);
+    }
+}
+
 // Persistent: one CTA per SM walks the tile list; two TMEM accumulator stages let the epilogue of tile i
 // overlap the main loop of tile i+1.
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -534,7 +582,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int grp = r / p.rows_per_group;
         const int r_in = r - grp * p.rows_per_group;
         const bool r_ok = r < p.groups_per_tile * p.rows_per_group;
-        int acc = 0;
+        int acc = 0, pool_chunk = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             TC_DECODE_TILE(t)
@@ -578,6 +626,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         for (int rr = 0; rr < rows; ++rr)
                             if (n_ok) atomicAdd(dst + (size_t)rr * ep.ldo, sc[rr * 33 + lane]);
                         __syncwarp();
+                    }
+                    continue;
+                }
+                if (ep.mode == EPI_POOL) {
+                    for (int c0 = 0; c0 < p.n_tile; c0 += 16, ++pool_chunk) {      // the two staging buffers alternate ACROSS tiles as well
+                        if (n_base + c0 >= p.N) break;                      // uniform over the four epilogue warps
+                        float v[16];
+                        tc_ld16(t_addr + (uint32_t)c0, v);
+                        tc_pool_chunk16(ep, epi_scratch + (pool_chunk & 1) * (128 * TC_POOL_ROW), r, v, n_base + c0, p.N, p.rows_per_group,
+                                        p.groups_per_tile, tile_m * p.groups_per_tile, p.M / p.rows_per_group);
                     }
                     continue;
                 }
@@ -858,6 +916,7 @@ inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int
         const int tiles = grid_m * grid_n * (conv ? conv_tap_groups : 1);
         // split-K: every split adds a full tile of fp32 atomics, so keep at least tc_min_kiters() K blocks per CTA
         int split = std::max(1, std::min(std::max(1, j_total / tc_min_kiters()), tc_num_sms() / std::max(1, tiles)));
+        if (tuning().deterministic) split = 1;      // one CTA per output tile: the fp32 accumulation has a fixed order
         p.n_inner = cdiv(j_total, split);
         split = cdiv(j_total, p.n_inner);
         p.split_k = split;
@@ -876,7 +935,7 @@ inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int
     p.grid_m = grid_m; p.grid_n = grid_n; p.grid_z = grid_z;
     p.total_tiles = grid_m * grid_n * grid_z;
     const int stage_bytes = p.a.stage_bytes + p.b.stage_bytes;
-    const int epi_scratch_bytes = 4 * 32 * 33 * 4;
+    const int epi_scratch_bytes = std::max(4 * 32 * 33 * 4, ep.mode == EPI_POOL ? TC_POOL_SCRATCH_BYTES : 0);
     const int budget = tc_max_smem() - 2048 - epi_scratch_bytes;
     p.stages = std::min(TC_MAX_STAGES, budget / stage_bytes);
     if (p.stages < 2) return set_error(-5, "tc_gemm: stage of %d bytes does not fit twice in shared memory", stage_bytes);

@@ -280,7 +280,7 @@ bn_bwd_apply_kernel(const T* __restrict__ y, T* __restrict__ dz, const double* _
     }
     s1[threadIdx.y][threadIdx.x] = acc;
     __syncthreads();
-    if (threadIdx.y == 0 && c < C) {
+    if (dbias && threadIdx.y == 0 && c < C) {
         float t = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += s1[i][threadIdx.x];

@@ -384,7 +384,7 @@ bn_bwd_apply_v2_kernel(const T* __restrict__ y, T* __restrict__ dz, const double
     s1[0][threadIdx.y][threadIdx.x] = acc.x;
     s1[1][threadIdx.y][threadIdx.x] = acc.y;
     __syncthreads();
-    if (threadIdx.y < 2 && cp < pairs) {
+    if (dbias && threadIdx.y < 2 && cp < pairs) {
         float t = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += s1[threadIdx.y][i][threadIdx.x];
@@ -465,7 +465,7 @@ bn_bwd_apply_v8_kernel(const T* __restrict__ y, T* __restrict__ dz, const double
 #pragma unroll
     for (int i = 0; i < 8; ++i) sred[threadIdx.y * C + c0 + i] = acc[i];
     __syncthreads();
-    for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < C; c += blockDim.x * blockDim.y) {
+    for (int c = threadIdx.y * blockDim.x + threadIdx.x; dbias && c < C; c += blockDim.x * blockDim.y) {
         float t = 0.f;
         for (int ry = 0; ry < (int)blockDim.y; ++ry) t += sred[ry * C + c];
         atomicAdd(&dbias[c], t);

@@ -198,7 +198,7 @@ pool_bn_bwd_tma_kernel(const PoolBwdArgs g) {
         float sx = 0, sy = 0;
         for (int s = 0; s < g.nseg; ++s) { sx += red[0][t + s * pairs]; sy += red[1][t + s * pairs]; }
         if (MODE == 0) { atomicAdd(&g.bstats_out[2 * t], (double)sx); atomicAdd(&g.bstats_out[2 * t + 1], (double)sy); }
-        else { atomicAdd(&g.dbias[2 * t], sx); atomicAdd(&g.dbias[2 * t + 1], sy); }
+        else if (g.dbias) { atomicAdd(&g.dbias[2 * t], sx); atomicAdd(&g.dbias[2 * t + 1], sy); }
     }
     if (MODE == 0) {
         __syncthreads();

@@ -173,7 +173,7 @@ inline bool onehot_wgrad_tc_ok(const void* dy, const uint8_t* bases, int C1, int
 }
 
 // dw[C1][4][k] += ... (fp32 atomics; the caller zeroes it).  dy: [B, 256, ld] bf16.
-inline int onehot_conv_wgrad_tc(const uint8_t* bases, const bf16* dy, float* dw, int B, int C1, int k, int ld, cudaStream_t st) {
+inline int onehot_conv_wgrad_tc(const uint8_t* bases, const bf16* dy, float* dw, int B, int C1, int k, int ld, cudaStream_t st, int one_cta = 0) {
     int rc = tc_init();
     if (rc) return rc;
     if (first_on_device(1)) {
@@ -184,7 +184,7 @@ inline int onehot_conv_wgrad_tc(const uint8_t* bases, const bf16* dy, float* dw,
     rc = make_map(&map, dy, C1, SEQ_LEN, B, ld, (int64_t)SEQ_LEN * ld, 64, SEQ_LEN, 1);
     if (rc) return rc;
     const uint32_t idesc = make_idesc(1, 1, 128);
-    const int grid = std::min(B, tc_num_sms());
+    const int grid = one_cta ? 1 : std::min(B, tc_num_sms());      // one CTA = one contributor: the deterministic-reduction mode
     onehot_conv_wgrad_tc_kernel<<<grid, OHW_THREADS, OHW_SMEM, st>>>(map, bases, dw, B, C1, k, idesc);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error(-3, "onehot_conv_wgrad_tc launch failed: %s", cudaGetErrorString(err));

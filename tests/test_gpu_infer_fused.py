@@ -1,0 +1,45 @@
+"""Inference forward with BatchNorm(eval) + ReLU + MaxPool1d fused into the conv GEMM epilogue (EPI_POOL, csrc/gemm_tc.cuh):
+the pre-pooling conv output is never written.  The fused and the unfused eval forward share arithmetic and rounding points, so
+their outputs must be IDENTICAL; both are also held to the oracle's eval forward (EmbraceNetMultimodal_NoTrain.py:180-214)."""
+import numpy as np
+import pytest
+
+from oracle import embracenet_oracle as O
+from tests.golden.cases import ARCH_S, ARCH_M, ARCH_L, make_inputs
+from tests.test_gpu_parity import to_archspec
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('arch,B', [('S', 300), ('M', 130), ('L', 77), ('S', 4096)])
+def test_fused_pooling_epilogue_equals_unfused_eval_forward(arch, B):
+    import torch
+    from embrace_b200 import Engine, _native as N
+    spec = {'S': ARCH_S, 'M': ARCH_M, 'L': ARCH_L}[arch]
+    P = O.init_params(spec, 4242)
+    P = {k: (v.astype(np.float32).astype(np.float64) if v.dtype == np.float64 else v) for k, v in P.items()}
+    x, bases, _ = make_inputs(spec, B, 4243)
+    u = np.random.RandomState(4244).random_sample((B, spec['C']))
+    av = np.ones((B, 2), dtype=np.float32)
+    av[0::5, 0] = 0
+    av[1::7, 1] = 0
+    av[(av.sum(1) == 0), 0] = 1
+    out = {}
+    for fuse in (1, 0):
+        N.set_option('infer_fuse', fuse)
+        try:
+            eng = Engine(to_archspec(spec), max_batch=B, precision='bf16', tensor_core=True)
+            eng.load_numpy(P)
+            l0 = eng.launch_count
+            logits, probs = eng.forward(torch.from_numpy(x.astype(np.float32)), torch.from_numpy(bases), training=False,
+                                        draws={'embrace_u': u}, availabilities=torch.from_numpy(av), want_probs=True)
+            torch.cuda.synchronize()
+            out[fuse] = (logits.cpu().numpy(), probs.cpu().numpy(), eng.launch_count - l0)
+        finally:
+            N.set_option('infer_fuse', 1)
+    assert np.isfinite(out[1][0]).all()
+    assert np.array_equal(out[1][0], out[0][0]), np.abs(out[1][0] - out[0][0]).max()
+    assert out[1][2] < out[0][2], 'the fused forward must launch fewer kernels'
+    if B <= 300:
+        ref = O.predict_proba(spec, P, x, bases, u, availabilities=av)
+        assert np.abs(out[1][1] - ref).max() <= 5e-3
