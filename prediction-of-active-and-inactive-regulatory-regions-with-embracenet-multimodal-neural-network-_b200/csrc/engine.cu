@@ -827,6 +827,18 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
             const int groups = c.cout / 8;
             if (std::is_same<T, bf16>::value && tc_on(e) && onehot_fwd_tc_ok(c.y, bases, c.cout, c.k, c.ld)) {
                 // one-hot rows expanded in shared memory, all taps through a Toeplitz descriptor, fp32 weights as an exact hi/mid/lo bf16 split
+                if (!training && tuning().infer_fuse) {
+                    // inference: eval BatchNorm + ReLU + MaxPool on the staged sample inside the same kernel; y0 is never written
+                    bn_finalize_kernel<<<cdiv(c.cout, 128), 128, 0, st>>>(c.stats, e->params + c.gamma, e->params + c.beta, e->buffers + c.rm,
+                                                                          e->buffers + c.rv, c.scale, c.shift, c.mean, c.rstd, 1.0, c.cout, 0);
+                    EMB_CHECK_LAUNCH();
+                    LAUNCHED(e);
+                    int rcp = onehot_conv_fwd_tc(bases, e->params + c.w, e->params + c.b, (bf16*)c.y, nullptr, B, c.cout, c.k, c.ld, st, c.scale, c.shift,
+                                                 (bf16*)c.a, c.Lp);
+                    if (rcp) return rcp;
+                    LAUNCHED(e);
+                    continue;
+                }
                 int rcf = onehot_conv_fwd_tc(bases, e->params + c.w, e->params + c.b, (bf16*)c.y, training ? c.stats : nullptr, B, c.cout, c.k, c.ld, st);
                 if (rcf) return rcf;
                 stats_done = true;

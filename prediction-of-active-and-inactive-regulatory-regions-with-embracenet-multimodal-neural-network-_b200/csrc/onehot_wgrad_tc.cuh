@@ -229,14 +229,15 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
 
 __global__ void __launch_bounds__(OHF_THREADS, 2)
 onehot_conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_y, const uint8_t* __restrict__ bases, const float* __restrict__ w,
-                          const float* __restrict__ bias, double* __restrict__ stats, int B, int C1, int k, uint32_t idesc) {
+                          const float* __restrict__ bias, double* __restrict__ stats, int B, int C1, int k, uint32_t idesc,
+                          const float* __restrict__ pool_scale, const float* __restrict__ pool_shift, bf16* __restrict__ pool_out, int pool_Lp) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* tiles = smem;                                          // [8 epilogue warps][32 rows][128 B], 128B-swizzled
     uint8_t* wsm = tiles + 8 * OHF_TILE_BYTES;                      // W'1, W'2 in the un-swizzled K-major core-matrix layout
     uint8_t* stages = wsm + OHF_W_BYTES;                            // [stage]{rows[272][16 B], codes[256]}
     float* sbias = (float*)(stages + OHF_STAGES * OHF_STAGE);       // [64]
-    float* sred = sbias + 64;                                       // [8 warps][64 channels][2]
+    float* sred = sbias + 64;                                       // [8 warps][64 channels][2]; pooled (inference) mode: [64] scale | [64] shift
     uint64_t* codes_bar = (uint64_t*)(sred + 8 * 64 * 2);
     uint64_t* rows_full = codes_bar + OHF_STAGES;
     uint64_t* rows_empty = rows_full + OHF_STAGES;
@@ -261,6 +262,8 @@ onehot_conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_y, const uint8
         dst[8192 + 4 + c] = __float2bfloat16_rn(0.f);
     }
     for (int i = threadIdx.x; i < 64; i += OHF_THREADS) sbias[i] = i < C1 ? bias[i] : 0.f;
+    if (pool_out)
+        for (int i = threadIdx.x; i < 64; i += OHF_THREADS) { sred[i] = i < C1 ? pool_scale[i] : 0.f; sred[64 + i] = i < C1 ? pool_shift[i] : 0.f; }
     fence_async_smem();
     if (threadIdx.x == 0) {
         for (int s = 0; s < OHF_STAGES; ++s) { mbar_init(&codes_bar[s], 1); mbar_init(&rows_full[s], 2); mbar_init(&rows_empty[s], 1); }
@@ -343,8 +346,10 @@ onehot_conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_y, const uint8
             const int b = blockIdx.x + i * gridDim.x;
             mbar_wait(&tfull[h], (uint32_t)(i & 1));
             tc_fence_after();
-            if (lane == 0) bulk_wait_read<0>();                       // the previous store has drained the staging tile
-            __syncwarp();
+            if (!pool_out) {
+                if (lane == 0) bulk_wait_read<0>();                   // the previous store has drained the staging tile
+                __syncwarp();
+            }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float v[32];
@@ -364,6 +369,35 @@ onehot_conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_y, const uint8
                 }
             }
             tc_fence_before();
+            if (pool_out) {
+                // Inference: the eight staged tiles together are the sample's whole [256][64] conv output.  Eval BatchNorm + ReLU +
+                // MaxPool1d(10, 2) run on it here and only the pooled [Lp][C1] block goes to memory (thread = pooled row x 8 channels).
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[h])) : "memory");
+                asm volatile("bar.sync 2, 256;" ::: "memory");             // all eight epilogue warps have staged this sample
+                const int nch = C1 >> 3, et = ew * 32 + lane;
+                for (int item = et; item < pool_Lp * nch; item += 256) {
+                    const int j = item / nch, ch = item - j * nch;
+                    float sc[8], sh[8], m[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) { sc[c] = sred[ch * 8 + c]; sh[c] = sred[64 + ch * 8 + c]; m[c] = 0.f; }
+#pragma unroll
+                    for (int i2 = 0; i2 < 10; ++i2) {
+                        const int r = 2 * j + i2, lr = r & 31;
+                        const uint4 u = *reinterpret_cast<const uint4*>(tiles + (r >> 5) * OHF_TILE_BYTES + lr * 128 + ((ch ^ (lr & 7)) << 4));
+                        const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            m[2 * c] = fmaxf(m[2 * c], fmaf(__uint_as_float(wv[c] << 16), sc[2 * c], sh[2 * c]));
+                            m[2 * c + 1] = fmaxf(m[2 * c + 1], fmaf(__uint_as_float(wv[c] & 0xFFFF0000u), sc[2 * c + 1], sh[2 * c + 1]));
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(pool_out + ((size_t)b * pool_Lp + j) * C1 + ch * 8) =
+                        make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");             // the tiles may be overwritten by the next sample
+                continue;
+            }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -380,7 +414,7 @@ onehot_conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_y, const uint8
                 }
             }
         }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // every tile is in global memory
+        if (!pool_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // every tile is in global memory
         if (stats) {
             sred[(ew * 64 + 2 * lane) * 2] = s1a; sred[(ew * 64 + 2 * lane) * 2 + 1] = s2a;
             sred[(ew * 64 + 2 * lane + 1) * 2] = s1b; sred[(ew * 64 + 2 * lane + 1) * 2 + 1] = s2b;
@@ -408,7 +442,8 @@ inline bool onehot_fwd_tc_ok(const void* y, const uint8_t* bases, int C1, int k,
 
 // y: [B, 256, ld] bf16; stats (nullable): [2][C1] doubles, accumulated (sum, sum of squares of the rounded outputs).
 inline int onehot_conv_fwd_tc(const uint8_t* bases, const float* w, const float* bias, bf16* y, double* stats, int B, int C1, int k, int ld,
-                              cudaStream_t st) {
+                              cudaStream_t st, const float* pool_scale = nullptr, const float* pool_shift = nullptr, bf16* pool_out = nullptr,
+                              int pool_Lp = 0) {
     int rc = tc_init();
     if (rc) return rc;
     if (first_on_device(2)) {
@@ -420,7 +455,8 @@ inline int onehot_conv_fwd_tc(const uint8_t* bases, const float* w, const float*
     if (rc) return rc;
     const uint32_t idesc = make_idesc(0, 0, 64);
     const int grid = std::min(B, 2 * tc_num_sms());
-    onehot_conv_fwd_tc_kernel<<<grid, OHF_THREADS, OHF_SMEM, st>>>(map, bases, w, bias, stats, B, C1, k, idesc);
+    onehot_conv_fwd_tc_kernel<<<grid, OHF_THREADS, OHF_SMEM, st>>>(map, bases, w, bias, pool_out ? nullptr : stats, B, C1, k, idesc, pool_scale, pool_shift,
+                                                                   pool_out, pool_Lp);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error(-3, "onehot_conv_fwd_tc launch failed: %s", cudaGetErrorString(err));
     return 0;

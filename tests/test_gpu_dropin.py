@@ -207,8 +207,8 @@ def test_training_curve_auprc_parity_on_planted_signal():
     st = TP.TrainState(spec, {k: v.copy() for k, v in P.items()}, 'adam', lr=3e-3, wd=1e-4)
     # fixed-order reductions: with fp32 atomics the trajectory differs from run to run in the last bit, which 40 Adam steps in the
     # steep part of the learning curve amplify (observed once in r2: 0.014 instead of the usual 2e-4 .. 2e-6)
-    from embrace_b200 import _native as N
-    N.set_option('deterministic', 1)
+    from embrace_b200 import _native as NAT
+    NAT.set_option('deterministic', 1)
     m = build(spec, P, precision='fp32')
     cfg = lift_optimizer(torch.optim.Adam(m.parameters(), lr=3e-3, weight_decay=1e-4))
     m.train()
@@ -218,7 +218,7 @@ def test_training_curve_auprc_parity_on_planted_signal():
         draws = O.make_draws(spec, B, 5000 + s)
         st.step(torch.from_numpy(xb), torch.from_numpy(O.onehot_from_bases(bb)), yb, draws)
         m.train_batch(torch.from_numpy(xb), torch.from_numpy(bb), torch.from_numpy(yb), cfg, draws=draws)
-    N.set_option('deterministic', 0)
+    NAT.set_option('deterministic', 0)
     u = np.random.RandomState(9).random_sample((len(yte), spec['C']))
     Pt = {k: v.detach().numpy() for k, v in st.T.items()}
     ref_logits, _ = O.forward(spec, Pt, xte, bte, {'embrace_u': u}, training=False)
