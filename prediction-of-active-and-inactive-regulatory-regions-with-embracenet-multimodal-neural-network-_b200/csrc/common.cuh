@@ -56,7 +56,8 @@ struct Tuning {
     int wgrad_fuse_taps = 0;     // EMB_WGRAD_FUSE_TAPS     conv wgrad with Cin = 64: up to four taps per tcgen05.mma
     int deterministic = 0;       // EMB_DETERMINISTIC       fixed-order reductions: no split-K, one CTA per reduction column block
     int k2_wide = 1;             // EMB_K2_WIDE             8-channel (16-byte) forward pooling kernel where C % 8 == 0
-    int infer_fuse = 1;          // EMB_INFER_FUSE          eval forward: BatchNorm + ReLU + MaxPool in the conv GEMM epilogue (no pre-pooling tensor)
+    int infer_fuse = 0;          // EMB_INFER_FUSE          eval forward: BatchNorm + ReLU + MaxPool in the conv GEMM epilogue (no pre-pooling tensor);
+                                 //                         off by default: with four epilogue warps the fused epilogue is latency-bound and slower (r2 measurement)
     int fork = 1;                // EMB_FORK                independent branches of the step on side streams (parallel graph branches)
 };
 struct TuningName { const char* env; const char* name; int Tuning::*field; };
