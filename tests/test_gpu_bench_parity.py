@@ -199,21 +199,27 @@ def test_adamw_matches_decoupled_rule():
 
 def test_training_curve_auprc_parity_bf16_tensor_core_large_batch():
     """AUPRC after training on the PRODUCTION path: bf16 storage + tcgen05 GEMMs at batch 1024, arch S, against the reference's
-    fp64 CPU path (oracle/torch_port.py) with the same replayed draws -- 100 Adam steps at lr 3e-3 and 30 at 3e-4 on
+    fp64 CPU path (oracle/torch_port.py) with the same replayed draws -- 200 Adam steps at lr 3e-3 and 60 at 3e-4 on
     planted-signal data (logistic on 4 features + a motif), then ranking AUPRC (sklearn average_precision_score of z1 - z0)
     and the reference's hard-prediction AUPRC (utils.py:80-86) on 16 384 held-out rows.
 
-    Bound: 0.005, not north_star's 0.002.  Training is a chaotic map of its rounding: the REFERENCE ITSELF, re-run with its
-    initial weights perturbed by 1e-6 relative, ends 0.003 (ranking) / 0.004 (hard) away from its own unperturbed run on this
-    task (measured r2 with the fp32 port, 130 steps); 0.002 is met where the trajectories can be kept identical -- the fp32
-    engine in deterministic mode, tests/test_gpu_dropin.py (measured 2e-6 .. 2e-4)."""
+    Bounds: 0.004 (ranking) / 0.008 (hard), next to north_star's 0.002.  Training is a chaotic map of its rounding: what can be
+    asked is that the engine lands inside the reference's OWN sensitivity band.  Measured r2 (profiles/r02_training_curve.json,
+    `python profiles/training_curve.py 260`, 8192 held-out rows), final ranking / hard AUPRC and distance to the reference:
+        reference fp64                          0.98938 / 0.9237
+        reference, initial weights * (1+1e-6)   0.99081 / 0.9262    +0.0014 / +0.0026   <- the band
+        engine fp32 (SIMT)                      0.99058 / 0.9275    +0.0012 / +0.0038
+        engine bf16 (tcgen05)                   0.98872 / 0.9217    -0.0007 / -0.0020
+    while mid-training (step 60, the steep part of the curve) the four runs are spread over 0.62 .. 0.94.  0.002 itself is met
+    where trajectories can be kept identical: the fp32 engine in deterministic mode on a converged task, tests/test_gpu_dropin.py
+    (measured 0.0009 / 0.0012).  The engine runs in deterministic mode here so that the test's outcome is reproducible."""
     import torch
     from sklearn.metrics import average_precision_score
     from oracle import torch_port as TP
     from embrace_b200 import Engine
     spec = ARCH_S
     rs = np.random.RandomState(3)
-    N, B, steps, decay_at = 8192, 1024, 130, 100
+    N, B, steps, decay_at = 8192, 1024, 260, 200
     F = spec['F']
 
     def data(n):
@@ -234,6 +240,8 @@ def test_training_curve_auprc_parity_bf16_tensor_core_large_batch():
     P = {k: (v.astype(np.float32).astype(np.float64) if v.dtype == np.float64 else v) for k, v in P.items()}
     torch.set_num_threads(os.cpu_count() or 1)
     st = TP.TrainState(spec, {k: v.copy() for k, v in P.items()}, 'adam', lr=3e-3, wd=1e-4)
+    from embrace_b200 import _native as NAT
+    NAT.set_option('deterministic', 1)
     eng = Engine(to_archspec(spec), max_batch=16384, precision='bf16', tensor_core=True)
     eng.load_numpy(P)
     for s in range(steps):
@@ -246,6 +254,7 @@ def test_training_curve_auprc_parity_bf16_tensor_core_large_batch():
         draws = O.make_draws(spec, B, 5000 + s)
         st.step(torch.from_numpy(xb), torch.from_numpy(O.onehot_from_bases(bb)), yb, draws)
         eng.train_step(torch.from_numpy(xb.astype(np.float32)), torch.from_numpy(bb), torch.from_numpy(yb), cfg, draws=draws)
+    NAT.set_option('deterministic', 0)
     u = np.random.RandomState(9).random_sample((len(yte), spec['C']))
     with torch.no_grad():
         Tt = {k: v.detach() for k, v in st.T.items()}
@@ -263,5 +272,5 @@ def test_training_curve_auprc_parity_bf16_tensor_core_large_batch():
         json.dump(rep, f, indent=1)
     print(json.dumps(rep))
     assert rank_ref > yte.mean() + 0.3 and rank_got > yte.mean() + 0.3, 'both must have learned the planted signal'
-    assert abs(rank_ref - rank_got) <= 0.005
-    assert abs(hard_ref - hard_got) <= 0.01
+    assert abs(rank_ref - rank_got) <= 0.004
+    assert abs(hard_ref - hard_got) <= 0.008
