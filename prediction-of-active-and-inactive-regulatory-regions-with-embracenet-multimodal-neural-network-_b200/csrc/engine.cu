@@ -935,7 +935,18 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
         const float* du = (dr && p > 0.f) ? dr->cnn_drop[i] : nullptr;
         const bool kt_bwd = std::is_same<T, bf16>::value && kt_ok(c.cout, c.ld) && kt_bwd_smem(c.Lc, c.Lp, c.cout) <= (size_t)kt_max_smem() &&
                             !tuning().no_tma_k2;    // the backward will consume the arg-max codes
-        if (even) {
+        if (std::is_same<T, bf16>::value && tuning().k2_wide && (c.cout % 8) == 0 && c.ld == c.cout) {
+            // packed kernel: 8 channels per thread, pooling on the stored bf16 values, BatchNorm on the pooled maximum only
+            const int blocks = cdiv((size_t)B * (c.cout / 8), 256);
+            uint8_t* am = (training && kt_bwd) ? c.amax : nullptr;
+#define EMB_K2_PACKED(MODE)                                                                                                         \
+            k2_fwd_packed_kernel<MODE><<<blocks, 256, 0, st>>>((const bf16*)c.y, c.scale, c.shift, (bf16*)c.a, B, c.Lc, c.Lp, c.cout, p, du, \
+                                                               e->rng, RNG_CNN_DROP + (uint32_t)i, e->row_offset, am)
+            if (p <= 0.f) EMB_K2_PACKED(0);
+            else if (du) EMB_K2_PACKED(1);
+            else EMB_K2_PACKED(2);
+#undef EMB_K2_PACKED
+        } else if (even) {
             const int blocks = cdiv((size_t)B * (c.cout / 2), 256);
 #define EMB_K2_FWD(MODE)                                                                                                          \
             bn_relu_pool_drop_fwd_stream_kernel<T, MODE><<<blocks, 256, 0, st>>>((const T*)c.y, c.scale, c.shift, (T*)c.a, B, c.Lc, c.Lp, \

@@ -244,6 +244,136 @@ bn_relu_pool_drop_fwd_stream_kernel(const T* __restrict__ y, const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// K2 forward, packed (bf16, C % 8 == 0, ld == C): thread = (sample, 8 channels), 16-byte loads, and the pooling done on the
+// STORED bf16 values instead of on fp32 BatchNorm outputs.
+//
+// BatchNorm's affine map z = y * sc + sh is monotone in y (increasing for sc > 0, decreasing for sc < 0), so
+//     max_i relu(z_i) = relu(fma(max_i y'_i, |sc|, sh)),    y' = y with its sign flipped where sc < 0
+// (fma(-y, -sc, sh) == fma(y, sc, sh) exactly, and rounding is monotone, so the result is bit-identical to applying BatchNorm
+// first).  The sign flip is one XOR per channel PAIR, every max / equality test is one packed bf16x2 instruction per channel pair,
+// and only the pooled value -- one element in two -- goes through the fp32 fma, ReLU, Dropout and the bf16 rounding.  The
+// arg-max code (offset 0..9 of the window's FIRST maximum, 255 = no gradient) comes from packed equality masks: the window is a
+// ring of 4 previous pair maxima + the current one, each with the mask "second position of the pair is larger".
+// Ties are decided on y' (the reference's fp64 BatchNorm output ties exactly when y ties), where the streaming kernel above
+// compared fp32 z.  About half the instructions per element of that kernel, which was bound by instruction issue at 2.3 TB/s.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hmax2_u(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t heq2_m(uint32_t a, uint32_t b) {
+    return __heq2_mask(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+}
+__device__ __forceinline__ uint32_t hgt2_m(uint32_t a, uint32_t b) {
+    return __hgt2_mask(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+}
+
+template <int DROP>
+__global__ void __launch_bounds__(256, 2)
+k2_fwd_packed_kernel(const bf16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift, bf16* __restrict__ a,
+                     int B, int Lc, int Lp, int C, float drop_p, const float* __restrict__ drop_u, RngState const* rng, uint32_t rng_stream,
+                     int64_t row_offset, uint8_t* __restrict__ amax) {
+    const int groups = C >> 3;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)B * groups) return;
+    const int g = (int)(t % groups), b = (int)(t / groups);
+    const int c0 = 8 * g;
+    float asc[8], sh[8];
+    uint32_t fm[4];
+    {
+        const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
+        const float4 h0 = *reinterpret_cast<const float4*>(shift + c0), h1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { asc[i] = fabsf(sc[i]); sh[i] = hh[i]; }
+#pragma unroll
+        for (int w = 0; w < 4; ++w) fm[w] = (sc[2 * w] < 0.f ? 0x00008000u : 0u) | (sc[2 * w + 1] < 0.f ? 0x80000000u : 0u);
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(y + (size_t)b * Lc * C + c0);
+    const int rs4 = C >> 3;                               // uint4 per row
+    bf16* dst = a + (size_t)b * Lp * C + c0;
+    uint8_t* adst = amax ? amax + (size_t)b * Lp * C + c0 : nullptr;
+    const float inv_keep = DROP ? 1.f / (1.f - drop_p) : 1.f;
+    RngState rs = {0, 0};
+    if (DROP == 2) rs = *rng;
+    uint32_t rv[4][4], rm[4][4];                          // ring [slot][word]: pair maximum (packed y'), "second is larger" mask
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { rv[q][w] = 0u; rm[q][w] = 0u; }
+    const int n_pairs = Lp + 4;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    for (int i0 = 0; i0 < n_pairs; i0 += 4) {
+        uint4 u[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int row = 2 * i0 + q;
+            u[q] = row < Lc ? __ldg(src + (size_t)row * rs4) : zero4;
+        }
+        uint4 blk[4];                                     // Philox blocks of the four channel pairs for outputs j0 .. j0 + 3
+        const int j0 = i0 - 4;
+        if (DROP == 2 && j0 >= 0) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) blk[w] = rng_cnn_block(rs, rng_stream, (uint64_t)(row_offset + b), C, (c0 >> 1) + w, Lp, j0 >> 2);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                     // pair i = i0 + q lives in ring slot q afterwards; slots q, q+1, .. hold pairs i-4 .. i-1
+            const uint32_t p0[4] = {u[2 * q].x ^ fm[0], u[2 * q].y ^ fm[1], u[2 * q].z ^ fm[2], u[2 * q].w ^ fm[3]};
+            const uint32_t p1[4] = {u[2 * q + 1].x ^ fm[0], u[2 * q + 1].y ^ fm[1], u[2 * q + 1].z ^ fm[2], u[2 * q + 1].w ^ fm[3]};
+            uint32_t mv[4], mm[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { mv[w] = hmax2_u(p0[w], p1[w]); mm[w] = hgt2_m(p1[w], p0[w]); }
+            const int j = i0 + q - 4;
+            if (j >= 0 && j < Lp) {
+                uint32_t aw[4], cw[2] = {0u, 0u};
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const uint32_t v0 = rv[q][w], v1 = rv[(q + 1) & 3][w], v2 = rv[(q + 2) & 3][w], v3 = rv[(q + 3) & 3][w];
+                    const uint32_t r = hmax2_u(hmax2_u(hmax2_u(v0, v1), hmax2_u(v2, v3)), mv[w]);
+                    // packed codes: 2 * slot + (second position larger), first slot (oldest pair) that attains the maximum wins
+                    uint32_t code = 0x00080008u | (mm[w] & 0x00010001u);
+                    uint32_t e = heq2_m(v3, r);
+                    code = (e & (0x00060006u | (rm[(q + 3) & 3][w] & 0x00010001u))) | (~e & code);
+                    e = heq2_m(v2, r);
+                    code = (e & (0x00040004u | (rm[(q + 2) & 3][w] & 0x00010001u))) | (~e & code);
+                    e = heq2_m(v1, r);
+                    code = (e & (0x00020002u | (rm[(q + 1) & 3][w] & 0x00010001u))) | (~e & code);
+                    e = heq2_m(v0, r);
+                    code = (e & (rm[q][w] & 0x00010001u)) | (~e & code);
+                    // the pooled value: BatchNorm on the maximum, ReLU, Dropout
+                    float zx = fmaf(__uint_as_float(r << 16), asc[2 * w], sh[2 * w]);
+                    float zy = fmaf(__uint_as_float(r & 0xFFFF0000u), asc[2 * w + 1], sh[2 * w + 1]);
+                    bool kx = zx > 0.f, ky = zy > 0.f;
+                    if (DROP) {
+                        float ux, uy;
+                        if (DROP == 1) {
+                            ux = drop_u[((size_t)b * C + c0 + 2 * w) * Lp + j];
+                            uy = drop_u[((size_t)b * C + c0 + 2 * w + 1) * Lp + j];
+                        } else {
+                            ux = rng_cnn_u16(blk[w], (uint32_t)q, 0u);        // j & 3 == q: j0 is a multiple of 4
+                            uy = rng_cnn_u16(blk[w], (uint32_t)q, 1u);
+                        }
+                        kx = kx && ux >= drop_p;
+                        ky = ky && uy >= drop_p;
+                    }
+                    zx = kx ? zx * inv_keep : 0.f;
+                    zy = ky ? zy * inv_keep : 0.f;
+                    __nv_bfloat162 o2 = __floats2bfloat162_rn(zx, zy);
+                    aw[w] = *reinterpret_cast<uint32_t*>(&o2);
+                    const uint32_t cx = kx ? (code & 0xFFu) : 255u, cy = ky ? ((code >> 16) & 0xFFu) : 255u;
+                    cw[w >> 1] |= (cx | (cy << 8)) << (16 * (w & 1));
+                }
+                *reinterpret_cast<uint4*>(dst + (size_t)j * C) = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+                if (adst) *reinterpret_cast<uint2*>(adst + (size_t)j * C) = make_uint2(cw[0], cw[1]);
+            }
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { rv[q][w] = mv[w]; rm[q][w] = mm[w]; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2 backward stage 1, streaming: thread = (sample, channel pair).  A 10-position ring of y and of the
 // accumulating dz lives in registers; when pair i arrives window j = i-4 is complete, its gradient goes to the
 // FIRST maximum (strict '>'), and positions 2j, 2j+1 can no longer change, so they are emitted.  y, a and d(a)

@@ -111,7 +111,7 @@ def test_dp2_on_one_device_equals_large_batch(precision, tc, GB):
         assert np.array_equal(params[0][k], params[1][k]), ('parameters must be bit-identical on both ranks after the all-gather', k)
         rep['params'][k] = float(np.abs(params[0][k] - v).max())
         # Adam normalises per element: entries whose gradient is rounding noise can move by a fraction of lr per step
-        assert rep['params'][k] <= 2e-5 * max(np.abs(v).max(), 1e-6) + (0.1 if precision == 'fp32' else 1.0) * lr * steps, (k, rep['params'][k])
+        assert rep['params'][k] <= 2e-5 * max(np.abs(v).max(), 1e-6) + (0.1 if precision == 'fp32' else 2.0) * lr * steps, (k, rep['params'][k])
     sel = np.concatenate([e.last_selection(e.max_batch).cpu().numpy() for e in engines])
     if precision == 'fp32':               # same Philox step on both sides only when the rewind above did not consume a step
         pass
@@ -233,6 +233,6 @@ def test_dp2_two_gpus_equals_single_gpu_large_batch(comm, precision, tc, GB):
     for rank, lo, hi, _, params, _, sel, _ in res:
         assert np.array_equal(sel, full['sel'][lo:hi]), 'selection must not depend on the partition'
         for k, v in full['params'].items():      # Adam normalises per element: the update can differ by a fraction of lr per step
-            assert np.abs(params[k] - v).max() <= 2e-5 * max(np.abs(v).max(), 1e-6) + (0.1 if precision == 'fp32' else 1.0) * 1e-3 * steps, (rank, k)
+            assert np.abs(params[k] - v).max() <= 2e-5 * max(np.abs(v).max(), 1e-6) + (0.1 if precision == 'fp32' else 2.0) * 1e-3 * steps, (rank, k)
     for k in res[0][4]:
         np.testing.assert_array_equal(res[0][4][k], res[1][4][k])     # bit-identical parameters on both ranks
