@@ -53,11 +53,12 @@ struct Tuning {
     int min_kiters = 8;          // EMB_MIN_KITERS          split-K: minimum K blocks per CTA
     int wgrad_taps = 0;          // EMB_WGRAD_TAPS          conv wgrad taps per CTA (0: as many as TMEM holds, 1: per-tap kernel)
     int wgrad_ntile = 128;       // EMB_WGRAD_NT            conv wgrad N tile
-    int wgrad_fuse_taps = 0;     // EMB_WGRAD_FUSE_TAPS     conv wgrad with Cin = 64: up to four taps per tcgen05.mma
+    int wgrad_fuse_taps = 1;     // EMB_WGRAD_FUSE_TAPS     conv wgrad with Cin = 64: up to four taps per tcgen05.mma (verified r2; 0 = one MMA per tap)
     int deterministic = 0;       // EMB_DETERMINISTIC       fixed-order reductions: no split-K, one CTA per reduction column block
     int k2_wide = 1;             // EMB_K2_WIDE             8-channel (16-byte) forward pooling kernel where C % 8 == 0
     int infer_fuse = 0;          // EMB_INFER_FUSE          eval forward: BatchNorm + ReLU + MaxPool in the conv GEMM epilogue (no pre-pooling tensor);
                                  //                         off by default: with four epilogue warps the fused epilogue is latency-bound and slower (r2 measurement)
+    int tc_min_mflop = 0;        // EMB_TC_MIN_MFLOP        Linear GEMMs below this many MFLOP run on the SIMT kernel (0: tensor cores whenever the shape allows)
     int fork = 1;                // EMB_FORK                independent branches of the step on side streams (parallel graph branches)
 };
 struct TuningName { const char* env; const char* name; int Tuning::*field; };
@@ -71,7 +72,7 @@ inline const TuningName* tuning_names(int* n) {
         {"EMB_MIN_KITERS", "min_kiters", &Tuning::min_kiters}, {"EMB_WGRAD_TAPS", "wgrad_taps", &Tuning::wgrad_taps},
         {"EMB_WGRAD_NT", "wgrad_ntile", &Tuning::wgrad_ntile}, {"EMB_WGRAD_FUSE_TAPS", "wgrad_fuse_taps", &Tuning::wgrad_fuse_taps},
         {"EMB_DETERMINISTIC", "deterministic", &Tuning::deterministic}, {"EMB_K2_WIDE", "k2_wide", &Tuning::k2_wide},
-        {"EMB_FORK", "fork", &Tuning::fork}, {"EMB_INFER_FUSE", "infer_fuse", &Tuning::infer_fuse},
+        {"EMB_FORK", "fork", &Tuning::fork}, {"EMB_TC_MIN_MFLOP", "tc_min_mflop", &Tuning::tc_min_mflop}, {"EMB_INFER_FUSE", "infer_fuse", &Tuning::infer_fuse},
     };
     *n = (int)(sizeof t / sizeof t[0]);
     return t;

@@ -683,8 +683,11 @@ int stream_after(EmbEngine* e, cudaStream_t from, cudaStream_t to) {
 }
 
 // can this Linear layer's GEMMs run on the tensor-core kernel?  (the flattened CNN input must be dense)
-bool tc_linear_ok(const EmbEngine* e, const LinearLayer& l) {
+bool tc_linear_ok(const EmbEngine* e, const LinearLayer& l, int B = 1 << 30) {
     if (!tc_on(e) || l.out < 16 || l.in < 16) return false;
+    // a persistent tcgen05 launch costs ~10 us before its first MMA retires (TMEM allocation, barrier set-up, pipeline fill): below
+    // `tc_min_mflop` the SIMT kernel finishes first (small-batch steps, the narrow FFNN layers)
+    if (2.0 * (double)B * l.out * l.in < 1e6 * (double)tuning().tc_min_mflop) return false;
     if (l.flat_in && e->cnn_ld_last != e->cnn_C_last) return false;
     return true;
 }
@@ -743,7 +746,7 @@ int linear_forward(EmbEngine* e, const LinearLayer& l, const Act& in, const Act&
     ep.bias = e->params + l.b;
     ep.relu = l.relu;
     if (training && l.drop > 0.f) { ep.drop_p = l.drop; ep.drop_u = drop_u; ep.rng_stream = stream_id; }
-    if (tc_linear_ok(e, l)) {
+    if (tc_linear_ok(e, l, B)) {
         TcProblem pr = {};
         pr.kind = TC_LINEAR_FWD; pr.a = (const bf16*)in.p; pr.lda = in.ld; pr.b = l.wc; pr.ldb = round_up(l.in, 8);
         pr.M = B; pr.N = l.out; pr.K = l.in;
@@ -768,7 +771,7 @@ int linear_wgrad(EmbEngine* e, const LinearLayer& l, const void* g, int g_dtype,
         LAUNCHED(e);
         return EMB_OK;
     }
-    if (tc_linear_ok(e, l) && g_dtype == 1 && (g_ld % 8) == 0) {
+    if (tc_linear_ok(e, l, B) && g_dtype == 1 && (g_ld % 8) == 0) {
         TcProblem pr = {};
         pr.kind = TC_LINEAR_WGRAD; pr.a = (const bf16*)g; pr.lda = g_ld; pr.b = (const bf16*)in.p; pr.ldb = in.ld;
         pr.M = l.out; pr.N = l.in; pr.K = B;
@@ -805,7 +808,7 @@ int linear_dgrad(EmbEngine* e, const LinearLayer& l, const void* g, int g_dtype,
         LAUNCHED(e);
         return EMB_OK;
     }
-    if (tc_linear_ok(e, l) && g_dtype == 1 && (g_ld % 8) == 0) {
+    if (tc_linear_ok(e, l, B) && g_dtype == 1 && (g_ld % 8) == 0) {
         TcProblem pr = {};
         pr.kind = TC_LINEAR_DGRAD; pr.a = (const bf16*)g; pr.lda = g_ld; pr.b = l.wc; pr.ldb = round_up(l.in, 8);
         pr.M = B; pr.N = l.in; pr.K = l.out;
@@ -1205,7 +1208,7 @@ int forward_impl(EmbEngine* e, const float* x_ffnn, const uint8_t* bases, const 
             ep.emb_u = dr ? dr->embrace_u : nullptr;
             ep.cum0 = e->cum0;
             ep.idx_out = e->idx;
-            if (tc_linear_ok(e, e->dock1)) {
+            if (tc_linear_ok(e, e->dock1, B)) {
                 TcProblem pr = {};
                 pr.kind = TC_LINEAR_FWD; pr.a = (const bf16*)flat.p; pr.lda = flat.ld; pr.b = e->dock1.wc; pr.ldb = round_up(e->dock1.in, 8);
                 pr.M = B; pr.N = C; pr.K = e->dock1.in;

@@ -78,7 +78,7 @@ def run_case(name, precision, tensor_core=False, B_override=None):
             plain, _ = O.forward(spec, P, x, bases, draws, training=True)
             # bf16 storage makes the step chaotic at small batch (one rounding flip re-routes a max-pool / ReLU
             # gradient): calibrate each tensor's tolerance with the emulated oracle's OWN sensitivity to a 1e-6
-            # relative perturbation of the weights (scratch/chaos.py: up to 1e-1 on arch M at batch 48)
+            # relative perturbation of the weights (profiles/r01_chaos.py: up to 1e-1 on arch M at batch 48)
             prs = np.random.RandomState(12345 + step)
             P_pert = {k: (v * (1 + 1e-6 * prs.standard_normal(v.shape)) if (v.dtype == np.float64 and v.ndim >= 1) else v.copy())
                       for k, v in P.items()}
