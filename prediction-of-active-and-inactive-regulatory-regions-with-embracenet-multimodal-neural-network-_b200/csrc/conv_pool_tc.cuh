@@ -1,0 +1,239 @@
+// Inference conv layer in ONE kernel:  a = MaxPool1d(10, 2)( ReLU( BatchNorm_eval( Conv1d(x) ) ) )      (CNN_pre.py:39-49 in eval mode)
+//
+// The training-shaped forward writes the pre-pooling conv output y (bf16, [B, L, Cout]) and reads it back in the pooling
+// kernel; at inference that round trip is most of the time (arch S, 65 536 regions: 6.2 of 10 GB of traffic).  Fusing the
+// pooling into the epilogue of the row-major conv GEMM (rows = positions) was measured 2.3x SLOWER than not fusing: pooling
+// runs ACROSS rows there, i.e. across threads, through shared memory and named barriers, on four epilogue warps.
+//
+// This kernel computes the TRANSPOSED product instead,
+//     D[cout, position] = sum_{tap, cin} W[tap][cout][cin] * x[position + tap - pad][cin]
+// A = the weights (K-major, 128 cout rows, resident in shared memory for every tap), B = the activation tile (K-major, the
+// same staged tile with its zero halo that conv_tc.cuh uses; tap t is the tile read through a descriptor advanced by t rows),
+// so a TMEM LANE is an output channel and the TMEM COLUMNS are the positions of whole samples.  An epilogue thread then owns
+// one channel: BatchNorm is two registers, and the max-pool window slides along the thread's own registers -- no exchange
+// between threads at all.  Eight epilogue warps (two per TMEM lane quarter, each taking half of the tile's pooled rows) hide
+// the latency of that sequential walk; each pooled row leaves as 32 channels x 2 bytes per warp, channels-last, which is the
+// next layer's input layout.  Arithmetic and rounding points equal the unfused forward (bf16 conv output, fp32 BatchNorm,
+// one bf16 rounding of the pooled value): the results are bit-identical.
+//
+//   warp 0 TMA producer      warp 1 MMA issuer      warps 2-9 epilogue (TMEM lane quarter = warp % 4)
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace emb {
+
+struct TcPoolParams {
+    int Bn, L, S, bt, Lp;            // samples, conv positions, staged rows per sample (L + pad), samples per tile, pooled length
+    int taps, pad, Cout;
+    int n_chunks, k_steps_last;      // K chunks of 64 input channels; UMMA K steps of the last one
+    int total_tiles;
+    int a_slot_bytes, a_box_bytes;   // activation slot ([rows][64 ch], 128B swizzle) and the bytes one TMA box deposits
+    uint32_t idesc;
+    int ld_out;
+};
+
+constexpr int TCP_THREADS = 64 + 8 * 32;
+constexpr int TCP_W_SLOT = 128 * 128;        // one (chunk, tap) weight block: 128 cout rows x 64 cin x bf16
+
+__global__ void __launch_bounds__(TCP_THREADS, 1)
+tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcPoolParams p,
+                    const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift, bf16* __restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_w = smem + 2 * p.a_slot_bytes;
+    uint64_t* bars = (uint64_t*)(smem_w + (size_t)p.taps * p.n_chunks * TCP_W_SLOT);
+    uint64_t* a_full = bars;             // [2]
+    uint64_t* a_empty = a_full + 2;      // [2]
+    uint64_t* w_full = a_empty + 2;      // [1]
+    uint64_t* tfull = w_full + 1;        // [2]
+    uint64_t* tempty = tfull + 2;        // [2]
+    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+    {   // halo / tail rows of the activation slots must read as zero
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < 2 * p.a_slot_bytes / 16; i += TCP_THREADS) ((uint4*)smem)[i] = z;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+        mbar_init(w_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            const uint64_t mx = (uint64_t)&map_x, mw = (uint64_t)&map_w;
+            const uint32_t sa0 = smem_u32(smem), sw0 = smem_u32(smem_w);
+            {   // every tap of the weights, once: box {64 cin, 128 cout rows (rows >= Cout are zero-filled), 1 tap}
+                const uint32_t bar = smem_u32(w_full);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(p.taps * p.n_chunks * TCP_W_SLOT)) : "memory");
+                for (int c = 0; c < p.n_chunks; ++c)
+                    for (int t = 0; t < p.taps; ++t)
+                        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                                     ::"r"(sw0 + (uint32_t)((c * p.taps + t) * TCP_W_SLOT)), "l"(mw), "r"(bar), "r"(c * 64), "r"(0), "r"(t) : "memory");
+            }
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x)
+                for (int c = 0; c < p.n_chunks; ++c) {
+                    mbar_wait(&a_empty[as], aphase ^ 1);
+                    const uint32_t abar = smem_u32(&a_full[as]);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(abar), "r"((uint32_t)p.a_box_bytes) : "memory");
+                    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                                 ::"r"(sa0 + (uint32_t)(as * p.a_slot_bytes)), "l"(mx), "r"(abar), "r"(c * 64), "r"(-p.pad), "r"(tile * p.bt) : "memory");
+                    if (++as == 2) { as = 0; aphase ^= 1; }
+                }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer: D[cout][position] += W[tap][cout][:] . x[position + tap][:] =================
+        const uint64_t dproto = umma_desc(0, 16, 1024);
+        const uint32_t d_hi = (uint32_t)(dproto >> 32), d_lo16 = (uint32_t)dproto;
+        const uint32_t sa0 = smem_u32(smem), sw0 = smem_u32(smem_w), idesc = p.idesc;
+        int as = 0, acc = 0;
+        uint32_t aphase = 0, acc_phase = 0;
+        mbar_wait(w_full, 0);
+        tc_fence_after();
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+            uint32_t accumulate = 0;
+            for (int c = 0; c < p.n_chunks; ++c) {
+                mbar_wait(&a_full[as], aphase);
+                tc_fence_after();
+                const int ks = (c == p.n_chunks - 1) ? p.k_steps_last : 4;
+                if (elect_one_sync()) {
+                    uint64_t dx = ((uint64_t)d_hi << 32) | (d_lo16 | (((sa0 + (uint32_t)(as * p.a_slot_bytes)) & 0x3FFFFu) >> 4));
+                    uint64_t dw = ((uint64_t)d_hi << 32) | (d_lo16 | (((sw0 + (uint32_t)(c * p.taps) * TCP_W_SLOT) & 0x3FFFFu) >> 4));
+#pragma unroll 1
+                    for (int t = 0; t < p.taps; ++t) {
+                        for (int s2 = 0; s2 < ks; ++s2) {
+                            tc_mma_f16(d_tmem, dw + (uint64_t)(2 * s2), dx + (uint64_t)(2 * s2), idesc, accumulate);
+                            accumulate = 1;
+                        }
+                        dx += 8;                               // next tap: the activation tile one row (128 bytes) further
+                        dw += (uint64_t)(TCP_W_SLOT >> 4);
+                    }
+                    tc_commit(&a_empty[as]);
+                }
+                __syncwarp();
+                accumulate = 1;
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+            if (elect_one_sync()) tc_commit(&tfull[acc]);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ================= epilogue: thread = output channel; its registers walk the positions =================
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int ch = q * 32 + lane;
+        const bool ch_ok = ch < p.Cout;
+        const float b0 = ch_ok ? bias[ch] : 0.f, sc = ch_ok ? scale[ch] : 0.f, sh = ch_ok ? shift[ch] : 0.f;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
+            const int sample0 = tile * p.bt;
+            const int n_samples = min(p.bt, p.Bn - sample0);
+            const int PR = n_samples * p.Lp;                              // pooled rows of this tile, flattened (sample, j)
+            const int pr_lo = half == 0 ? 0 : (PR + 1) / 2, pr_hi = half == 0 ? (PR + 1) / 2 : PR;
+            int pr = pr_lo;
+            while (pr < pr_hi) {
+                const int g = pr / p.Lp, j_lo = pr - g * p.Lp;
+                const int j_hi = min(p.Lp, j_lo + (pr_hi - pr));          // this segment: pooled rows j_lo .. j_hi - 1 of sample g
+                const int col_lo = g * p.S + 2 * j_lo, col_hi = g * p.S + 2 * (j_hi - 1) + 9;      // inclusive
+                bf16* dst = out + ((size_t)(sample0 + g) * p.Lp + j_lo) * p.ld_out + ch;
+                float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f, ze = 0.f;
+                int k = 0;                                                // pairs completed in this segment
+                for (int c16 = col_lo & ~15; c16 <= col_hi; c16 += 16) {
+                    float v[16];
+                    tc_ld16(t_addr + (uint32_t)c16, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int col = c16 + i;
+                        if (col < col_lo || col > col_hi) continue;       // uniform over the warp
+                        const float yv = __bfloat162float(__float2bfloat16_rn(v[i] + b0));
+                        const float z = fmaxf(fmaf(yv, sc, sh), 0.f);
+                        if (((col - col_lo) & 1) == 0) { ze = z; continue; }
+                        const float pm = fmaxf(ze, z);
+                        if (k >= 4) {
+                            const float r = fmaxf(fmaxf(fmaxf(w0, w1), fmaxf(w2, w3)), pm);
+                            if (ch_ok) dst[(size_t)(k - 4) * p.ld_out] = __float2bfloat16_rn(r);
+                        }
+                        w0 = w1; w1 = w2; w2 = w3; w3 = pm;
+                        ++k;
+                    }
+                }
+                pr += j_hi - j_lo;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    }
+}
+
+inline size_t tc_conv_pool_smem(int L, int pad, int taps, int Cin) {
+    const int a_rows = round_up(128 + 2 * pad, 8);
+    return (size_t)2 * a_rows * 128 + (size_t)taps * cdiv(Cin, 64) * TCP_W_SLOT + 1024 + 256;
+}
+
+// x [B, L, Cin] bf16 (ldx), w = Wf [taps][Cout][ldw] bf16, out [B, Lp, ld_out] bf16
+inline bool tc_conv_pool_ok(int L, int pad, int taps, int Cin, int Cout, int Lp, int ldx, int ld_out) {
+    if (L > 128 || taps < 1 || taps > 15 || Cin < 16 || (Cin % 8) || Cout < 8 || Cout > 128 || (Cout % 8) || Lp < 1) return false;
+    if (ldx != Cin || ld_out != Cout) return false;
+    return tc_conv_pool_smem(L, pad, taps, Cin) <= (size_t)tc_max_smem();
+}
+
+inline int tc_conv_pool(const bf16* x, const bf16* w, int ldw, const float* bias, const float* scale, const float* shift, bf16* out, int B, int L,
+                        int Lp, int Cin, int Cout, int taps, int pad, cudaStream_t st) {
+    int rc = tc_init();
+    if (rc) return rc;
+    if (first_on_device(3)) {
+        cudaError_t err = cudaFuncSetAttribute(tc_conv_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_max_smem());
+        if (err != cudaSuccess) return set_error(-3, "cudaFuncSetAttribute(tc_conv_pool_kernel): %s", cudaGetErrorString(err));
+    }
+    TcPoolParams p = {};
+    p.Bn = B; p.L = L; p.S = L + pad; p.bt = 1 + (128 - L) / p.S; p.Lp = Lp; p.taps = taps; p.pad = pad; p.Cout = Cout;
+    p.n_chunks = cdiv(Cin, 64);
+    p.k_steps_last = cdiv(Cin - 64 * (p.n_chunks - 1), 16);
+    p.total_tiles = cdiv(B, p.bt);
+    const int a_rows = round_up(128 + 2 * pad, 8);
+    p.a_slot_bytes = a_rows * 128;
+    p.a_box_bytes = p.bt * p.S * 128;
+    if (p.bt * p.S > a_rows) return set_error(-5, "tc_conv_pool: tile rows exceed the activation slot");
+    p.idesc = make_idesc(0, 0, 128);
+    p.ld_out = Cout;
+    CUtensorMap mx, mw;
+    rc = make_map(&mx, x, Cin, L, B, Cin, (int64_t)L * Cin, 64, p.S, p.bt);
+    if (rc) return rc;
+    rc = make_map(&mw, w, Cin, Cout, taps, ldw, (int64_t)Cout * ldw, 64, 128, 1);
+    if (rc) return rc;
+    const size_t smem = tc_conv_pool_smem(L, pad, taps, Cin);
+    const int grid = std::min(p.total_tiles, tc_num_sms());
+    tc_conv_pool_kernel<<<grid, TCP_THREADS, smem, st>>>(mx, mw, p, bias, scale, shift, out);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return set_error(-3, "tc_conv_pool launch failed: %s", cudaGetErrorString(err));
+    return 0;
+}
+
+}  // namespace emb

@@ -24,6 +24,7 @@
 #include "onehot_wgrad_tc.cuh"
 #include "probe.cuh"
 #include "dp_peer.cuh"
+#include "conv_pool_tc.cuh"
 
 namespace emb {
 
@@ -830,7 +831,7 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
             const int groups = c.cout / 8;
             if (std::is_same<T, bf16>::value && tc_on(e) && onehot_fwd_tc_ok(c.y, bases, c.cout, c.k, c.ld)) {
                 // one-hot rows expanded in shared memory, all taps through a Toeplitz descriptor, fp32 weights as an exact hi/mid/lo bf16 split
-                if (!training && tuning().infer_fuse) {
+                if (!training && tuning().infer_fuse == 1) {
                     // inference: eval BatchNorm + ReLU + MaxPool on the staged sample inside the same kernel; y0 is never written
                     bn_finalize_kernel<<<cdiv(c.cout, 128), 128, 0, st>>>(c.stats, e->params + c.gamma, e->params + c.beta, e->buffers + c.rm,
                                                                           e->buffers + c.rv, c.scale, c.shift, c.mean, c.rstd, 1.0, c.cout, 0);
@@ -876,7 +877,23 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
             Epilogue ep = base_epi(e, EPI_LINEAR, c.y, c.ld);
             ep.bias = e->params + c.b;
             int rc;
-            if (!training && tc_conv_ok(e, c) && c.ld == c.cout && tuning().infer_fuse) {
+            if (!training && tuning().infer_fuse == 2 && tc_on(e) && std::is_same<T, bf16>::value &&
+                tc_conv_pool_ok(c.Lc, c.pad, c.k, c.cin, c.cout, c.Lp, pr_.ld, c.ld)) {
+                // Inference, transposed form (conv_pool_tc.cuh): TMEM lane = output channel, columns = positions; eval BatchNorm + ReLU +
+                // MaxPool slide along each epilogue thread's own registers.  The pre-pooling conv output is never written.
+                bn_finalize_kernel<<<cdiv(c.cout, 128), 128, 0, st>>>(c.stats, e->params + c.gamma, e->params + c.beta, e->buffers + c.rm,
+                                                                      e->buffers + c.rv, c.scale, c.shift, c.mean, c.rstd, 1.0, c.cout, 0);
+                EMB_CHECK_LAUNCH();
+                LAUNCHED(e);
+                prof_begin(e, 2.0 * B * c.Lc * c.cout * c.k * c.cin, st);
+                int rcp = tc_conv_pool((const bf16*)pr_.a, c.wc, round_up(c.cin, 8), e->params + c.b, c.scale, c.shift, (bf16*)c.a, B, c.Lc, c.Lp, c.cin,
+                                       c.cout, c.k, c.pad, st);
+                prof_end(e, st);
+                if (rcp) return rcp;
+                LAUNCHED(e);
+                continue;
+            }
+            if (!training && tc_conv_ok(e, c) && c.ld == c.cout && tuning().infer_fuse == 1) {
                 // Inference: eval-mode BatchNorm (one scale / shift per channel from the running statistics) + ReLU + MaxPool run in
                 // the conv GEMM's epilogue on the tile, which holds whole samples: the pre-pooling conv output is never written.
                 bn_finalize_kernel<<<cdiv(c.cout, 128), 128, 0, st>>>(c.stats, e->params + c.gamma, e->params + c.beta, e->buffers + c.rm,

@@ -1,6 +1,9 @@
-"""Inference forward with BatchNorm(eval) + ReLU + MaxPool1d fused into the conv GEMM epilogue (EPI_POOL, csrc/gemm_tc.cuh):
-the pre-pooling conv output is never written.  The fused and the unfused eval forward share arithmetic and rounding points, so
-their outputs must be IDENTICAL; both are also held to the oracle's eval forward (EmbraceNetMultimodal_NoTrain.py:180-214)."""
+"""Inference forwards that never write the pre-pooling conv output (option `infer_fuse`):
+  2  transposed conv + in-register pooling (csrc/conv_pool_tc.cuh: TMEM lane = channel, columns = positions)
+  1  BatchNorm(eval) + ReLU + MaxPool1d in the row-major conv GEMM epilogue (EPI_POOL, csrc/gemm_tc.cuh)
+  0  unfused (conv writes y, the pooling kernel reads it)
+All share arithmetic and rounding points; 1 must equal 0 bit for bit, 2 up to the accumulation order; all are held to the oracle's
+eval forward (EmbraceNetMultimodal_NoTrain.py:180-214)."""
 import numpy as np
 import pytest
 
@@ -25,7 +28,7 @@ def test_fused_pooling_epilogue_equals_unfused_eval_forward(arch, B):
     av[1::7, 1] = 0
     av[(av.sum(1) == 0), 0] = 1
     out = {}
-    for fuse in (1, 0):
+    for fuse in (2, 1, 0):
         N.set_option('infer_fuse', fuse)
         try:
             eng = Engine(to_archspec(spec), max_batch=B, precision='bf16', tensor_core=True)
@@ -37,9 +40,16 @@ def test_fused_pooling_epilogue_equals_unfused_eval_forward(arch, B):
             out[fuse] = (logits.cpu().numpy(), probs.cpu().numpy(), eng.launch_count - l0)
         finally:
             N.set_option('infer_fuse', 0)
-    assert np.isfinite(out[1][0]).all()
+    for fuse in (2, 1):
+        assert np.isfinite(out[fuse][0]).all()
+        assert out[fuse][2] <= out[0][2], 'a fused forward must not launch more kernels'
+    # pooling in the row-major epilogue shares every accumulation with the unfused forward: identical bits
     assert np.array_equal(out[1][0], out[0][0]), np.abs(out[1][0] - out[0][0]).max()
-    assert out[1][2] < out[0][2], 'the fused forward must launch fewer kernels'
+    # the transposed kernel shares products and rounding points; only the tensor core's accumulation order may differ, which
+    # can move an fp32 sum across a bf16 rounding boundary now and then
+    scale = np.abs(out[0][0]).max()
+    assert np.abs(out[2][0] - out[0][0]).max() <= 2e-3 * scale, np.abs(out[2][0] - out[0][0]).max() / scale
     if B <= 300:
         ref = O.predict_proba(spec, P, x, bases, u, availabilities=av)
-        assert np.abs(out[1][1] - ref).max() <= 5e-3
+        for fuse in (2, 1, 0):
+            assert np.abs(out[fuse][1] - ref).max() <= 5e-3
