@@ -14,7 +14,8 @@
 // between threads at all.  Eight epilogue warps (two per TMEM lane quarter, each taking half of the tile's pooled rows) hide
 // the latency of that sequential walk; each pooled row leaves as 32 channels x 2 bytes per warp, channels-last, which is the
 // next layer's input layout.  Arithmetic and rounding points equal the unfused forward (bf16 conv output, fp32 BatchNorm,
-// one bf16 rounding of the pooled value): the results are bit-identical.
+// one bf16 rounding of the pooled value) except that the conv bias is folded into the BatchNorm shift, i.e. the conv output is
+// not rounded to bf16 on the way: one rounding FEWER than the unfused forward.
 //
 //   warp 0 TMA producer      warp 1 MMA issuer      warps 2-9 epilogue (TMEM lane quarter = warp % 4)
 #pragma once
@@ -136,10 +137,15 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
     } else {
         // ================= epilogue: thread = output channel; its registers walk the positions =================
+        // Per PAIR of positions: two fma (the conv bias is folded into the BatchNorm shift), one max for the pair, then the window =
+        // max(four previous pair maxima, this one, 0): ReLU is applied once per pooled element, not per position.  The four ring
+        // slots are named registers (the pair loop is unrolled by 8, a multiple of 4): no moves.  S is even, so every sample starts
+        // on an even column and pairs never straddle samples; pairs that precede a segment only pass through the ring.
         const int q = warp & 3, half = (warp - 2) >> 2;
         const int ch = q * 32 + lane;
         const bool ch_ok = ch < p.Cout;
-        const float b0 = ch_ok ? bias[ch] : 0.f, sc = ch_ok ? scale[ch] : 0.f, sh = ch_ok ? shift[ch] : 0.f;
+        const float sc = ch_ok ? scale[ch] : 0.f;
+        const float shb = ch_ok ? fmaf(bias[ch], sc, shift[ch]) : 0.f;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -153,31 +159,27 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             int pr = pr_lo;
             while (pr < pr_hi) {
                 const int g = pr / p.Lp, j_lo = pr - g * p.Lp;
-                const int j_hi = min(p.Lp, j_lo + (pr_hi - pr));          // this segment: pooled rows j_lo .. j_hi - 1 of sample g
-                const int col_lo = g * p.S + 2 * j_lo, col_hi = g * p.S + 2 * (j_hi - 1) + 9;      // inclusive
-                bf16* dst = out + ((size_t)(sample0 + g) * p.Lp + j_lo) * p.ld_out + ch;
-                float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f, ze = 0.f;
-                int k = 0;                                                // pairs completed in this segment
-                for (int c16 = col_lo & ~15; c16 <= col_hi; c16 += 16) {
+                const int n = min(p.Lp - j_lo, pr_hi - pr);               // this segment: pooled rows j_lo .. j_lo + n - 1 of sample g
+                const int P_first = ((g * p.S) >> 1) + j_lo + 4, P_end = P_first + n;      // the pair that completes window j is pair j + 4
+                bf16* dst = out + ((size_t)(sample0 + g) * p.Lp + j_lo) * p.ld_out + ch - (size_t)P_first * p.ld_out;
+                float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+                for (int c16 = (2 * (P_first - 4)) & ~15; c16 < 2 * P_end; c16 += 16) {
                     float v[16];
                     tc_ld16(t_addr + (uint32_t)c16, v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int col = c16 + i;
-                        if (col < col_lo || col > col_hi) continue;       // uniform over the warp
-                        const float yv = __bfloat162float(__float2bfloat16_rn(v[i] + b0));
-                        const float z = fmaxf(fmaf(yv, sc, sh), 0.f);
-                        if (((col - col_lo) & 1) == 0) { ze = z; continue; }
-                        const float pm = fmaxf(ze, z);
-                        if (k >= 4) {
-                            const float r = fmaxf(fmaxf(fmaxf(w0, w1), fmaxf(w2, w3)), pm);
-                            if (ch_ok) dst[(size_t)(k - 4) * p.ld_out] = __float2bfloat16_rn(r);
-                        }
-                        w0 = w1; w1 = w2; w2 = w3; w3 = pm;
-                        ++k;
+                    const int P0 = c16 >> 1;
+#define EMB_POOL_PAIR(PP, SLOT)                                                                              \
+                    {                                                                                        \
+                        const float pm = fmaxf(fmaf(v[2 * (PP)], sc, shb), fmaf(v[2 * (PP) + 1], sc, shb));  \
+                        const float r = fmaxf(fmaxf(fmaxf(w0, w1), fmaxf(w2, w3)), fmaxf(pm, 0.f));          \
+                        const int P = P0 + (PP);                                                             \
+                        if (ch_ok && P >= P_first && P < P_end) dst[(size_t)P * p.ld_out] = __float2bfloat16_rn(r); \
+                        SLOT = pm;                                                                           \
                     }
+                    EMB_POOL_PAIR(0, w0) EMB_POOL_PAIR(1, w1) EMB_POOL_PAIR(2, w2) EMB_POOL_PAIR(3, w3)
+                    EMB_POOL_PAIR(4, w0) EMB_POOL_PAIR(5, w1) EMB_POOL_PAIR(6, w2) EMB_POOL_PAIR(7, w3)
+#undef EMB_POOL_PAIR
                 }
-                pr += j_hi - j_lo;
+                pr += n;
             }
             tc_fence_before();
             __syncwarp();
@@ -213,7 +215,8 @@ inline int tc_conv_pool(const bf16* x, const bf16* w, int ldw, const float* bias
         if (err != cudaSuccess) return set_error(-3, "cudaFuncSetAttribute(tc_conv_pool_kernel): %s", cudaGetErrorString(err));
     }
     TcPoolParams p = {};
-    p.Bn = B; p.L = L; p.S = L + pad; p.bt = 1 + (128 - L) / p.S; p.Lp = Lp; p.taps = taps; p.pad = pad; p.Cout = Cout;
+    p.Bn = B; p.L = L; p.S = round_up(L + pad, 2);          // even: every sample starts on an even TMEM column
+    p.bt = 1 + (128 - L) / p.S; p.Lp = Lp; p.taps = taps; p.pad = pad; p.Cout = Cout;
     p.n_chunks = cdiv(Cin, 64);
     p.k_steps_last = cdiv(Cin - 64 * (p.n_chunks - 1), 16);
     p.total_tiles = cdiv(B, p.bt);

@@ -955,7 +955,8 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
         const float* du = (dr && p > 0.f) ? dr->cnn_drop[i] : nullptr;
         const bool kt_bwd = std::is_same<T, bf16>::value && kt_ok(c.cout, c.ld) && kt_bwd_smem(c.Lc, c.Lp, c.cout) <= (size_t)kt_max_smem() &&
                             !tuning().no_tma_k2;    // the backward will consume the arg-max codes
-        if (std::is_same<T, bf16>::value && tuning().k2_wide && (c.cout % 8) == 0 && c.ld == c.cout) {
+        if (training && std::is_same<T, bf16>::value && tuning().k2_wide && (c.cout % 8) == 0 && c.ld == c.cout) {
+            // (eval keeps the streaming kernel: without codes and Dropout it already runs at 5.9 TB/s)
             // packed kernel: 8 channels per thread, pooling on the stored bf16 values, BatchNorm on the pooled maximum only
             const int blocks = cdiv((size_t)B * (c.cout / 8), 256);
             uint8_t* am = (training && kt_bwd) ? c.amax : nullptr;
