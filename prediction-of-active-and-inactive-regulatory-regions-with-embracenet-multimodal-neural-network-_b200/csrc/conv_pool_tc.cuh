@@ -29,23 +29,27 @@ struct TcPoolParams {
     int n_chunks, k_steps_last;      // K chunks of 64 input channels; UMMA K steps of the last one
     int total_tiles;
     int a_slot_bytes, a_box_bytes;   // activation slot ([rows][64 ch], 128B swizzle) and the bytes one TMA box deposits
+    int a_slots;                     // activation slots in flight: tiles are small (one or two boxes), so the prefetch must be several tiles deep
+    int w_bytes;                     // all weight blocks + one slack block for the last MMA's over-read, rounded to 1 KB
+    int w_slot_bytes;                // one (chunk, tap) weight block: Cout rows x 128 B.  The MMA reads 128 rows from there: for Cout < 128 the
+                                     // rows behind are the next block's (or the barriers') bytes -- they only feed TMEM lanes >= Cout, which nobody reads
     uint32_t idesc;
     int ld_out;
 };
 
 constexpr int TCP_THREADS = 64 + 8 * 32;
-constexpr int TCP_W_SLOT = 128 * 128;        // one (chunk, tap) weight block: 128 cout rows x 64 cin x bf16
+constexpr int TCP_MAX_SLOTS = 8;
 
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcPoolParams p,
                     const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift, bf16* __restrict__ out) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* smem_w = smem + 2 * p.a_slot_bytes;
-    uint64_t* bars = (uint64_t*)(smem_w + (size_t)p.taps * p.n_chunks * TCP_W_SLOT);
-    uint64_t* a_full = bars;             // [2]
-    uint64_t* a_empty = a_full + 2;      // [2]
-    uint64_t* w_full = a_empty + 2;      // [1]
+    uint8_t* smem_w = smem + p.a_slots * p.a_slot_bytes;
+    uint64_t* bars = (uint64_t*)(smem_w + p.w_bytes);
+    uint64_t* a_full = bars;                        // [8]
+    uint64_t* a_empty = a_full + TCP_MAX_SLOTS;      // [8]
+    uint64_t* w_full = a_empty + TCP_MAX_SLOTS;      // [1]
     uint64_t* tfull = w_full + 1;        // [2]
     uint64_t* tempty = tfull + 2;        // [2]
     uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
@@ -53,11 +57,12 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
     {   // halo / tail rows of the activation slots must read as zero
         const uint4 z = make_uint4(0, 0, 0, 0);
-        for (int i = threadIdx.x; i < 2 * p.a_slot_bytes / 16; i += TCP_THREADS) ((uint4*)smem)[i] = z;
+        for (int i = threadIdx.x; i < p.a_slots * p.a_slot_bytes / 16; i += TCP_THREADS) ((uint4*)smem)[i] = z;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+        for (int s = 0; s < TCP_MAX_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
         mbar_init(w_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -75,13 +80,13 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         if (lane == 0) {
             const uint64_t mx = (uint64_t)&map_x, mw = (uint64_t)&map_w;
             const uint32_t sa0 = smem_u32(smem), sw0 = smem_u32(smem_w);
-            {   // every tap of the weights, once: box {64 cin, 128 cout rows (rows >= Cout are zero-filled), 1 tap}
+            {   // every tap of the weights, once: box {64 cin, Cout rows, 1 tap}
                 const uint32_t bar = smem_u32(w_full);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(p.taps * p.n_chunks * TCP_W_SLOT)) : "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(p.taps * p.n_chunks * p.w_slot_bytes)) : "memory");
                 for (int c = 0; c < p.n_chunks; ++c)
                     for (int t = 0; t < p.taps; ++t)
                         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                                     ::"r"(sw0 + (uint32_t)((c * p.taps + t) * TCP_W_SLOT)), "l"(mw), "r"(bar), "r"(c * 64), "r"(0), "r"(t) : "memory");
+                                     ::"r"(sw0 + (uint32_t)((c * p.taps + t) * p.w_slot_bytes)), "l"(mw), "r"(bar), "r"(c * 64), "r"(0), "r"(t) : "memory");
             }
             int as = 0;
             uint32_t aphase = 0;
@@ -92,7 +97,7 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(abar), "r"((uint32_t)p.a_box_bytes) : "memory");
                     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                                  ::"r"(sa0 + (uint32_t)(as * p.a_slot_bytes)), "l"(mx), "r"(abar), "r"(c * 64), "r"(-p.pad), "r"(tile * p.bt) : "memory");
-                    if (++as == 2) { as = 0; aphase ^= 1; }
+                    if (++as == p.a_slots) { as = 0; aphase ^= 1; }
                 }
         }
     } else if (warp == 1) {
@@ -115,7 +120,7 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 const int ks = (c == p.n_chunks - 1) ? p.k_steps_last : 4;
                 if (elect_one_sync()) {
                     uint64_t dx = ((uint64_t)d_hi << 32) | (d_lo16 | (((sa0 + (uint32_t)(as * p.a_slot_bytes)) & 0x3FFFFu) >> 4));
-                    uint64_t dw = ((uint64_t)d_hi << 32) | (d_lo16 | (((sw0 + (uint32_t)(c * p.taps) * TCP_W_SLOT) & 0x3FFFFu) >> 4));
+                    uint64_t dw = ((uint64_t)d_hi << 32) | (d_lo16 | (((sw0 + (uint32_t)(c * p.taps) * (uint32_t)p.w_slot_bytes) & 0x3FFFFu) >> 4));
 #pragma unroll 1
                     for (int t = 0; t < p.taps; ++t) {
                         for (int s2 = 0; s2 < ks; ++s2) {
@@ -123,13 +128,13 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                             accumulate = 1;
                         }
                         dx += 8;                               // next tap: the activation tile one row (128 bytes) further
-                        dw += (uint64_t)(TCP_W_SLOT >> 4);
+                        dw += (uint64_t)(p.w_slot_bytes >> 4);
                     }
                     tc_commit(&a_empty[as]);
                 }
                 __syncwarp();
                 accumulate = 1;
-                if (++as == 2) { as = 0; aphase ^= 1; }
+                if (++as == p.a_slots) { as = 0; aphase ^= 1; }
             }
             if (elect_one_sync()) tc_commit(&tfull[acc]);
             __syncwarp();
@@ -194,16 +199,17 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     }
 }
 
-inline size_t tc_conv_pool_smem(int L, int pad, int taps, int Cin) {
+inline size_t tc_conv_pool_wbytes(int taps, int Cin, int Cout) { return round_up64((int64_t)taps * cdiv(Cin, 64) * Cout * 128 + 128 * 128, 1024); }
+inline size_t tc_conv_pool_smem(int pad, int taps, int Cin, int Cout, int slots) {
     const int a_rows = round_up(128 + 2 * pad, 8);
-    return (size_t)2 * a_rows * 128 + (size_t)taps * cdiv(Cin, 64) * TCP_W_SLOT + 1024 + 256;
+    return (size_t)slots * a_rows * 128 + tc_conv_pool_wbytes(taps, Cin, Cout) + 1024 + 512;
 }
 
 // x [B, L, Cin] bf16 (ldx), w = Wf [taps][Cout][ldw] bf16, out [B, Lp, ld_out] bf16
 inline bool tc_conv_pool_ok(int L, int pad, int taps, int Cin, int Cout, int Lp, int ldx, int ld_out) {
     if (L > 128 || taps < 1 || taps > 15 || Cin < 16 || (Cin % 8) || Cout < 8 || Cout > 128 || (Cout % 8) || Lp < 1) return false;
     if (ldx != Cin || ld_out != Cout) return false;
-    return tc_conv_pool_smem(L, pad, taps, Cin) <= (size_t)tc_max_smem();
+    return tc_conv_pool_smem(pad, taps, Cin, Cout, 2) <= (size_t)tc_max_smem();
 }
 
 inline int tc_conv_pool(const bf16* x, const bf16* w, int ldw, const float* bias, const float* scale, const float* shift, bf16* out, int B, int L,
@@ -229,9 +235,13 @@ inline int tc_conv_pool(const bf16* x, const bf16* w, int ldw, const float* bias
     CUtensorMap mx, mw;
     rc = make_map(&mx, x, Cin, L, B, Cin, (int64_t)L * Cin, 64, p.S, p.bt);
     if (rc) return rc;
-    rc = make_map(&mw, w, Cin, Cout, taps, ldw, (int64_t)Cout * ldw, 64, 128, 1);
+    rc = make_map(&mw, w, Cin, Cout, taps, ldw, (int64_t)Cout * ldw, 64, Cout, 1);
     if (rc) return rc;
-    const size_t smem = tc_conv_pool_smem(L, pad, taps, Cin);
+    p.w_slot_bytes = Cout * 128;
+    p.w_bytes = (int)tc_conv_pool_wbytes(taps, Cin, Cout);
+    p.a_slots = 2;
+    while (p.a_slots < TCP_MAX_SLOTS && tc_conv_pool_smem(pad, taps, Cin, Cout, p.a_slots + 1) <= (size_t)tc_max_smem()) ++p.a_slots;
+    const size_t smem = tc_conv_pool_smem(pad, taps, Cin, Cout, p.a_slots);
     const int grid = std::min(p.total_tiles, tc_num_sms());
     tc_conv_pool_kernel<<<grid, TCP_THREADS, smem, st>>>(mx, mw, p, bias, scale, shift, out);
     cudaError_t err = cudaGetLastError();
