@@ -168,22 +168,35 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 const int P_first = ((g * p.S) >> 1) + j_lo + 4, P_end = P_first + n;      // the pair that completes window j is pair j + 4
                 bf16* dst = out + ((size_t)(sample0 + g) * p.Lp + j_lo) * p.ld_out + ch - (size_t)P_first * p.ld_out;
                 float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-                for (int c16 = (2 * (P_first - 4)) & ~15; c16 < 2 * P_end; c16 += 16) {
-                    float v[16];
-                    tc_ld16(t_addr + (uint32_t)c16, v);
-                    const int P0 = c16 >> 1;
-#define EMB_POOL_PAIR(PP, SLOT)                                                                              \
+#define EMB_POOL_PAIR(V, PP, SLOT)                                                                           \
                     {                                                                                        \
-                        const float pm = fmaxf(fmaf(v[2 * (PP)], sc, shb), fmaf(v[2 * (PP) + 1], sc, shb));  \
+                        const float pm = fmaxf(fmaf(V[2 * (PP)], sc, shb), fmaf(V[2 * (PP) + 1], sc, shb));  \
                         const float r = fmaxf(fmaxf(fmaxf(w0, w1), fmaxf(w2, w3)), fmaxf(pm, 0.f));          \
                         const int P = P0 + (PP);                                                             \
                         if (ch_ok && P >= P_first && P < P_end) dst[(size_t)P * p.ld_out] = __float2bfloat16_rn(r); \
                         SLOT = pm;                                                                           \
                     }
-                    EMB_POOL_PAIR(0, w0) EMB_POOL_PAIR(1, w1) EMB_POOL_PAIR(2, w2) EMB_POOL_PAIR(3, w3)
-                    EMB_POOL_PAIR(4, w0) EMB_POOL_PAIR(5, w1) EMB_POOL_PAIR(6, w2) EMB_POOL_PAIR(7, w3)
-#undef EMB_POOL_PAIR
+#define EMB_POOL_CHUNK(V)                                                                                    \
+                    EMB_POOL_PAIR(V, 0, w0) EMB_POOL_PAIR(V, 1, w1) EMB_POOL_PAIR(V, 2, w2) EMB_POOL_PAIR(V, 3, w3) \
+                    EMB_POOL_PAIR(V, 4, w0) EMB_POOL_PAIR(V, 5, w1) EMB_POOL_PAIR(V, 6, w2) EMB_POOL_PAIR(V, 7, w3)
+                // up to four 16-column TMEM loads are in flight before the single wait: the load latency is exposed once per 64
+                // columns, not once per 16 (with one wait per chunk the epilogue, not the tensor pipe, set the tile time)
+                for (int c16 = (2 * (P_first - 4)) & ~15; c16 < 2 * P_end; c16 += 64) {
+                    float va[16], vb[16], vc[16], vd[16];
+                    const bool hb = c16 + 16 < 2 * P_end, hc = c16 + 32 < 2 * P_end, hd = c16 + 48 < 2 * P_end;
+                    tc_ld16_nowait(t_addr + (uint32_t)c16, va);
+                    if (hb) tc_ld16_nowait(t_addr + (uint32_t)(c16 + 16), vb);
+                    if (hc) tc_ld16_nowait(t_addr + (uint32_t)(c16 + 32), vc);
+                    if (hd) tc_ld16_nowait(t_addr + (uint32_t)(c16 + 48), vd);
+                    tc_ld_wait();
+                    int P0 = c16 >> 1;
+                    EMB_POOL_CHUNK(va)
+                    if (hb) { P0 += 8; EMB_POOL_CHUNK(vb) }
+                    if (hc) { P0 += 8; EMB_POOL_CHUNK(vc) }
+                    if (hd) { P0 += 8; EMB_POOL_CHUNK(vd) }
                 }
+#undef EMB_POOL_CHUNK
+#undef EMB_POOL_PAIR
                 pr += n;
             }
             tc_fence_before();

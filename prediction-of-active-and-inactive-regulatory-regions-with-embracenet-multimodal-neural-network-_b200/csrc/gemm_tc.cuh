@@ -83,6 +83,17 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// the same load without the wait: several can be in flight before one tc_ld_wait() (the registers are undefined until then)
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): SWIZZLE_128B, version 1 (Blackwell)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -785,7 +796,10 @@ inline int tc_gemm(const TcProblem& pr, const Epilogue& ep, cudaStream_t st, int
     if (kind == TC_LINEAR_FWD || kind == TC_CONV_FWD || kind == TC_LINEAR_DGRAD || kind == TC_CONV_DGRAD) {
         const int N = pr.N;
         n_tile = N <= 256 ? round_up(N, 16) : 256;
-        // balance the N tiles (e.g. N = 1000 -> 4 x 256 rather than 3 x 256 + 232 is the same count; keep 256)
+        // few row tiles (small batch, data-parallel shards): narrower N tiles until the launch has about one tile per SM -- a
+        // 1024 x 1024 x 4096 docking GEMM is 32 tiles of 128 x 256 (48 us on 32 SMs) or 128 tiles of 128 x 64
+        if (!conv)
+            while (n_tile >= 128 && (n_tile % 32) == 0 && cdiv(pr.M, 128) * cdiv(N, n_tile) < tc_num_sms() / 2) n_tile /= 2;
         grid_n = cdiv(N, n_tile);
         p.M = pr.M; p.N = N; p.n_logical = N;
         if (conv) {
