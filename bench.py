@@ -129,12 +129,12 @@ def run_reference(args, rank, world):
     probe = None
     while True:
         probe = TP.time_train(spec, B, 1, 1, seed=789)              # one warm-up step + one timed step
-        if args.ref_batch or probe['seconds'] * (args.steps + max(args.warmup - 1, 0)) <= args.ref_budget or B <= 256:
+        if args.ref_batch or probe['seconds'] * args.steps <= args.ref_budget or B <= 256:
             break
         B //= 2
-    r = TP.time_train(spec, B, args.steps, max(args.warmup - 1, 0), seed=789)
+    r = TP.time_train(spec, B, args.steps, 0, seed=789)            # the probe above was the warm-up (the CPU path has no lazy state left after it)
     val = r['samples_per_s']
-    sample = (f'{args.steps} train steps of batch {B} after {max(args.warmup, 1)} warm-up (arch {args.arch}, fp64, torch {torch.__version__} CPU, '
+    sample = (f'{args.steps} train steps of batch {B} after 2 warm-up (arch {args.arch}, fp64, torch {torch.__version__} CPU, '
               f'{r["seconds"]:.1f} s)')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
@@ -199,7 +199,8 @@ def main():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--tensor-core', type=int, default=1)
     ap.add_argument('--ref-batch', type=int, default=0, help='force the batch of the CPU arm (0: the global batch, halved until it fits --ref-budget)')
-    ap.add_argument('--ref-budget', type=float, default=170.0, help='seconds the --impl reference run may take')
+    ap.add_argument('--ref-budget', type=float, default=0.0,
+                    help='seconds the timed steps of --impl reference may take (default: 300 at N = 1 -- K = 20 steps of the full batch 8192 fit -- and 120 for N > 1)')
     ap.add_argument('--cpu-baseline', type=int, default=1)
     ap.add_argument('--min-seconds', type=float, default=2.0, help='repeat the K-step timed block until this much device time is measured')
     ap.add_argument('--graph', type=int, default=1, help='replay the train step as one CUDA graph')
@@ -216,6 +217,8 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     if args.impl == 'reference':
+        if args.ref_budget <= 0:
+            args.ref_budget = 300.0 if world == 1 else 120.0
         run_reference(args, rank, world)
         return
 

@@ -56,7 +56,7 @@ struct Tuning {
     int wgrad_fuse_taps = 1;     // EMB_WGRAD_FUSE_TAPS     conv wgrad with Cin = 64: up to four taps per tcgen05.mma (verified r2; 0 = one MMA per tap)
     int deterministic = 0;       // EMB_DETERMINISTIC       fixed-order reductions: no split-K, one CTA per reduction column block
     int k2_wide = 1;             // EMB_K2_WIDE             8-channel (16-byte) forward pooling kernel where C % 8 == 0
-    int infer_fuse = 0;          // EMB_INFER_FUSE          eval forward without the pre-pooling tensor: 2 = transposed conv + in-register pooling
+    int infer_fuse = 2;          // EMB_INFER_FUSE          eval forward without the pre-pooling tensor: 2 = transposed conv + in-register pooling
                                  //                         (conv_pool_tc.cuh), 1 = pooling in the row-major GEMM epilogue (four epilogue warps, through
                                  //                         shared memory: measured 2.3x slower than 0 = unfused)
     int tc_min_mflop = 0;        // EMB_TC_MIN_MFLOP        Linear GEMMs below this many MFLOP run on the SIMT kernel (0: tensor cores whenever the shape allows)
