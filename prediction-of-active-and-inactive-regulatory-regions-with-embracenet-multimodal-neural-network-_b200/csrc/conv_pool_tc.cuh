@@ -42,7 +42,8 @@ constexpr int TCP_MAX_SLOTS = 8;
 
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcPoolParams p,
-                    const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift, bf16* __restrict__ out) {
+                    const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift, bf16* __restrict__ out,
+                    bf16* __restrict__ scratch) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_w = smem + p.a_slots * p.a_slot_bytes;
@@ -151,6 +152,10 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const bool ch_ok = ch < p.Cout;
         const float sc = ch_ok ? scale[ch] : 0.f;
         const float shb = ch_ok ? fmaf(bias[ch], sc, shift[ch]) : 0.f;
+        // A conditional store compiles to a branch with a reconvergence barrier per pair (measured: the epilogue warps then sit in
+        // branch latency, 17 % tensor-pipe activity); pairs outside the segment store to a per-thread scratch slot instead.
+        bf16* const dummy = scratch + (size_t)blockIdx.x * TCP_THREADS + threadIdx.x;
+        const bool quarter_live = q * 32 < p.Cout;                        // a whole warp beyond Cout only keeps the barrier protocol going
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -161,19 +166,21 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             const int n_samples = min(p.bt, p.Bn - sample0);
             const int PR = n_samples * p.Lp;                              // pooled rows of this tile, flattened (sample, j)
             const int pr_lo = half == 0 ? 0 : (PR + 1) / 2, pr_hi = half == 0 ? (PR + 1) / 2 : PR;
-            int pr = pr_lo;
+            int pr = quarter_live ? pr_lo : pr_hi;
             while (pr < pr_hi) {
                 const int g = pr / p.Lp, j_lo = pr - g * p.Lp;
                 const int n = min(p.Lp - j_lo, pr_hi - pr);               // this segment: pooled rows j_lo .. j_lo + n - 1 of sample g
                 const int P_first = ((g * p.S) >> 1) + j_lo + 4, P_end = P_first + n;      // the pair that completes window j is pair j + 4
                 bf16* dst = out + ((size_t)(sample0 + g) * p.Lp + j_lo) * p.ld_out + ch - (size_t)P_first * p.ld_out;
+                const int P_stop = ch_ok ? P_end : P_first;               // lanes beyond Cout never store for real
                 float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
 #define EMB_POOL_PAIR(V, PP, SLOT)                                                                           \
                     {                                                                                        \
                         const float pm = fmaxf(fmaf(V[2 * (PP)], sc, shb), fmaf(V[2 * (PP) + 1], sc, shb));  \
                         const float r = fmaxf(fmaxf(fmaxf(w0, w1), fmaxf(w2, w3)), fmaxf(pm, 0.f));          \
                         const int P = P0 + (PP);                                                             \
-                        if (ch_ok && P >= P_first && P < P_end) dst[(size_t)P * p.ld_out] = __float2bfloat16_rn(r); \
+                        bf16* ptr = (P >= P_first && P < P_stop) ? dst + (size_t)P * p.ld_out : dummy;       \
+                        *ptr = __float2bfloat16_rn(r);        /* branch-free: invalid pairs hit a scratch slot */ \
                         SLOT = pm;                                                                           \
                     }
 #define EMB_POOL_CHUNK(V)                                                                                    \
@@ -225,8 +232,9 @@ inline bool tc_conv_pool_ok(int L, int pad, int taps, int Cin, int Cout, int Lp,
     return tc_conv_pool_smem(pad, taps, Cin, Cout, 2) <= (size_t)tc_max_smem();
 }
 
-inline int tc_conv_pool(const bf16* x, const bf16* w, int ldw, const float* bias, const float* scale, const float* shift, bf16* out, int B, int L,
-                        int Lp, int Cin, int Cout, int taps, int pad, cudaStream_t st) {
+// scratch: at least 148 * TCP_THREADS bf16 elements nobody else uses during the launch (the unused pre-pooling buffer of the layer)
+inline int tc_conv_pool(const bf16* x, const bf16* w, int ldw, const float* bias, const float* scale, const float* shift, bf16* out, bf16* scratch,
+                        int B, int L, int Lp, int Cin, int Cout, int taps, int pad, cudaStream_t st) {
     int rc = tc_init();
     if (rc) return rc;
     if (first_on_device(3)) {
@@ -256,7 +264,7 @@ inline int tc_conv_pool(const bf16* x, const bf16* w, int ldw, const float* bias
     while (p.a_slots < TCP_MAX_SLOTS && tc_conv_pool_smem(pad, taps, Cin, Cout, p.a_slots + 1) <= (size_t)tc_max_smem()) ++p.a_slots;
     const size_t smem = tc_conv_pool_smem(pad, taps, Cin, Cout, p.a_slots);
     const int grid = std::min(p.total_tiles, tc_num_sms());
-    tc_conv_pool_kernel<<<grid, TCP_THREADS, smem, st>>>(mx, mw, p, bias, scale, shift, out);
+    tc_conv_pool_kernel<<<grid, TCP_THREADS, smem, st>>>(mx, mw, p, bias, scale, shift, out, scratch);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error(-3, "tc_conv_pool launch failed: %s", cudaGetErrorString(err));
     return 0;

@@ -886,8 +886,8 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
                 EMB_CHECK_LAUNCH();
                 LAUNCHED(e);
                 prof_begin(e, 2.0 * B * c.Lc * c.cout * c.k * c.cin, st);
-                int rcp = tc_conv_pool((const bf16*)pr_.a, c.wc, round_up(c.cin, 8), e->params + c.b, c.scale, c.shift, (bf16*)c.a, B, c.Lc, c.Lp, c.cin,
-                                       c.cout, c.k, c.pad, st);
+                int rcp = tc_conv_pool((const bf16*)pr_.a, c.wc, round_up(c.cin, 8), e->params + c.b, c.scale, c.shift, (bf16*)c.a, (bf16*)c.y, B, c.Lc, c.Lp,
+                                       c.cin, c.cout, c.k, c.pad, st);
                 prof_end(e, st);
                 if (rcp) return rcp;
                 LAUNCHED(e);
