@@ -152,9 +152,7 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const bool ch_ok = ch < p.Cout;
         const float sc = ch_ok ? scale[ch] : 0.f;
         const float shb = ch_ok ? fmaf(bias[ch], sc, shift[ch]) : 0.f;
-        // A conditional store compiles to a branch with a reconvergence barrier per pair (measured: the epilogue warps then sit in
-        // branch latency, 17 % tensor-pipe activity); pairs outside the segment store to a per-thread scratch slot instead.
-        bf16* const dummy = scratch + (size_t)blockIdx.x * TCP_THREADS + threadIdx.x;
+        (void)scratch;
         const bool quarter_live = q * 32 < p.Cout;                        // a whole warp beyond Cout only keeps the barrier protocol going
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -171,24 +169,30 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 const int g = pr / p.Lp, j_lo = pr - g * p.Lp;
                 const int n = min(p.Lp - j_lo, pr_hi - pr);               // this segment: pooled rows j_lo .. j_lo + n - 1 of sample g
                 const int P_first = ((g * p.S) >> 1) + j_lo + 4, P_end = P_first + n;      // the pair that completes window j is pair j + 4
-                bf16* dst = out + ((size_t)(sample0 + g) * p.Lp + j_lo) * p.ld_out + ch - (size_t)P_first * p.ld_out;
-                const int P_stop = ch_ok ? P_end : P_first;               // lanes beyond Cout never store for real
+                // k = index of the pooled row the current pair completes (negative while the window is still filling, >= n behind the
+                // segment); `o` walks the output column of this channel in step with k.  One unsigned compare and one pointer add
+                // per pair: the first version recomputed a 64-bit address and two range tests per pair and spent 60 % of its
+                // instructions (and a branch with a reconvergence barrier per store) on that.
+                const int c_first = (2 * (P_first - 4)) & ~15;
+                int k = (c_first >> 1) - P_first;
+                const unsigned n_eff = ch_ok ? (unsigned)n : 0u;
+                const long long ld = p.ld_out;
+                bf16* o = out + ((long long)(sample0 + g) * p.Lp + j_lo + k) * ld + ch;
                 float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
 #define EMB_POOL_PAIR(V, PP, SLOT)                                                                           \
                     {                                                                                        \
                         const float pm = fmaxf(fmaf(V[2 * (PP)], sc, shb), fmaf(V[2 * (PP) + 1], sc, shb));  \
-                        const float r = fmaxf(fmaxf(fmaxf(w0, w1), fmaxf(w2, w3)), fmaxf(pm, 0.f));          \
-                        const int P = P0 + (PP);                                                             \
-                        bf16* ptr = (P >= P_first && P < P_stop) ? dst + (size_t)P * p.ld_out : dummy;       \
-                        *ptr = __float2bfloat16_rn(r);        /* branch-free: invalid pairs hit a scratch slot */ \
+                        const bf16 rv = __float2bfloat16_rn(fmaxf(fmaxf(fmaxf(w0, w1), fmaxf(w2, w3)), fmaxf(pm, 0.f))); \
+                        if ((unsigned)k < n_eff) *o = rv;                                                    \
+                        ++k;                                                                                 \
+                        o += ld;                                                                             \
                         SLOT = pm;                                                                           \
                     }
 #define EMB_POOL_CHUNK(V)                                                                                    \
                     EMB_POOL_PAIR(V, 0, w0) EMB_POOL_PAIR(V, 1, w1) EMB_POOL_PAIR(V, 2, w2) EMB_POOL_PAIR(V, 3, w3) \
                     EMB_POOL_PAIR(V, 4, w0) EMB_POOL_PAIR(V, 5, w1) EMB_POOL_PAIR(V, 6, w2) EMB_POOL_PAIR(V, 7, w3)
-                // up to four 16-column TMEM loads are in flight before the single wait: the load latency is exposed once per 64
-                // columns, not once per 16 (with one wait per chunk the epilogue, not the tensor pipe, set the tile time)
-                for (int c16 = (2 * (P_first - 4)) & ~15; c16 < 2 * P_end; c16 += 64) {
+                // up to four 16-column TMEM loads are in flight before the single wait
+                for (int c16 = c_first; c16 < 2 * P_end; c16 += 64) {
                     float va[16], vb[16], vc[16], vd[16];
                     const bool hb = c16 + 16 < 2 * P_end, hc = c16 + 32 < 2 * P_end, hd = c16 + 48 < 2 * P_end;
                     tc_ld16_nowait(t_addr + (uint32_t)c16, va);
@@ -196,11 +200,10 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     if (hc) tc_ld16_nowait(t_addr + (uint32_t)(c16 + 32), vc);
                     if (hd) tc_ld16_nowait(t_addr + (uint32_t)(c16 + 48), vd);
                     tc_ld_wait();
-                    int P0 = c16 >> 1;
                     EMB_POOL_CHUNK(va)
-                    if (hb) { P0 += 8; EMB_POOL_CHUNK(vb) }
-                    if (hc) { P0 += 8; EMB_POOL_CHUNK(vc) }
-                    if (hd) { P0 += 8; EMB_POOL_CHUNK(vd) }
+                    if (hb) { EMB_POOL_CHUNK(vb) }
+                    if (hc) { EMB_POOL_CHUNK(vc) }
+                    if (hd) { EMB_POOL_CHUNK(vd) }
                 }
 #undef EMB_POOL_CHUNK
 #undef EMB_POOL_PAIR
