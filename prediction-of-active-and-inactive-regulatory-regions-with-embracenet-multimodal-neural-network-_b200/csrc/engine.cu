@@ -25,6 +25,7 @@
 #include "probe.cuh"
 #include "dp_peer.cuh"
 #include "conv_pool_tc.cuh"
+#include "onehot_pool_tc.cuh"
 
 namespace emb {
 
@@ -831,6 +832,17 @@ int cnn_forward_t(EmbEngine* e, const uint8_t* bases, int B, bool training, cons
             const int groups = c.cout / 8;
             if (std::is_same<T, bf16>::value && tc_on(e) && onehot_fwd_tc_ok(c.y, bases, c.cout, c.k, c.ld)) {
                 // one-hot rows expanded in shared memory, all taps through a Toeplitz descriptor, fp32 weights as an exact hi/mid/lo bf16 split
+                if (!training && tuning().infer_fuse == 2 && tuning().infer_fuse_k1 && onehot_pool_tc_ok(bases, c.cout, c.k, c.ld, c.Lp)) {
+                    // inference, transposed form (onehot_pool_tc.cuh): lane = (position block, channel), pooling in registers; y0 is never written
+                    bn_finalize_kernel<<<cdiv(c.cout, 128), 128, 0, st>>>(c.stats, e->params + c.gamma, e->params + c.beta, e->buffers + c.rm,
+                                                                          e->buffers + c.rv, c.scale, c.shift, c.mean, c.rstd, 1.0, c.cout, 0);
+                    EMB_CHECK_LAUNCH();
+                    LAUNCHED(e);
+                    int rcp = onehot_conv_pool_tc(bases, e->params + c.w, e->params + c.b, c.scale, c.shift, (bf16*)c.a, B, c.cout, c.k, c.Lp, st);
+                    if (rcp) return rcp;
+                    LAUNCHED(e);
+                    continue;
+                }
                 if (!training && tuning().infer_fuse == 1) {
                     // inference: eval BatchNorm + ReLU + MaxPool on the staged sample inside the same kernel; y0 is never written
                     bn_finalize_kernel<<<cdiv(c.cout, 128), 128, 0, st>>>(c.stats, e->params + c.gamma, e->params + c.beta, e->buffers + c.rm,

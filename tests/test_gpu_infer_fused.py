@@ -1,5 +1,6 @@
 """Inference forwards that never write the pre-pooling conv output (option `infer_fuse`):
-  2  transposed conv + in-register pooling (csrc/conv_pool_tc.cuh: TMEM lane = channel, columns = positions)
+  2  transposed conv + in-register pooling (csrc/conv_pool_tc.cuh: TMEM lane = channel, columns = positions; the first, one-hot
+     layer through csrc/onehot_pool_tc.cuh: lane = (position block, channel))
   1  BatchNorm(eval) + ReLU + MaxPool1d in the row-major conv GEMM epilogue (EPI_POOL, csrc/gemm_tc.cuh)
   0  unfused (conv writes y, the pooling kernel reads it)
 All share arithmetic and rounding points; 1 must equal 0 bit for bit, 2 up to the accumulation order; all are held to the oracle's
@@ -8,18 +9,35 @@ import numpy as np
 import pytest
 
 from oracle import embracenet_oracle as O
-from tests.golden.cases import ARCH_S, ARCH_M, ARCH_L, make_inputs
+from tests.golden.cases import ARCH_S, ARCH_M, ARCH_L, ARCH_W, espec, make_inputs
 from tests.test_gpu_parity import to_archspec
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('arch,B', [('S', 300), ('M', 130), ('L', 77), ('S', 4096)])
+# first-layer shapes of the search space the three benchmark archs do not have (CNN_pre.py:22: out_channels_l0 in {16, 32, 64}, k in {5, 11, 15}):
+# 16 channels = eight position blocks per sample in onehot_pool_tc.cuh, the last one short; 64 channels with the short tap range
+ARCH_C16 = espec(48, [(64, 0.2)], [(16, 15, 0.2), (64, 11, 0.4)], 256, [(64, 0.0)], 0.5)
+ARCH_C64 = espec(48, [(64, 0.2)], [(64, 5, 0.2), (32, 5, 0.4)], 256, [], 0.4)
+
+
+@pytest.mark.parametrize('arch,B', [('S', 300), ('M', 130), ('L', 77), ('S', 4096), ('W', 150), ('C16', 300), ('C64', 301), ('S', 1)])
 def test_fused_pooling_epilogue_equals_unfused_eval_forward(arch, B):
     import torch
     from embrace_b200 import Engine, _native as N
-    spec = {'S': ARCH_S, 'M': ARCH_M, 'L': ARCH_L}[arch]
+    spec = {'S': ARCH_S, 'M': ARCH_M, 'L': ARCH_L, 'W': ARCH_W, 'C16': ARCH_C16, 'C64': ARCH_C64}[arch]
     P = O.init_params(spec, 4242)
+    # a trained model's BatchNorm: running statistics away from (0, 1), gamma of both signs (a negative gamma reverses the order of
+    # the pre-activation values, which a fused pooling that maximises BEFORE the affine map would get wrong)
+    rs = np.random.RandomState(4245)
+    for k_ in list(P):
+        if k_.endswith('running_mean'):
+            stem = k_[:-len('running_mean')]
+            n = P[k_].shape[0]
+            P[k_] = 0.3 * rs.standard_normal(n)
+            P[stem + 'running_var'] = 0.5 + rs.random_sample(n)
+            P[stem + 'weight'] = (0.5 + rs.random_sample(n)) * np.where(rs.random_sample(n) < 0.3, -1.0, 1.0)
+            P[stem + 'bias'] = 0.2 * rs.standard_normal(n)
     P = {k: (v.astype(np.float32).astype(np.float64) if v.dtype == np.float64 else v) for k, v in P.items()}
     x, bases, _ = make_inputs(spec, B, 4243)
     u = np.random.RandomState(4244).random_sample((B, spec['C']))
