@@ -60,6 +60,7 @@ struct Tuning {
                                  //                         (conv_pool_tc.cuh), 1 = pooling in the row-major GEMM epilogue (four epilogue warps, through
                                  //                         shared memory: measured 2.3x slower than 0 = unfused)
     int infer_fuse_k1 = 1;       // EMB_INFER_FUSE_K1       with infer_fuse = 2: the first (one-hot) conv layer through onehot_pool_tc.cuh as well
+    int pool_parts = 0;          // EMB_POOL_PARTS          pooled inference kernels: epilogue warps sharing one tile (0 = heuristic; 1, 2, 4)
     int tc_min_mflop = 0;        // EMB_TC_MIN_MFLOP        Linear GEMMs below this many MFLOP run on the SIMT kernel (0: tensor cores whenever the shape allows)
     int fork = 1;                // EMB_FORK                independent branches of the step on side streams (parallel graph branches)
 };
@@ -75,7 +76,7 @@ inline const TuningName* tuning_names(int* n) {
         {"EMB_WGRAD_NT", "wgrad_ntile", &Tuning::wgrad_ntile}, {"EMB_WGRAD_FUSE_TAPS", "wgrad_fuse_taps", &Tuning::wgrad_fuse_taps},
         {"EMB_DETERMINISTIC", "deterministic", &Tuning::deterministic}, {"EMB_K2_WIDE", "k2_wide", &Tuning::k2_wide},
         {"EMB_FORK", "fork", &Tuning::fork}, {"EMB_TC_MIN_MFLOP", "tc_min_mflop", &Tuning::tc_min_mflop}, {"EMB_INFER_FUSE", "infer_fuse", &Tuning::infer_fuse},
-        {"EMB_INFER_FUSE_K1", "infer_fuse_k1", &Tuning::infer_fuse_k1},
+        {"EMB_INFER_FUSE_K1", "infer_fuse_k1", &Tuning::infer_fuse_k1}, {"EMB_POOL_PARTS", "pool_parts", &Tuning::pool_parts},
     };
     *n = (int)(sizeof t / sizeof t[0]);
     return t;

@@ -23,9 +23,73 @@
 
 namespace emb {
 
+// The pooling walk of ONE epilogue thread (= one output channel) over TMEM columns [c_first, c_end) of its lane: columns are
+// positions, two per pair; per pair two fma (BatchNorm with the conv bias folded into the shift) and one max; the window of pooled
+// row j = max(pair maxima j .. j + 4, 0) (ReLU once per pooled element, not per position).  The four ring slots are named
+// registers (a chunk is 8 pairs, a multiple of 4): no moves.  `k` is the pooled row the first pair completes (negative while the
+// window is still filling), rows 0 <= k < n_eff are stored at o[k * LD]; `o` arrives pointing at row k.
+// A chunk whose eight rows are all stored takes the FAST form: no predicates, and with the row stride LD a template constant
+// the eight stores are immediate offsets from one pointer (the first version spent two thirds of its instructions on a 64-bit
+// pointer add, a counter and a range test per pair).  Up to four 16-column TMEM loads are in flight before the single wait.
+// experiment (EMB_CONV_DEBUG & 8): non-blocking test_wait spin instead of the potentially suspending try_wait
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+#define POOL_WAIT(bar, parity) do { if (p.dbg & 8) mbar_wait_spin(bar, parity); else mbar_wait(bar, parity); } while (0)
+
+template <int LD>
+__device__ __forceinline__ void pool_walk(uint32_t t_addr, int c_first, int c_end, int k, unsigned n_eff, bf16* o, long long ld_rt,
+                                          float sc, float shb) {
+    const long long ld = LD ? (long long)LD : ld_rt;
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+#define EMB_POOL_VALUE(V, PP)                                                                                 \
+        const float pm = fmaxf(fmaf(V[2 * (PP)], sc, shb), fmaf(V[2 * (PP) + 1], sc, shb));                   \
+        const bf16 rv = __float2bfloat16_rn(fmaxf(fmaxf(fmaxf(w0, w1), fmaxf(w2, w3)), fmaxf(pm, 0.f)));
+#define EMB_POOL_FAST(V, PP, SLOT) { EMB_POOL_VALUE(V, PP) o[(PP) * ld] = rv; SLOT = pm; }
+#define EMB_POOL_SLOW(V, PP, SLOT) { EMB_POOL_VALUE(V, PP) if ((unsigned)(k + (PP)) < n_eff) o[(PP) * ld] = rv; SLOT = pm; }
+#define EMB_POOL_CHUNK(V)                                                                                     \
+        if (k >= 0 && k + 7 < (int)n_eff) {                                                                   \
+            EMB_POOL_FAST(V, 0, w0) EMB_POOL_FAST(V, 1, w1) EMB_POOL_FAST(V, 2, w2) EMB_POOL_FAST(V, 3, w3)   \
+            EMB_POOL_FAST(V, 4, w0) EMB_POOL_FAST(V, 5, w1) EMB_POOL_FAST(V, 6, w2) EMB_POOL_FAST(V, 7, w3)   \
+        } else {                                                                                              \
+            EMB_POOL_SLOW(V, 0, w0) EMB_POOL_SLOW(V, 1, w1) EMB_POOL_SLOW(V, 2, w2) EMB_POOL_SLOW(V, 3, w3)   \
+            EMB_POOL_SLOW(V, 4, w0) EMB_POOL_SLOW(V, 5, w1) EMB_POOL_SLOW(V, 6, w2) EMB_POOL_SLOW(V, 7, w3)   \
+        }                                                                                                     \
+        k += 8;                                                                                               \
+        o += 8 * ld;
+    for (int c16 = c_first; c16 < c_end; c16 += 64) {
+        float va[16], vb[16], vc[16], vd[16];
+        const bool hb = c16 + 16 < c_end, hc = c16 + 32 < c_end, hd = c16 + 48 < c_end;
+        tc_ld16_nowait(t_addr + (uint32_t)c16, va);
+        if (hb) tc_ld16_nowait(t_addr + (uint32_t)(c16 + 16), vb);
+        if (hc) tc_ld16_nowait(t_addr + (uint32_t)(c16 + 32), vc);
+        if (hd) tc_ld16_nowait(t_addr + (uint32_t)(c16 + 48), vd);
+        tc_ld_wait();
+        { EMB_POOL_CHUNK(va) }
+        if (hb) { EMB_POOL_CHUNK(vb) }
+        if (hc) { EMB_POOL_CHUNK(vc) }
+        if (hd) { EMB_POOL_CHUNK(vd) }
+    }
+#undef EMB_POOL_CHUNK
+#undef EMB_POOL_SLOW
+#undef EMB_POOL_FAST
+#undef EMB_POOL_VALUE
+}
+
 struct TcPoolParams {
     int Bn, L, S, bt, Lp;            // samples, conv positions, staged rows per sample (L + pad), samples per tile, pooled length
     int taps, pad, Cout;
+    int parts;                       // epilogue warps per lane quarter that share one tile's pooled rows (1, 2 or 4)
     int n_chunks, k_steps_last;      // K chunks of 64 input channels; UMMA K steps of the last one
     int total_tiles;
     int a_slot_bytes, a_box_bytes;   // activation slot ([rows][64 ch], 128B swizzle) and the bytes one TMA box deposits
@@ -35,11 +99,18 @@ struct TcPoolParams {
                                      // rows behind are the next block's (or the barriers') bytes -- they only feed TMEM lanes >= Cout, which nobody reads
     uint32_t idesc;
     int ld_out;
+    int dbg;                         // EMB_CONV_DEBUG bisection: 1 = epilogue does not pool, 2 = no MMAs
 };
 
-constexpr int TCP_THREADS = 64 + 8 * 32;
+constexpr int TCP_EPI_WARPS = 16;            // sets x parts x 4 lane quarters
+constexpr int TCP_ACCS = 4;                  // TMEM accumulators of 128 columns in flight.  An accumulator hand-over (tcgen05.commit -> epilogue
+                                             // wake-up -> arrive -> MMA-warp wake-up) was measured at ~1 us with nothing else to do (r2 bisection,
+                                             // profiles/r02_infer_bisect.txt): with two accumulators that latency, not the MMAs or the pooling, set the
+                                             // tile period
+constexpr int TCP_THREADS = 64 + TCP_EPI_WARPS * 32;
 constexpr int TCP_MAX_SLOTS = 8;
 
+template <int LD>          // LD = Cout = the output row stride when it is one of the search space's values, 0 = run-time stride
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcPoolParams p,
                     const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift, bf16* __restrict__ out,
@@ -51,9 +122,9 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     uint64_t* a_full = bars;                        // [8]
     uint64_t* a_empty = a_full + TCP_MAX_SLOTS;      // [8]
     uint64_t* w_full = a_empty + TCP_MAX_SLOTS;      // [1]
-    uint64_t* tfull = w_full + 1;        // [2]
-    uint64_t* tempty = tfull + 2;        // [2]
-    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+    uint64_t* tfull = w_full + 1;        // [TCP_ACCS]
+    uint64_t* tempty = tfull + TCP_ACCS; // [TCP_ACCS]
+    uint32_t* tmem_slot = (uint32_t*)(tempty + TCP_ACCS);
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     {   // halo / tail rows of the activation slots must read as zero
@@ -63,12 +134,12 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < TCP_MAX_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+        for (int s = 0; s < TCP_ACCS; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4 * p.parts); }
         mbar_init(w_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCP_ACCS * 128) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -93,7 +164,7 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             uint32_t aphase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x)
                 for (int c = 0; c < p.n_chunks; ++c) {
-                    mbar_wait(&a_empty[as], aphase ^ 1);
+                    POOL_WAIT(&a_empty[as], aphase ^ 1);
                     const uint32_t abar = smem_u32(&a_full[as]);
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(abar), "r"((uint32_t)p.a_box_bytes) : "memory");
                     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -108,15 +179,15 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const uint32_t sa0 = smem_u32(smem), sw0 = smem_u32(smem_w), idesc = p.idesc;
         int as = 0, acc = 0;
         uint32_t aphase = 0, acc_phase = 0;
-        mbar_wait(w_full, 0);
+        POOL_WAIT(w_full, 0);
         tc_fence_after();
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            POOL_WAIT(&tempty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
             uint32_t accumulate = 0;
             for (int c = 0; c < p.n_chunks; ++c) {
-                mbar_wait(&a_full[as], aphase);
+                POOL_WAIT(&a_full[as], aphase);
                 tc_fence_after();
                 const int ks = (c == p.n_chunks - 1) ? p.k_steps_last : 4;
                 if (elect_one_sync()) {
@@ -125,6 +196,7 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll 1
                     for (int t = 0; t < p.taps; ++t) {
                         for (int s2 = 0; s2 < ks; ++s2) {
+                            if (p.dbg & 2) continue;
                             tc_mma_f16(d_tmem, dw + (uint64_t)(2 * s2), dx + (uint64_t)(2 * s2), idesc, accumulate);
                             accumulate = 1;
                         }
@@ -139,86 +211,51 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             }
             if (elect_one_sync()) tc_commit(&tfull[acc]);
             __syncwarp();
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == TCP_ACCS) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ================= epilogue: thread = output channel; its registers walk the positions =================
-        // Per PAIR of positions: two fma (the conv bias is folded into the BatchNorm shift), one max for the pair, then the window =
-        // max(four previous pair maxima, this one, 0): ReLU is applied once per pooled element, not per position.  The four ring
-        // slots are named registers (the pair loop is unrolled by 8, a multiple of 4): no moves.  S is even, so every sample starts
-        // on an even column and pairs never straddle samples; pairs that precede a segment only pass through the ring.
-        const int q = warp & 3, half = (warp - 2) >> 2;
+        // (pool_walk above.)  S is even, so every sample starts on an even column and pairs never straddle samples; pairs that
+        // precede a segment only pass through the ring.
+        const int q = warp & 3, sub = (warp - 2) >> 2;                    // sub 0 .. TCP_EPI_WARPS / 4 - 1
+        const int sets = (TCP_EPI_WARPS / 4) / p.parts;                   // warp sets take tiles round-robin; `parts` warps per quarter share a tile's rows
+        const int set = sub % sets, part = sub / sets;
         const int ch = q * 32 + lane;
         const bool ch_ok = ch < p.Cout;
         const float sc = ch_ok ? scale[ch] : 0.f;
         const float shb = ch_ok ? fmaf(bias[ch], sc, shift[ch]) : 0.f;
         (void)scratch;
         const bool quarter_live = q * 32 < p.Cout;                        // a whole warp beyond Cout only keeps the barrier protocol going
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            mbar_wait(&tfull[acc], acc_phase);
+        for (int t = set, tile = blockIdx.x + set * gridDim.x; tile < p.total_tiles; t += sets, tile += sets * gridDim.x) {
+            const int acc = t % TCP_ACCS;
+            POOL_WAIT(&tfull[acc], (uint32_t)(t / TCP_ACCS) & 1u);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
             const int sample0 = tile * p.bt;
             const int n_samples = min(p.bt, p.Bn - sample0);
             const int PR = n_samples * p.Lp;                              // pooled rows of this tile, flattened (sample, j)
-            const int pr_lo = half == 0 ? 0 : (PR + 1) / 2, pr_hi = half == 0 ? (PR + 1) / 2 : PR;
+            const int per = (PR + p.parts - 1) / p.parts;
+            const int pr_lo = min(PR, part * per), pr_hi = min(PR, pr_lo + per);
             int pr = quarter_live ? pr_lo : pr_hi;
             while (pr < pr_hi) {
                 const int g = pr / p.Lp, j_lo = pr - g * p.Lp;
                 const int n = min(p.Lp - j_lo, pr_hi - pr);               // this segment: pooled rows j_lo .. j_lo + n - 1 of sample g
                 const int P_first = ((g * p.S) >> 1) + j_lo + 4, P_end = P_first + n;      // the pair that completes window j is pair j + 4
-                // k = index of the pooled row the current pair completes (negative while the window is still filling, >= n behind the
-                // segment); `o` walks the output column of this channel in step with k.  One unsigned compare and one pointer add
-                // per pair: the first version recomputed a 64-bit address and two range tests per pair and spent 60 % of its
-                // instructions (and a branch with a reconvergence barrier per store) on that.
                 const int c_first = (2 * (P_first - 4)) & ~15;
-                int k = (c_first >> 1) - P_first;
-                const unsigned n_eff = ch_ok ? (unsigned)n : 0u;
-                const long long ld = p.ld_out;
-                bf16* o = out + ((long long)(sample0 + g) * p.Lp + j_lo + k) * ld + ch;
-                float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-#define EMB_POOL_PAIR(V, PP, SLOT)                                                                           \
-                    {                                                                                        \
-                        const float pm = fmaxf(fmaf(V[2 * (PP)], sc, shb), fmaf(V[2 * (PP) + 1], sc, shb));  \
-                        const bf16 rv = __float2bfloat16_rn(fmaxf(fmaxf(fmaxf(w0, w1), fmaxf(w2, w3)), fmaxf(pm, 0.f))); \
-                        if ((unsigned)k < n_eff) *o = rv;                                                    \
-                        ++k;                                                                                 \
-                        o += ld;                                                                             \
-                        SLOT = pm;                                                                           \
-                    }
-#define EMB_POOL_CHUNK(V)                                                                                    \
-                    EMB_POOL_PAIR(V, 0, w0) EMB_POOL_PAIR(V, 1, w1) EMB_POOL_PAIR(V, 2, w2) EMB_POOL_PAIR(V, 3, w3) \
-                    EMB_POOL_PAIR(V, 4, w0) EMB_POOL_PAIR(V, 5, w1) EMB_POOL_PAIR(V, 6, w2) EMB_POOL_PAIR(V, 7, w3)
-                // up to four 16-column TMEM loads are in flight before the single wait
-                for (int c16 = c_first; c16 < 2 * P_end; c16 += 64) {
-                    float va[16], vb[16], vc[16], vd[16];
-                    const bool hb = c16 + 16 < 2 * P_end, hc = c16 + 32 < 2 * P_end, hd = c16 + 48 < 2 * P_end;
-                    tc_ld16_nowait(t_addr + (uint32_t)c16, va);
-                    if (hb) tc_ld16_nowait(t_addr + (uint32_t)(c16 + 16), vb);
-                    if (hc) tc_ld16_nowait(t_addr + (uint32_t)(c16 + 32), vc);
-                    if (hd) tc_ld16_nowait(t_addr + (uint32_t)(c16 + 48), vd);
-                    tc_ld_wait();
-                    EMB_POOL_CHUNK(va)
-                    if (hb) { EMB_POOL_CHUNK(vb) }
-                    if (hc) { EMB_POOL_CHUNK(vc) }
-                    if (hd) { EMB_POOL_CHUNK(vd) }
-                }
-#undef EMB_POOL_CHUNK
-#undef EMB_POOL_PAIR
+                const int k = (c_first >> 1) - P_first;                   // the pooled row the first pair completes (negative: still filling)
+                bf16* o = out + ((long long)(sample0 + g) * p.Lp + j_lo + k) * (long long)p.ld_out + ch;
+                if (!(p.dbg & 1)) pool_walk<LD>(t_addr, c_first, 2 * P_end, k, ch_ok ? (unsigned)n : 0u, o, p.ld_out, sc, shb);
                 pr += n;
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCP_ACCS * 128) : "memory");
     }
 }
 
@@ -240,9 +277,13 @@ inline int tc_conv_pool(const bf16* x, const bf16* w, int ldw, const float* bias
                         int B, int L, int Lp, int Cin, int Cout, int taps, int pad, cudaStream_t st) {
     int rc = tc_init();
     if (rc) return rc;
+    using Kern = void (*)(const CUtensorMap, const CUtensorMap, const TcPoolParams, const float*, const float*, const float*, bf16*, bf16*);
+    static const Kern kerns[5] = {tc_conv_pool_kernel<0>, tc_conv_pool_kernel<32>, tc_conv_pool_kernel<64>, tc_conv_pool_kernel<96>, tc_conv_pool_kernel<128>};
     if (first_on_device(3)) {
-        cudaError_t err = cudaFuncSetAttribute(tc_conv_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_max_smem());
-        if (err != cudaSuccess) return set_error(-3, "cudaFuncSetAttribute(tc_conv_pool_kernel): %s", cudaGetErrorString(err));
+        for (Kern kf : kerns) {
+            cudaError_t err = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_max_smem());
+            if (err != cudaSuccess) return set_error(-3, "cudaFuncSetAttribute(tc_conv_pool_kernel): %s", cudaGetErrorString(err));
+        }
     }
     TcPoolParams p = {};
     p.Bn = B; p.L = L; p.S = round_up(L + pad, 2);          // even: every sample starts on an even TMEM column
@@ -256,6 +297,9 @@ inline int tc_conv_pool(const bf16* x, const bf16* w, int ldw, const float* bias
     if (p.bt * p.S > a_rows) return set_error(-5, "tc_conv_pool: tile rows exceed the activation slot");
     p.idesc = make_idesc(0, 0, 128);
     p.ld_out = Cout;
+    p.dbg = tuning().conv_debug;
+    p.parts = 1;                                 // measured (profiles/r02_infer_parts.sh): whole tiles per warp beat shared ones
+    if (tuning().pool_parts == 1 || tuning().pool_parts == 2 || tuning().pool_parts == 4) p.parts = tuning().pool_parts;
     CUtensorMap mx, mw;
     rc = make_map(&mx, x, Cin, L, B, Cin, (int64_t)L * Cin, 64, p.S, p.bt);
     if (rc) return rc;
@@ -267,7 +311,8 @@ inline int tc_conv_pool(const bf16* x, const bf16* w, int ldw, const float* bias
     while (p.a_slots < TCP_MAX_SLOTS && tc_conv_pool_smem(pad, taps, Cin, Cout, p.a_slots + 1) <= (size_t)tc_max_smem()) ++p.a_slots;
     const size_t smem = tc_conv_pool_smem(pad, taps, Cin, Cout, p.a_slots);
     const int grid = std::min(p.total_tiles, tc_num_sms());
-    tc_conv_pool_kernel<<<grid, TCP_THREADS, smem, st>>>(mx, mw, p, bias, scale, shift, out, scratch);
+    const Kern kf = kerns[(Cout % 32) == 0 && Cout <= 128 ? Cout / 32 : 0];     // the row stride as a compile-time constant where it is a usual one
+    kf<<<grid, TCP_THREADS, smem, st>>>(mx, mw, p, bias, scale, shift, out, scratch);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error(-3, "tc_conv_pool launch failed: %s", cudaGetErrorString(err));
     return 0;

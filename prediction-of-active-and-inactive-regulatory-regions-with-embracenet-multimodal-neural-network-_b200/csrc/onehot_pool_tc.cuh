@@ -14,7 +14,8 @@
 //               window that starts (128 - C1) - q C1 rows down has the weights exactly in rows [q C1, (q + 1) C1) and zeros
 //               elsewhere, so every block uses the SAME shared-memory weights through a shifted descriptor;
 //   B (N x K) = the Toeplitz view of the sample's one-hot rows (onehot_wgrad_tc.cuh), started 2 q Pq rows down.
-//   nb x (Kw / 16) tcgen05.mma (128 x N x 16) per sample; Kw = 8 slots x 8 (k <= 7) or 16 (k <= 15) tap slots.
+//   nb x ceil(k / 2) tcgen05.mma (128 x N x 16) per sample (two tap slots of 8 K elements each); the weight array holds
+//   Kw / 8 = 8 (k <= 7) or 16 (k <= 15) tap slots.
 //
 // The fp32 master weight enters as a two-term bf16 split {hi, mid} against the one-hot stored twice per row (2^-17 relative;
 // the training forward needs the exact three-term split because one bf16 ulp re-routes max-pool gradients; inference does not).
@@ -22,37 +23,46 @@
 // of the pooled value.
 //
 //   warp 0 producer (base codes, bulk copy)   warp 1 MMA issuer   warps 2-3 generators (codes -> one-hot rows)
-//   warps 4-19 epilogue: TMEM lane quarter = warp % 4; the four warp sets take whole samples round-robin (one TMEM accumulator
-//   each), or two sets share a sample by halves of the pooled rows when the accumulator is wider than 128 columns (C1 = 64)
+//   warps 4-19 epilogue: TMEM lane quarter = warp % 4; `parts` warps per quarter share a sample's pooled rows and 4 / parts warp
+//   sets take samples round-robin; 512 / N accumulators are in flight (the MMA -> epilogue -> MMA hand-over costs ~1 us)
 #pragma once
 #include "onehot_wgrad_tc.cuh"
+#include "conv_pool_tc.cuh"
 
 namespace emb {
 
-constexpr int OHP_STAGES = 4;
+constexpr int OHP_STAGES = 6;                               // one-hot row arrays in flight (freed by the MMAs that read them)
+constexpr int OHP_CODES = 16;                               // base-code buffers in flight (freed by the generators): the 256-byte loads are pure
+                                                            // DRAM latency, and with one buffer per row array the MMA warp starved (r2 ncu: 63 %
+                                                            // of the kernel's stall samples were epilogue warps waiting for an accumulator)
 constexpr int OHP_ROWS = 288;                               // one-hot rows per stage: 2 (nb - 1) Pq + N + 16 <= 288 for every C1
-constexpr int OHP_STAGE = OHP_ROWS * 16 + SEQ_LEN;          // + the 256 base codes
+constexpr int OHP_STAGE = OHP_ROWS * 16;
+constexpr int OHP_DATA_BYTES = OHP_STAGES * OHP_STAGE + OHP_CODES * SEQ_LEN;
 constexpr int OHP_EPI_WARPS = 16;
 constexpr int OHP_THREADS = 128 + OHP_EPI_WARPS * 32;
-constexpr int OHP_MAX_BUF = 4;
+constexpr int OHP_MAX_BUF = 8;
 
 struct OhpParams {
     int B, C1, k, Lp;
     int nb, Pq, N, Kw;               // position blocks, pooled rows per block, MMA N (positions per block, padded), K per block
-    int NS, nbuf;                    // TMEM column stride of one accumulator, accumulators in flight
+    int NS, nbuf, parts;             // TMEM column stride of one accumulator, accumulators in flight, epilogue warps per quarter sharing a sample
     int w_bytes, sbo;                // tall weight array: bytes (rounded), bytes between 8-row groups
     uint32_t idesc;
+    int dbg;                         // EMB_CONV_DEBUG bisection: 1 = epilogue does not pool, 2 = no MMAs, 4 = one MMA per block
 };
 
+template <int C1T>         // C1T = C1 = the output row stride (16 / 32 / 64)
 __global__ void __launch_bounds__(OHP_THREADS, 1)
 onehot_conv_pool_tc_kernel(const uint8_t* __restrict__ bases, const float* __restrict__ w, const float* __restrict__ bias,
                            const float* __restrict__ scale, const float* __restrict__ shift, bf16* __restrict__ out, const OhpParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* wsm = smem;                                            // [256 - C1 rows][Kw] bf16, un-swizzled K-major core matrices
-    uint8_t* stages = wsm + p.w_bytes;                              // [stage]{rows[288][16 B], codes[256]}
-    uint64_t* codes_bar = (uint64_t*)(stages + OHP_STAGES * OHP_STAGE);
-    uint64_t* rows_full = codes_bar + OHP_STAGES;
+    uint8_t* stages = wsm + p.w_bytes;                              // [stage] rows[288][16 B]
+    uint8_t* codes_sm = stages + OHP_STAGES * OHP_STAGE;            // [code buffer][256]
+    uint64_t* codes_full = (uint64_t*)(codes_sm + OHP_CODES * SEQ_LEN);
+    uint64_t* codes_empty = codes_full + OHP_CODES;
+    uint64_t* rows_full = codes_empty + OHP_CODES;
     uint64_t* rows_empty = rows_full + OHP_STAGES;
     uint64_t* tfull = rows_empty + OHP_STAGES;
     uint64_t* tempty = tfull + OHP_MAX_BUF;
@@ -60,10 +70,10 @@ onehot_conv_pool_tc_kernel(const uint8_t* __restrict__ bases, const float* __res
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int pad = (p.k - 1) / 2;
     const int n_mine = (int)blockIdx.x < p.B ? (p.B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int sets = p.nbuf, parts = (OHP_EPI_WARPS / 4) / sets;    // epilogue warp sets per sample round and row parts per sample
+    const int parts = p.parts, sets = (OHP_EPI_WARPS / 4) / parts;  // row parts per sample; warp sets take samples round-robin
 
     // zero rows of the weight array, the halo rows and the unused tap slots read as zero for the whole kernel
-    for (int i = threadIdx.x; i < (p.w_bytes + OHP_STAGES * OHP_STAGE) / 16; i += OHP_THREADS) ((uint4*)smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < (p.w_bytes + OHP_DATA_BYTES) / 16; i += OHP_THREADS) ((uint4*)smem)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     {
         const int slots = p.Kw >> 3;                                // tap slots of 8 K elements: {onehot hi-part, onehot mid-part}
@@ -80,7 +90,8 @@ onehot_conv_pool_tc_kernel(const uint8_t* __restrict__ bases, const float* __res
     }
     fence_async_smem();
     if (threadIdx.x == 0) {
-        for (int s = 0; s < OHP_STAGES; ++s) { mbar_init(&codes_bar[s], 1); mbar_init(&rows_full[s], 2); mbar_init(&rows_empty[s], 1); }
+        for (int s = 0; s < OHP_STAGES; ++s) { mbar_init(&rows_full[s], 2); mbar_init(&rows_empty[s], 1); }
+        for (int s = 0; s < OHP_CODES; ++s) { mbar_init(&codes_full[s], 1); mbar_init(&codes_empty[s], 2); }
         for (int a = 0; a < OHP_MAX_BUF; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4 * parts); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -94,27 +105,27 @@ onehot_conv_pool_tc_kernel(const uint8_t* __restrict__ bases, const float* __res
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= producer: the sample's 256 base codes =================
+        // ================= producer: the samples' 256 base codes, up to OHP_CODES samples ahead =================
         if (lane == 0) {
-            int stage = 0;
+            int cs = 0;
             uint32_t phase = 0;
             for (int i = 0; i < n_mine; ++i) {
                 const int b = blockIdx.x + i * gridDim.x;
-                mbar_wait(&rows_empty[stage], phase ^ 1);
-                mbar_expect_tx(&codes_bar[stage], SEQ_LEN);
-                bulk_load(stages + stage * OHP_STAGE + OHP_ROWS * 16, bases + (size_t)b * SEQ_LEN, SEQ_LEN, &codes_bar[stage]);
-                if (++stage == OHP_STAGES) { stage = 0; phase ^= 1; }
+                POOL_WAIT(&codes_empty[cs], phase ^ 1);
+                mbar_expect_tx(&codes_full[cs], SEQ_LEN);
+                bulk_load(codes_sm + cs * SEQ_LEN, bases + (size_t)b * SEQ_LEN, SEQ_LEN, &codes_full[cs]);
+                if (++cs == OHP_CODES) { cs = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         const uint64_t dw_base = umma_desc_noswizzle(0, 128, (uint32_t)p.sbo), dx_base = umma_desc_noswizzle(0, 16, 128);
-        const int ksteps = p.Kw >> 4;
+        const int ksteps = (p.k + 1) >> 1;                  // 16 K elements = two tap slots; slots >= k hold zero weights and are skipped
         int stage = 0, buf = 0;
         uint32_t phase = 0, use = 0;
         for (int i = 0; i < n_mine; ++i) {
-            mbar_wait(&rows_full[stage], phase);
-            mbar_wait(&tempty[buf], (use & 1u) ^ 1u);
+            POOL_WAIT(&rows_full[stage], phase);
+            POOL_WAIT(&tempty[buf], (use & 1u) ^ 1u);
             tc_fence_after();
             if (elect_one_sync()) {
                 const uint32_t rows = smem_u32(stages + stage * OHP_STAGE);
@@ -123,7 +134,8 @@ onehot_conv_pool_tc_kernel(const uint8_t* __restrict__ bases, const float* __res
                     const uint32_t wa = smem_u32(wsm) + (uint32_t)((128 - p.C1 - q * p.C1) >> 3) * (uint32_t)p.sbo;
                     const uint32_t xa = rows + (uint32_t)(2 * q * p.Pq) * 16u;
                     const uint64_t dw = dw_base | (uint64_t)((wa & 0x3FFFFu) >> 4), dx = dx_base | (uint64_t)((xa & 0x3FFFFu) >> 4);
-                    for (int s = 0; s < ksteps; ++s)                // 16 K elements = two tap slots: weights + 2 K blocks (256 B), rows + 2 (32 B)
+                    if (p.dbg & 2) continue;
+                    for (int s = 0; s < ((p.dbg & 4) ? 1 : ksteps); ++s)                // 16 K elements = two tap slots: weights + 2 K blocks (256 B), rows + 2 (32 B)
                         tc_mma_f16(d_tmem, dw + (uint64_t)(s * 16), dx + (uint64_t)(s * 2), p.idesc, (q | s) ? 1u : 0u);
                 }
                 tc_commit(&tfull[buf]);
@@ -135,14 +147,14 @@ onehot_conv_pool_tc_kernel(const uint8_t* __restrict__ bases, const float* __res
         }
     } else if (warp < 4) {
         // ================= generators: 256 code bytes -> 256 rows {onehot, onehot} of 16 bytes =================
-        int stage = 0;
-        uint32_t phase = 0;
+        int stage = 0, cs = 0;
+        uint32_t phase = 0, cphase = 0;
         const int t = threadIdx.x - 64;                   // 0..63
         for (int i = 0; i < n_mine; ++i) {
-            mbar_wait(&codes_bar[stage], phase);
-            uint8_t* st = stages + stage * OHP_STAGE;
-            const uint8_t* codes = st + OHP_ROWS * 16;
-            uint4* rows = (uint4*)st + pad;
+            POOL_WAIT(&codes_full[cs], cphase);
+            POOL_WAIT(&rows_empty[stage], phase ^ 1);      // the MMAs that read this row array OHP_STAGES samples ago are complete
+            const uint8_t* codes = codes_sm + cs * SEQ_LEN;
+            uint4* rows = (uint4*)(stages + stage * OHP_STAGE) + pad;
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
                 const uint32_t c = codes[t + h * 64];
@@ -152,13 +164,13 @@ onehot_conv_pool_tc_kernel(const uint8_t* __restrict__ bases, const float* __res
             }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&rows_full[stage]);
+            if (lane == 0) { mbar_arrive(&rows_full[stage]); mbar_arrive(&codes_empty[cs]); }
             if (++stage == OHP_STAGES) { stage = 0; phase ^= 1; }
+            if (++cs == OHP_CODES) { cs = 0; cphase ^= 1; }
         }
     } else {
         // ================= epilogue: thread = (position block, channel); its registers walk the block's positions =================
-        // The pair loop is the one of conv_pool_tc.cuh: two fma per pair of positions, the window = max(four previous pair maxima,
-        // this one, 0), four named ring registers, one unsigned compare and one pointer add per pooled row.
+        // The pair loop is pool_walk of conv_pool_tc.cuh.
         const int e = warp - 4, wq = e & 3, sub = e >> 2;
         const int set = sub % sets, part = sub / sets;
         const int li = wq * 32 + lane, qb = li / p.C1, ch = li - qb * p.C1;
@@ -172,45 +184,17 @@ onehot_conv_pool_tc_kernel(const uint8_t* __restrict__ bases, const float* __res
         const int c_first = (2 * lo) & ~15;
         const int k_first = (c_first >> 1) - P_first;
         const long long ld = p.C1;
-        const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(set * p.NS);
-        uint32_t use = 0;
-        for (int i = set; i < n_mine; i += sets, ++use) {
+        for (int i = set; i < n_mine; i += sets) {
             const int b = blockIdx.x + i * gridDim.x;
-            mbar_wait(&tfull[set], use & 1u);
+            const int buf = i % p.nbuf;
+            POOL_WAIT(&tfull[buf], (uint32_t)(i / p.nbuf) & 1u);
             tc_fence_after();
-            int k = k_first;
-            bf16* o = out + ((long long)b * p.Lp + qb * p.Pq + lo + k) * ld + ch;
-            float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-#define EMB_POOL_PAIR(V, PP, SLOT)                                                                           \
-            {                                                                                                \
-                const float pm = fmaxf(fmaf(V[2 * (PP)], sc, shb), fmaf(V[2 * (PP) + 1], sc, shb));          \
-                const bf16 rv = __float2bfloat16_rn(fmaxf(fmaxf(fmaxf(w0, w1), fmaxf(w2, w3)), fmaxf(pm, 0.f))); \
-                if ((unsigned)k < n_eff) *o = rv;                                                            \
-                ++k;                                                                                         \
-                o += ld;                                                                                     \
-                SLOT = pm;                                                                                   \
-            }
-#define EMB_POOL_CHUNK(V)                                                                                    \
-            EMB_POOL_PAIR(V, 0, w0) EMB_POOL_PAIR(V, 1, w1) EMB_POOL_PAIR(V, 2, w2) EMB_POOL_PAIR(V, 3, w3)  \
-            EMB_POOL_PAIR(V, 4, w0) EMB_POOL_PAIR(V, 5, w1) EMB_POOL_PAIR(V, 6, w2) EMB_POOL_PAIR(V, 7, w3)
-            for (int c16 = c_first; c16 < 2 * P_end; c16 += 64) {
-                float va[16], vb[16], vc[16], vd[16];
-                const bool hb = c16 + 16 < 2 * P_end, hc = c16 + 32 < 2 * P_end, hd = c16 + 48 < 2 * P_end;
-                tc_ld16_nowait(t_addr + (uint32_t)c16, va);
-                if (hb) tc_ld16_nowait(t_addr + (uint32_t)(c16 + 16), vb);
-                if (hc) tc_ld16_nowait(t_addr + (uint32_t)(c16 + 32), vc);
-                if (hd) tc_ld16_nowait(t_addr + (uint32_t)(c16 + 48), vd);
-                tc_ld_wait();
-                EMB_POOL_CHUNK(va)
-                if (hb) { EMB_POOL_CHUNK(vb) }
-                if (hc) { EMB_POOL_CHUNK(vc) }
-                if (hd) { EMB_POOL_CHUNK(vd) }
-            }
-#undef EMB_POOL_CHUNK
-#undef EMB_POOL_PAIR
+            const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * p.NS);
+            bf16* o = out + ((long long)b * p.Lp + qb * p.Pq + lo + k_first) * ld + ch;
+            if (!(p.dbg & 1)) pool_walk<C1T>(t_addr, c_first, 2 * P_end, k_first, n_eff, o, ld, sc, shb);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[set]);
+            if (lane == 0) mbar_arrive(&tempty[buf]);
         }
     }
     tc_fence_before();
@@ -228,11 +212,14 @@ inline OhpParams onehot_pool_params(int B, int C1, int k, int Lp) {
     p.Pq = cdiv(Lp, p.nb);
     p.N = round_up(2 * p.Pq + 8, 16);
     p.Kw = k <= 7 ? 64 : 128;
-    p.NS = p.N <= 64 ? 64 : p.N <= 128 ? 128 : 256;
+    p.NS = p.N;                                  // accumulators packed back to back: the hand-over latency (~1 us) wants as many in flight as fit
     p.nbuf = std::min(OHP_MAX_BUF, 512 / p.NS);
+    p.parts = 1;                                 // measured (profiles/r02_infer_parts.sh): whole samples per warp beat shared ones
+    if (tuning().pool_parts == 1 || tuning().pool_parts == 2 || tuning().pool_parts == 4) p.parts = tuning().pool_parts;
     p.sbo = p.Kw * 16;
     p.w_bytes = round_up(((256 - C1) / 8) * p.sbo, 1024);
     p.idesc = make_idesc(0, 0, p.N);
+    p.dbg = tuning().conv_debug;
     return p;
 }
 
@@ -249,14 +236,18 @@ inline int onehot_conv_pool_tc(const uint8_t* bases, const float* w, const float
     int rc = tc_init();
     if (rc) return rc;
     const OhpParams p = onehot_pool_params(B, C1, k, Lp);
-    const size_t smem = 1024 + (size_t)p.w_bytes + OHP_STAGES * OHP_STAGE + 256;
+    const size_t smem = 1024 + (size_t)p.w_bytes + OHP_DATA_BYTES + 512;
+    using Kern = void (*)(const uint8_t*, const float*, const float*, const float*, const float*, bf16*, const OhpParams);
+    static const Kern kerns[3] = {onehot_conv_pool_tc_kernel<16>, onehot_conv_pool_tc_kernel<32>, onehot_conv_pool_tc_kernel<64>};
     if (first_on_device(4)) {
-        cudaError_t e = cudaFuncSetAttribute(onehot_conv_pool_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_max_smem());
-        if (e != cudaSuccess) return set_error(-3, "cudaFuncSetAttribute(onehot_conv_pool_tc_kernel): %s", cudaGetErrorString(e));
+        for (Kern kf : kerns) {
+            cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_max_smem());
+            if (e != cudaSuccess) return set_error(-3, "cudaFuncSetAttribute(onehot_conv_pool_tc_kernel): %s", cudaGetErrorString(e));
+        }
     }
     if (smem > (size_t)tc_max_smem()) return set_error(-5, "onehot_conv_pool_tc: shared memory");
     const int grid = std::min(B, tc_num_sms());
-    onehot_conv_pool_tc_kernel<<<grid, OHP_THREADS, smem, st>>>(bases, w, bias, scale, shift, out, p);
+    kerns[C1 == 16 ? 0 : C1 == 32 ? 1 : 2]<<<grid, OHP_THREADS, smem, st>>>(bases, w, bias, scale, shift, out, p);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error(-3, "onehot_conv_pool_tc launch failed: %s", cudaGetErrorString(err));
     return 0;
