@@ -99,7 +99,7 @@ struct TcPoolParams {
                                      // rows behind are the next block's (or the barriers') bytes -- they only feed TMEM lanes >= Cout, which nobody reads
     uint32_t idesc;
     int ld_out;
-    int dbg;                         // EMB_CONV_DEBUG bisection: 1 = epilogue does not pool, 2 = no MMAs
+    int dbg;                         // EMB_CONV_DEBUG bisection: 1 = epilogue does not pool, 8 = test_wait spin instead of try_wait
 };
 
 constexpr int TCP_EPI_WARPS = 16;            // sets x parts x 4 lane quarters
@@ -110,7 +110,12 @@ constexpr int TCP_ACCS = 4;                  // TMEM accumulators of 128 columns
 constexpr int TCP_THREADS = 64 + TCP_EPI_WARPS * 32;
 constexpr int TCP_MAX_SLOTS = 8;
 
-template <int LD>          // LD = Cout = the output row stride when it is one of the search space's values, 0 = run-time stride
+// LD = Cout (the output row stride and the rows of one weight block) and TAPS = the kernel size when they are the search space's
+// values (CNN_pre.py:22-27), 0 = run-time.  The specialisation is for the MMA-issuing thread as much as for the epilogue: r2's
+// bisection (profiles/r02_infer_bisect.txt) showed the kernel taking 250 us with the MMAs AND the pooling switched off -- the
+// time of the one elected thread walking its tap loop (constant-bank reloads, descriptor multiplies) at single-thread latency.
+// With both constants the loop unrolls into descriptor adds with immediates, three instructions per tcgen05.mma.
+template <int LD, int TAPS>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcPoolParams p,
                     const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift, bf16* __restrict__ out,
@@ -193,15 +198,24 @@ tc_conv_pool_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 if (elect_one_sync()) {
                     uint64_t dx = ((uint64_t)d_hi << 32) | (d_lo16 | (((sa0 + (uint32_t)(as * p.a_slot_bytes)) & 0x3FFFFu) >> 4));
                     uint64_t dw = ((uint64_t)d_hi << 32) | (d_lo16 | (((sw0 + (uint32_t)(c * p.taps) * (uint32_t)p.w_slot_bytes) & 0x3FFFFu) >> 4));
+                    if (TAPS) {
+#pragma unroll
+                        for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+                            for (int s2 = 0; s2 < 4; ++s2)
+                                if (s2 < ks)
+                                    tc_mma_f16(d_tmem, dw + (uint64_t)(t * (LD * 8) + 2 * s2), dx + (uint64_t)(8 * t + 2 * s2), idesc,
+                                               (t | s2) ? 1u : accumulate);
+                    } else {
 #pragma unroll 1
-                    for (int t = 0; t < p.taps; ++t) {
-                        for (int s2 = 0; s2 < ks; ++s2) {
-                            if (p.dbg & 2) continue;
-                            tc_mma_f16(d_tmem, dw + (uint64_t)(2 * s2), dx + (uint64_t)(2 * s2), idesc, accumulate);
-                            accumulate = 1;
+                        for (int t = 0; t < p.taps; ++t) {
+                            for (int s2 = 0; s2 < ks; ++s2) {
+                                tc_mma_f16(d_tmem, dw + (uint64_t)(2 * s2), dx + (uint64_t)(2 * s2), idesc, accumulate);
+                                accumulate = 1;
+                            }
+                            dx += 8;                               // next tap: the activation tile one row (128 bytes) further
+                            dw += (uint64_t)(p.w_slot_bytes >> 4);
                         }
-                        dx += 8;                               // next tap: the activation tile one row (128 bytes) further
-                        dw += (uint64_t)(p.w_slot_bytes >> 4);
                     }
                     tc_commit(&a_empty[as]);
                 }
@@ -278,10 +292,13 @@ inline int tc_conv_pool(const bf16* x, const bf16* w, int ldw, const float* bias
     int rc = tc_init();
     if (rc) return rc;
     using Kern = void (*)(const CUtensorMap, const CUtensorMap, const TcPoolParams, const float*, const float*, const float*, bf16*, bf16*);
-    static const Kern kerns[5] = {tc_conv_pool_kernel<0>, tc_conv_pool_kernel<32>, tc_conv_pool_kernel<64>, tc_conv_pool_kernel<96>, tc_conv_pool_kernel<128>};
+#define EMB_TCP_ROW(LD) {tc_conv_pool_kernel<LD, 5>, tc_conv_pool_kernel<LD, 11>, tc_conv_pool_kernel<LD, 15>}
+    static const Kern kerns[4][3] = {EMB_TCP_ROW(32), EMB_TCP_ROW(64), EMB_TCP_ROW(96), EMB_TCP_ROW(128)};
+#undef EMB_TCP_ROW
+    static const Kern generic = tc_conv_pool_kernel<0, 0>;
     if (first_on_device(3)) {
-        for (Kern kf : kerns) {
-            cudaError_t err = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_max_smem());
+        for (int i = 0; i <= 12; ++i) {
+            cudaError_t err = cudaFuncSetAttribute(i < 12 ? kerns[i / 3][i % 3] : generic, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_max_smem());
             if (err != cudaSuccess) return set_error(-3, "cudaFuncSetAttribute(tc_conv_pool_kernel): %s", cudaGetErrorString(err));
         }
     }
@@ -311,7 +328,8 @@ inline int tc_conv_pool(const bf16* x, const bf16* w, int ldw, const float* bias
     while (p.a_slots < TCP_MAX_SLOTS && tc_conv_pool_smem(pad, taps, Cin, Cout, p.a_slots + 1) <= (size_t)tc_max_smem()) ++p.a_slots;
     const size_t smem = tc_conv_pool_smem(pad, taps, Cin, Cout, p.a_slots);
     const int grid = std::min(p.total_tiles, tc_num_sms());
-    const Kern kf = kerns[(Cout % 32) == 0 && Cout <= 128 ? Cout / 32 : 0];     // the row stride as a compile-time constant where it is a usual one
+    const int ti = taps == 5 ? 0 : taps == 11 ? 1 : taps == 15 ? 2 : -1;
+    const Kern kf = ((Cout % 32) == 0 && Cout <= 128 && ti >= 0) ? kerns[Cout / 32 - 1][ti] : generic;
     kf<<<grid, TCP_THREADS, smem, st>>>(mx, mw, p, bias, scale, shift, out, scratch);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error(-3, "tc_conv_pool launch failed: %s", cudaGetErrorString(err));

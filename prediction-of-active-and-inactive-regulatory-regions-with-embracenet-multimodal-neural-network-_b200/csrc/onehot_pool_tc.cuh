@@ -48,10 +48,12 @@ struct OhpParams {
     int NS, nbuf, parts;             // TMEM column stride of one accumulator, accumulators in flight, epilogue warps per quarter sharing a sample
     int w_bytes, sbo;                // tall weight array: bytes (rounded), bytes between 8-row groups
     uint32_t idesc;
-    int dbg;                         // EMB_CONV_DEBUG bisection: 1 = epilogue does not pool, 2 = no MMAs, 4 = one MMA per block
+    int dbg;                         // EMB_CONV_DEBUG bisection: 1 = epilogue does not pool, 8 = test_wait spin instead of try_wait
 };
 
-template <int C1T>         // C1T = C1 = the output row stride (16 / 32 / 64)
+// C1T = C1 = the output row stride (16 / 32 / 64); KT = the kernel size when it is 5 / 11 / 15, 0 = run-time (the MMA-issuing thread's
+// loop then unrolls into descriptor adds with immediates: see conv_pool_tc.cuh)
+template <int C1T, int KT>
 __global__ void __launch_bounds__(OHP_THREADS, 1)
 onehot_conv_pool_tc_kernel(const uint8_t* __restrict__ bases, const float* __restrict__ w, const float* __restrict__ bias,
                            const float* __restrict__ scale, const float* __restrict__ shift, bf16* __restrict__ out, const OhpParams p) {
@@ -130,13 +132,24 @@ onehot_conv_pool_tc_kernel(const uint8_t* __restrict__ bases, const float* __res
             if (elect_one_sync()) {
                 const uint32_t rows = smem_u32(stages + stage * OHP_STAGE);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.NS);
-                for (int q = 0; q < p.nb; ++q) {
-                    const uint32_t wa = smem_u32(wsm) + (uint32_t)((128 - p.C1 - q * p.C1) >> 3) * (uint32_t)p.sbo;
-                    const uint32_t xa = rows + (uint32_t)(2 * q * p.Pq) * 16u;
-                    const uint64_t dw = dw_base | (uint64_t)((wa & 0x3FFFFu) >> 4), dx = dx_base | (uint64_t)((xa & 0x3FFFFu) >> 4);
-                    if (p.dbg & 2) continue;
-                    for (int s = 0; s < ((p.dbg & 4) ? 1 : ksteps); ++s)                // 16 K elements = two tap slots: weights + 2 K blocks (256 B), rows + 2 (32 B)
-                        tc_mma_f16(d_tmem, dw + (uint64_t)(s * 16), dx + (uint64_t)(s * 2), p.idesc, (q | s) ? 1u : 0u);
+                if (KT) {
+                    constexpr int NB = 128 / C1T, PQ = ((SEQ_LEN - 10) / 2 + 1 + NB - 1) / NB, KW = KT <= 7 ? 64 : 128;
+                    const uint32_t wa = smem_u32(wsm) + (uint32_t)((128 - C1T) >> 3) * (uint32_t)(KW * 16);
+                    const uint64_t dw = dw_base | (uint64_t)((wa & 0x3FFFFu) >> 4), dx = dx_base | (uint64_t)((rows & 0x3FFFFu) >> 4);
+#pragma unroll
+                    for (int q = 0; q < NB; ++q)
+#pragma unroll
+                        for (int s = 0; s < (KT + 1) / 2; ++s)
+                            tc_mma_f16(d_tmem, dw - (uint64_t)(q * (C1T / 8) * KW) + (uint64_t)(s * 16), dx + (uint64_t)(q * 2 * PQ + s * 2), p.idesc,
+                                       (q | s) ? 1u : 0u);
+                } else {
+                    for (int q = 0; q < p.nb; ++q) {
+                        const uint32_t wa = smem_u32(wsm) + (uint32_t)((128 - p.C1 - q * p.C1) >> 3) * (uint32_t)p.sbo;
+                        const uint32_t xa = rows + (uint32_t)(2 * q * p.Pq) * 16u;
+                        const uint64_t dw = dw_base | (uint64_t)((wa & 0x3FFFFu) >> 4), dx = dx_base | (uint64_t)((xa & 0x3FFFFu) >> 4);
+                        for (int s = 0; s < ksteps; ++s)            // 16 K elements = two tap slots: weights + 2 K blocks (256 B), rows + 2 (32 B)
+                            tc_mma_f16(d_tmem, dw + (uint64_t)(s * 16), dx + (uint64_t)(s * 2), p.idesc, (q | s) ? 1u : 0u);
+                    }
                 }
                 tc_commit(&tfull[buf]);
                 tc_commit(&rows_empty[stage]);
@@ -238,16 +251,18 @@ inline int onehot_conv_pool_tc(const uint8_t* bases, const float* w, const float
     const OhpParams p = onehot_pool_params(B, C1, k, Lp);
     const size_t smem = 1024 + (size_t)p.w_bytes + OHP_DATA_BYTES + 512;
     using Kern = void (*)(const uint8_t*, const float*, const float*, const float*, const float*, bf16*, const OhpParams);
-    static const Kern kerns[3] = {onehot_conv_pool_tc_kernel<16>, onehot_conv_pool_tc_kernel<32>, onehot_conv_pool_tc_kernel<64>};
+#define EMB_OHP_ROW(C) {onehot_conv_pool_tc_kernel<C, 0>, onehot_conv_pool_tc_kernel<C, 5>, onehot_conv_pool_tc_kernel<C, 11>, onehot_conv_pool_tc_kernel<C, 15>}
+    static const Kern kerns[3][4] = {EMB_OHP_ROW(16), EMB_OHP_ROW(32), EMB_OHP_ROW(64)};
+#undef EMB_OHP_ROW
     if (first_on_device(4)) {
-        for (Kern kf : kerns) {
-            cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_max_smem());
+        for (int i = 0; i < 12; ++i) {
+            cudaError_t e = cudaFuncSetAttribute(kerns[i / 4][i % 4], cudaFuncAttributeMaxDynamicSharedMemorySize, tc_max_smem());
             if (e != cudaSuccess) return set_error(-3, "cudaFuncSetAttribute(onehot_conv_pool_tc_kernel): %s", cudaGetErrorString(e));
         }
     }
     if (smem > (size_t)tc_max_smem()) return set_error(-5, "onehot_conv_pool_tc: shared memory");
     const int grid = std::min(B, tc_num_sms());
-    kerns[C1 == 16 ? 0 : C1 == 32 ? 1 : 2]<<<grid, OHP_THREADS, smem, st>>>(bases, w, bias, scale, shift, out, p);
+    kerns[C1 == 16 ? 0 : C1 == 32 ? 1 : 2][k == 5 ? 1 : k == 11 ? 2 : k == 15 ? 3 : 0]<<<grid, OHP_THREADS, smem, st>>>(bases, w, bias, scale, shift, out, p);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error(-3, "onehot_conv_pool_tc launch failed: %s", cudaGetErrorString(err));
     return 0;

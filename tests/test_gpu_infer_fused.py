@@ -19,13 +19,15 @@ pytestmark = pytest.mark.gpu
 # 16 channels = eight position blocks per sample in onehot_pool_tc.cuh, the last one short; 64 channels with the short tap range
 ARCH_C16 = espec(48, [(64, 0.2)], [(16, 15, 0.2), (64, 11, 0.4)], 256, [(64, 0.0)], 0.5)
 ARCH_C64 = espec(48, [(64, 0.2)], [(64, 5, 0.2), (32, 5, 0.4)], 256, [], 0.4)
+# kernel sizes outside the search space and a 48-channel layer: the kernels' run-time (unspecialised) instantiations
+ARCH_K7 = espec(48, [(64, 0.2)], [(32, 7, 0.2), (48, 9, 0.4)], 256, [], 0.4)
 
 
-@pytest.mark.parametrize('arch,B', [('S', 300), ('M', 130), ('L', 77), ('S', 4096), ('W', 150), ('C16', 300), ('C64', 301), ('S', 1)])
+@pytest.mark.parametrize('arch,B', [('S', 300), ('M', 130), ('L', 77), ('S', 4096), ('W', 150), ('C16', 300), ('C64', 301), ('K7', 140), ('S', 1)])
 def test_fused_pooling_epilogue_equals_unfused_eval_forward(arch, B):
     import torch
     from embrace_b200 import Engine, _native as N
-    spec = {'S': ARCH_S, 'M': ARCH_M, 'L': ARCH_L, 'W': ARCH_W, 'C16': ARCH_C16, 'C64': ARCH_C64}[arch]
+    spec = {'S': ARCH_S, 'M': ARCH_M, 'L': ARCH_L, 'W': ARCH_W, 'C16': ARCH_C16, 'C64': ARCH_C64, 'K7': ARCH_K7}[arch]
     P = O.init_params(spec, 4242)
     # a trained model's BatchNorm: running statistics away from (0, 1), gamma of both signs (a negative gamma reverses the order of
     # the pre-activation values, which a fused pooling that maximises BEFORE the affine map would get wrong)
