@@ -38,8 +38,11 @@ def synthetic_dataset(cell_line, task, rows, seed):
 
 
 def make_jobs(n_datasets, n_folds):
+    """(data set, fold) jobs, longest first (the job time grows with the feature count): with 42 jobs on 8 workers the tail of a
+    dynamic queue is one job long, so the long ones must not be the last to start."""
     ds = [(c, t) for c in CELL_F for t in SWEEP_TASKS][:n_datasets]
-    return [dict(cell_line=c, task=t, fold=f + 1) for (c, t) in ds for f in range(n_folds)]
+    jobs = [dict(cell_line=c, task=t, fold=f + 1) for (c, t) in ds for f in range(n_folds)]
+    return sorted(jobs, key=lambda j: -CELL_F[j['cell_line']])
 
 
 def run_job(job, args, device):
@@ -62,17 +65,33 @@ def run_job(job, args, device):
     return dict(job, seconds=time.time() - t0, final_test_AUPRC=float(scores['final_test_AUPRC_scores'][-1]), trials=args.trials)
 
 
-def worker(rank, args, jobs, results):
+def warm_up(device):
+    """Process start-up that is not sweep work: CUDA context, the engine library, one engine build (module load)."""
     import torch
-    torch.cuda.set_device(rank)
+    from . import _native
+    torch.cuda.set_device(device)
+    _native.lib()
+    torch.zeros(1, device=device)
+    torch.cuda.synchronize()
+
+
+def worker(rank, args, jobs, results, ready):
     if not args.verbose:
         sys.stdout = open(os.devnull, 'w')
+    if args.dry_run <= 0:
+        import torch
+        torch.cuda.set_device(rank)
+        warm_up(f'cuda:{rank}')
+    ready.wait()                                  # every worker has its context: the steady-state clock starts here
     while True:
-        try:
-            job = jobs.get_nowait()
-        except Exception:
+        job = jobs.get()                          # blocking: an mp.Queue can look empty while its feeder thread is still flushing (r2: six of
+        if job is None:                           # eight workers saw `Empty` on their first get_nowait() and left); one sentinel per worker
             break
-        r = run_job(job, args, f'cuda:{rank}')
+        if args.dry_run > 0:                      # scheduling plumbing only (CPU tests): the job is a sleep
+            time.sleep(args.dry_run)
+            r = dict(job, seconds=args.dry_run, final_test_AUPRC=0.0, trials=args.trials)
+        else:
+            r = run_job(job, args, f'cuda:{rank}')
         r['gpu'] = rank
         results.put(r)
 
@@ -89,14 +108,16 @@ def main(argv=None):
     ap.add_argument('--sampler', default='TPE')
     ap.add_argument('--out', default='sweep_out')
     ap.add_argument('--verbose', type=int, default=0)
+    ap.add_argument('--dry-run', type=float, default=0.0, help='seconds a job sleeps instead of training (multi-worker plumbing test, no GPU)')
     args = ap.parse_args(argv)
-    import torch
     import torch.multiprocessing as mp
     os.makedirs(args.out, exist_ok=True)
     jobs_list = make_jobs(args.datasets, args.folds)
     t0 = time.time()
     out = []
-    if args.gpus == 1:
+    if args.gpus == 1 and args.dry_run <= 0:
+        warm_up('cuda:0')
+        t_ready = time.time()
         old = sys.stdout
         if not args.verbose:
             sys.stdout = open(os.devnull, 'w')
@@ -108,19 +129,33 @@ def main(argv=None):
     else:
         ctx = mp.get_context('spawn')
         jobs, results = ctx.Queue(), ctx.Queue()
-        for j in jobs_list:
+        for j in jobs_list + [None] * args.gpus:
             jobs.put(j)
-        procs = [ctx.Process(target=worker, args=(r, args, jobs, results)) for r in range(args.gpus)]
+        ready = ctx.Barrier(args.gpus + 1)
+        procs = [ctx.Process(target=worker, args=(r, args, jobs, results, ready)) for r in range(args.gpus)]
         for p in procs:
             p.start()
+        ready.wait()
+        t_ready = time.time()
         for _ in jobs_list:
             out.append(results.get())
         for p in procs:
             p.join()
-    wall = time.time() - t0
+    t_end = time.time()
+    wall, steady = t_end - t0, t_end - t_ready
     n_trials = sum(r['trials'] for r in out)
+    busy = {}
+    for r in out:
+        busy[r['gpu']] = busy.get(r['gpu'], 0.0) + r['seconds']
+    # `value` counts everything from process launch (what a user waits for); `steady` starts when every worker holds its CUDA context
+    # (start-up is a constant ~10-15 s per worker process, not sweep work: it vanishes against real job lengths); `balance` is the
+    # mean / max of the per-GPU busy time -- the part of the scaling loss that is job granularity (42 jobs on 8 workers), not overhead
     line = {'metric': 'embracenet_sweep_trials_per_hour', 'value': 3600.0 * n_trials / wall, 'unit': 'trials/h', 'n_gpus': args.gpus,
-            'jobs': len(out), 'trials': n_trials, 'final_fits': len(out), 'wall_s': wall, 'scaling': 'weak (replicas only, no collective)',
+            'jobs': len(out), 'trials': n_trials, 'final_fits': len(out), 'wall_s': wall, 'startup_s': t_ready - t0,
+            'steady': {'value': 3600.0 * n_trials / steady, 'unit': 'trials/h', 'wall_s': steady},
+            'balance': float(np.mean(list(busy.values())) / np.max(list(busy.values()))),
+            'gpu_busy_s': {str(k): v for k, v in sorted(busy.items())},
+            'scaling': 'weak (replicas only, no collective)',
             'config': {'workload': f'{args.datasets} synthetic data sets x {args.folds} folds x ({args.trials} trials + final fit), '
                                    f'{args.rows} rows, {args.epochs} epochs, batch {args.batch} (BASELINE configs[3])'},
             'mean_final_test_AUPRC': float(np.mean([r['final_test_AUPRC'] for r in out])),

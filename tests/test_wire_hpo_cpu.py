@@ -213,3 +213,16 @@ def test_sweep_job_list_and_inference_sharding():
     from embrace_b200.infer import synthetic_availabilities
     av = synthetic_availabilities(10000, 0)
     assert abs((av.sum(1) == 2).mean() - 0.8) < 0.02 and (av.sum(1) >= 1).all()
+
+
+def test_sweep_driver_hands_every_worker_jobs(tmp_path):
+    """The fold-parallel driver's queue plumbing without a GPU (`--dry-run`: a job is a sleep).  Round 2 found six of eight
+    workers leaving at once because `Queue.get_nowait()` raced the queue's feeder thread; jobs are now pulled with a blocking
+    get and one sentinel per worker ends them."""
+    from embrace_b200 import sweep
+    line = sweep.main(['--gpus', '3', '--datasets', '4', '--folds', '3', '--trials', '2', '--dry-run', '0.05', '--out', str(tmp_path / 'sw')])
+    assert line['jobs'] == 12 and line['trials'] == 24
+    assert sorted(line['gpu_busy_s']) == ['0', '1', '2'], line['gpu_busy_s']
+    assert line['balance'] > 0.6
+    jobs = sweep.make_jobs(14, 3)
+    assert len(jobs) == 42 and sweep.CELL_F[jobs[0]['cell_line']] == max(sweep.CELL_F.values())      # longest first
