@@ -101,8 +101,7 @@ class DeviceLoader:
 
     def _batches(self, ticket):
         src = self.data.x if self.modality == 'FFNN' else self.data.codes
-        for idx in self.plan.batches(ticket):
-            ix = torch.as_tensor(idx, dtype=torch.int64, device=self.data.device)
+        for ix in self.plan.batches(ticket):          # device index tensors: no host->device copy per batch
             yield src.index_select(0, ix), self.data.y.index_select(0, ix).reshape(-1, 1)
 
 
@@ -123,8 +122,8 @@ class _Plan:
         def __init__(self, modality):
             self.modality, self.epoch, self.started = modality, None, False
 
-    def __init__(self, make):
-        self.make, self.pending = make, None
+    def __init__(self, make, device='cpu'):
+        self.make, self.pending, self.device = make, None, device
 
     def open(self, modality):
         t = _Plan._Ticket(modality)
@@ -143,7 +142,15 @@ class _Plan:
         if ticket.epoch is None:
             ticket.epoch = [None]
         if ticket.epoch[0] is None:
-            ticket.epoch[0] = list(self.make())
+            # the epoch's index lists go to the device in ONE copy; a batch is a view of that tensor.  (One pageable host->device
+            # copy per batch and modality was a sixth of a sweep job's host time, r2 profile, and a synchronisation point.)
+            lists = [np.asarray(b, dtype=np.int64).reshape(-1) for b in self.make()]
+            flat = torch.from_numpy(np.concatenate(lists) if lists else np.zeros(0, dtype=np.int64)).to(self.device)
+            out, o = [], 0
+            for b in lists:
+                out.append(flat[o:o + len(b)])
+                o += len(b)
+            ticket.epoch[0] = out
         return ticket.epoch[0]
 
 
@@ -153,7 +160,7 @@ def build_loaders(data: PackedDataset, batch_size=100, training=True, random_sta
     torch.Generator().manual_seed(random_state + 30)."""
     if training:
         sampler = BalancePos_BatchSampler(data.labels_host, batch_size)
-        plan, n_len = _Plan(lambda: iter(sampler)), len(sampler)
+        plan, n_len = _Plan(lambda: iter(sampler), data.device), len(sampler)
     else:
         bs = 2 * batch_size
         gen = torch.Generator().manual_seed(random_state + 30)
@@ -161,5 +168,5 @@ def build_loaders(data: PackedDataset, batch_size=100, training=True, random_sta
         def make():
             perm = torch.randperm(len(data), generator=gen).tolist()
             return (perm[i:i + bs] for i in range(0, len(perm), bs))
-        plan, n_len = _Plan(make), (len(data) + bs - 1) // bs
+        plan, n_len = _Plan(make, data.device), (len(data) + bs - 1) // bs
     return {'FFNN': DeviceLoader(data, 'FFNN', plan, n_len), 'CNN': DeviceLoader(data, 'CNN', plan, n_len)}

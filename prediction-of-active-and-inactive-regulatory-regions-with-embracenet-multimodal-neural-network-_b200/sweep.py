@@ -80,7 +80,8 @@ def worker(rank, args, jobs, results, ready):
         sys.stdout = open(os.devnull, 'w')
     if args.dry_run <= 0:
         import torch
-        torch.cuda.set_device(rank)
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // args.gpus))      # the host side of a job (samplers, HPO bookkeeping) must not
+        torch.cuda.set_device(rank)                                            # oversubscribe the cores it shares with the other workers
         warm_up(f'cuda:{rank}')
     ready.wait()                                  # every worker has its context: the steady-state clock starts here
     while True:
@@ -131,6 +132,9 @@ def main(argv=None):
         jobs, results = ctx.Queue(), ctx.Queue()
         for j in jobs_list + [None] * args.gpus:
             jobs.put(j)
+        # r2, 8 workers on 16 cores with the default thread pools (16 threads each): jobs took 4.6 s instead of 2.4 s
+        for var in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS'):
+            os.environ.setdefault(var, str(max(1, (os.cpu_count() or 1) // args.gpus)))
         ready = ctx.Barrier(args.gpus + 1)
         procs = [ctx.Process(target=worker, args=(r, args, jobs, results, ready)) for r in range(args.gpus)]
         for p in procs:
