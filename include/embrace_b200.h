@@ -206,6 +206,13 @@ int emb_train_step_host_flush(EmbEngine* e, EmbStepMetrics* metrics_host, int32_
 /* Predict through HOST buffers (probs_host [B]); synchronises the stream. */
 int emb_predict_host(EmbEngine* e, const float* x_ffnn_host, const uint8_t* bases_host,
                      const float* availabilities_host, int32_t B, float* probs_host, void* stream);
+/* Software-pipelined scoring loop over host batches (the batch-1 Python loop of Compare_Models_Result.get_model_predictions,
+ * visual.py:263-295, as a stream of large batches): call i uploads batch i on an engine-owned copy stream while batch i-1 is
+ * still being computed, enqueues its forward and the copy of its scores into `probs_host`, and returns when batch i-1 is complete
+ * (*prev_done = 1: the buffer passed to the previous call holds its scores).  emb_predict_host_flush waits for the last batch. */
+int emb_predict_host_pipelined(EmbEngine* e, const float* x_ffnn_host, const uint8_t* bases_host,
+                               const float* availabilities_host, int32_t B, float* probs_host, int32_t* prev_done, void* stream);
+int emb_predict_host_flush(EmbEngine* e, void* stream);
 
 int emb_metrics_reset(EmbEngine* e, void* stream);
 /* copies up to max_records records to host (synchronises); returns the number copied or <0 */

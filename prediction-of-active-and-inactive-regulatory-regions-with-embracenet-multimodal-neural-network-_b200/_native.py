@@ -88,6 +88,8 @@ SIGNATURES = {
     'emb_train_step_host_pipelined': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.POINTER(EmbOptConfig), C.POINTER(EmbStepMetrics), C.POINTER(C.c_int32), _P]),
     'emb_train_step_host_flush': (C.c_int, [_P, C.POINTER(EmbStepMetrics), C.POINTER(C.c_int32), _P]),
     'emb_predict_host': (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P]),
+    'emb_predict_host_pipelined': (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, C.POINTER(C.c_int32), _P]),
+    'emb_predict_host_flush': (C.c_int, [_P, _P]),
     'emb_metrics_reset': (C.c_int, [_P, _P]),
     'emb_metrics_read': (C.c_int, [_P, C.POINTER(EmbStepMetrics), C.c_int32, _P]),
     'emb_last_selection': (C.c_int, [_P, _P, C.c_int32, _P]),

@@ -325,6 +325,24 @@ class Engine:
                                           C.c_void_p(out.ctypes.data), self.stream))
         return out
 
+    def predict_host_pipelined(self, x_ffnn_host, bases_host, availabilities_host, out_host):
+        """Scoring loop step: uploads this batch while the previous one computes and enqueues its forward; `out_host` (pinned
+        float32 tensor or ndarray, [B]) holds the scores once the NEXT call -- or predict_host_flush() -- has returned.  Returns
+        True when the previous call's buffer became valid.  The inputs must stay alive and unchanged until then."""
+        B = (x_ffnn_host if x_ffnn_host is not None else bases_host).shape[0]
+
+        def hp(a):
+            if a is None:
+                return C.c_void_p(0)
+            return C.c_void_p(a.data_ptr() if torch.is_tensor(a) else a.ctypes.data)
+        done = C.c_int32(0)
+        N.check(self.lib.emb_predict_host_pipelined(self._h, hp(x_ffnn_host), hp(bases_host), hp(availabilities_host), B, hp(out_host),
+                                                    C.byref(done), self.stream))
+        return bool(done.value)
+
+    def predict_host_flush(self):
+        N.check(self.lib.emb_predict_host_flush(self._h, self.stream))
+
     def metrics_reset(self):
         N.check(self.lib.emb_metrics_reset(self._h, self.stream))
 

@@ -73,3 +73,47 @@ def test_fused_pooling_epilogue_equals_unfused_eval_forward(arch, B):
         ref = O.predict_proba(spec, P, x, bases, u, availabilities=av)
         for fuse in (2, 1, 0):
             assert np.abs(out[fuse][1] - ref).max() <= 5e-3
+
+
+def test_predict_host_equals_device_forward_on_a_large_batch():
+    """With exactly one modality available per row the eval forward is deterministic (the selection takes every dimension from that
+    modality, EmbraceNetMultimodal.py:63-76), so the host entry must reproduce the device forward row for row."""
+    import torch
+    from embrace_b200 import Engine
+    spec, B = ARCH_S, 4 * 4096 + 1234
+    eng = Engine(to_archspec(spec), max_batch=B, precision='bf16', tensor_core=True)
+    eng.load_numpy(O.init_params(spec, 77))
+    x, bases, _ = make_inputs(spec, B, 78)
+    av = np.zeros((B, 2), dtype=np.float32)
+    av[np.arange(B), np.random.RandomState(79).randint(0, 2, size=B)] = 1.0
+    xt, bt, at = torch.from_numpy(x.astype(np.float32)), torch.from_numpy(bases), torch.from_numpy(av)
+    _, ref = eng.forward(xt, bt, training=False, availabilities=at, want_probs=True)
+    got = eng.predict_host(xt.pin_memory(), bt.pin_memory(), at.pin_memory())
+    assert np.isfinite(got).all()
+    assert np.abs(got - ref.cpu().numpy()).max() <= 1e-6, np.abs(got - ref.cpu().numpy()).max()
+
+
+def test_predict_host_pipelined_loop_returns_every_batch_in_order():
+    """The software-pipelined scoring loop (emb_predict_host_pipelined): batch i's buffer is valid after call i + 1 (or the
+    flush); deterministic availabilities make every batch comparable with the synchronous entry."""
+    import torch
+    from embrace_b200 import Engine
+    spec, B, n_batches = ARCH_S, 700, 5
+    eng = Engine(to_archspec(spec), max_batch=B, precision='bf16', tensor_core=True)
+    eng.load_numpy(O.init_params(spec, 91))
+    batches, want = [], []
+    for i in range(n_batches):
+        nb = B if i != 3 else 333                                     # a shorter batch in the middle of the stream
+        x, bases, _ = make_inputs(spec, nb, 100 + i)
+        av = np.zeros((nb, 2), dtype=np.float32)
+        av[np.arange(nb), np.random.RandomState(200 + i).randint(0, 2, size=nb)] = 1.0
+        t = (torch.from_numpy(x.astype(np.float32)).pin_memory(), torch.from_numpy(bases).pin_memory(), torch.from_numpy(av).pin_memory())
+        batches.append(t)
+        want.append(eng.predict_host(*t))
+    outs = [torch.full((t[0].shape[0],), float('nan')).pin_memory() for t in batches]
+    flags = [eng.predict_host_pipelined(*t, o) for t, o in zip(batches, outs)]
+    assert flags == [False] + [True] * (n_batches - 1)
+    for i in range(n_batches - 1):                                    # valid as soon as the following call returned
+        assert np.abs(outs[i].numpy() - want[i]).max() <= 1e-6, i
+    eng.predict_host_flush()
+    assert np.abs(outs[-1].numpy() - want[-1]).max() <= 1e-6
