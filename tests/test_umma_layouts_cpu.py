@@ -94,3 +94,99 @@ def test_three_term_bf16_split_is_exact():
     assert np.array_equal(hi.astype(np.float64) + mid.astype(np.float64) + lo.astype(np.float64), w.astype(np.float64))
     two = np.abs(hi.astype(np.float64) + mid.astype(np.float64) - w)                                  # a two-term split is not
     assert two.max() > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# csrc/onehot_pool_tc.cuh (inference form of the first conv layer): the position blocks stacked on the TMEM lanes through a shifted
+# window of ONE tall weight array, and the pooling walk's index arithmetic.  Same facts as tests/test_gpu_infer_fused.py, on the host.
+import pytest
+
+
+def _ohp_params(C1, k, Lp=124):
+    nb = 128 // C1
+    Pq = -(-Lp // nb)
+    N = -(-(2 * Pq + 8) // 16) * 16
+    Kw = 64 if k <= 7 else 128
+    return dict(nb=nb, Pq=Pq, N=N, Kw=Kw, sbo=Kw * 16, ksteps=(k + 1) // 2, Lp=Lp)
+
+
+@pytest.mark.parametrize('C1,k', [(16, 15), (32, 5), (64, 15), (64, 5), (32, 11)])
+def test_stacked_position_blocks_and_pooling_walk_of_the_fused_first_layer(C1, k):
+    rs = np.random.RandomState(C1 + k)
+    p = _ohp_params(C1, k)
+    pad = (k - 1) // 2
+    assert 2 * (p['nb'] - 1) * p['Pq'] + p['N'] + p['Kw'] // 8 <= 288 and p['N'] <= 256        # onehot_pool_tc_ok
+    W = rs.standard_normal((C1, 4, k))
+    bases = rs.randint(0, 4, 256)
+    # shared memory as element arrays (index = byte offset / 2): the tall weight array and the sample's one-hot rows
+    w_rows = 256 - C1
+    wsm = np.zeros(w_rows // 8 * p['sbo'] // 2 + 4096)
+    for o in range(C1):
+        for t in range(p['Kw'] // 8):
+            for c in range(4):
+                v = W[o, c, t] if t < k else 0.0
+                R = 128 - C1 + o
+                off = (R >> 3) * p['sbo'] + t * 128 + (R & 7) * 16
+                wsm[off // 2 + c] = 0.75 * v                               # stand-ins for the {hi, mid} split: they add up to v
+                wsm[off // 2 + 4 + c] = 0.25 * v
+    rows = np.zeros((288, 8))
+    for l, c in enumerate(bases):
+        rows[l + pad, c] = rows[l + pad, 4 + c] = 1.0
+    xs = rows.reshape(-1)
+    # the MMAs: D[128, N] += A(128 x 16) . B(N x 16)^T for every block q and K step s, operands read through their descriptors
+    D = np.zeros((128, p['N']))
+    mrow, kk = np.arange(128), np.arange(16)
+    nrow = np.arange(p['N'])
+    a_off = kmajor_offset(mrow[:, None], kk[None, :], lbo=128, sbo=p['sbo'])
+    b_off = kmajor_offset(nrow[:, None], kk[None, :], lbo=16, sbo=128)
+    for q in range(p['nb']):
+        wa = ((128 - C1 - q * C1) >> 3) * p['sbo']
+        xa = 2 * q * p['Pq'] * 16
+        for s in range(p['ksteps']):
+            A = wsm[(wa + s * 256 + a_off) // 2]
+            B = xs[(xa + s * 32 + b_off) // 2]
+            D += A @ B.T
+    # lanes [q C1, (q + 1) C1) x columns n  ==  conv output of channel o at position 2 q Pq + n
+    conv = np.zeros((C1, 256 + 64))
+    for l in range(256):
+        for t in range(k):
+            pos = l + t - pad
+            if 0 <= pos < 256:
+                conv[:, l] += W[:, bases[pos], t]
+    for q in range(p['nb']):
+        for n in range(p['N']):
+            l = 2 * q * p['Pq'] + n
+            if l < 256:
+                assert np.allclose(D[q * C1:(q + 1) * C1, n], conv[:, l], atol=1e-12), (q, n)
+    # the pooling walk (pool_walk in conv_pool_tc.cuh) with the kernel's index arithmetic, every `parts` setting
+    sc, sh = rs.standard_normal(C1), rs.standard_normal(C1)
+    z = np.maximum(conv[:, :256] * sc[:, None] + sh[:, None], 0.0)
+    want = np.stack([z[:, 2 * j:2 * j + 10].max(axis=1) for j in range(p['Lp'])], axis=0)          # [Lp, C1]
+    for parts in (1, 2, 4):
+        out = np.full((p['Lp'], C1), np.nan)
+        for lane in range(128):
+            qb, ch = lane // C1, lane % C1
+            per = -(-p['Pq'] // parts)
+            for part in range(parts):
+                lo = min(part * per, p['Pq'])
+                hi = min(lo + per, p['Pq'])
+                valid = max(0, min(p['Pq'], p['Lp'] - qb * p['Pq']))
+                n_eff = max(0, min(hi, valid) - lo)
+                c_first = (2 * lo) & ~15
+                kq = (c_first >> 1) - (lo + 4)
+                ring = [0.0, 0.0, 0.0, 0.0]
+                c_end = 2 * (hi + 4)
+                assert c_end <= p['N']
+                for c16 in range(c_first, c_end, 16):                      # 16-column TMEM loads; whole chunks are walked
+                    for pp in range(8):
+                        v0, v1 = D[lane, c16 + 2 * pp], D[lane, c16 + 2 * pp + 1]
+                        pm = max(v0 * sc[ch] + sh[ch], v1 * sc[ch] + sh[ch])
+                        rv = max(max(ring), max(pm, 0.0))
+                        if 0 <= kq + pp < n_eff:
+                            j = qb * p['Pq'] + lo + kq + pp
+                            assert np.isnan(out[j, ch])                       # every pooled element is written exactly once
+                            out[j, ch] = rv
+                        ring[pp % 4] = pm
+                    kq += 8
+        assert not np.isnan(out).any()
+        assert np.allclose(out, want, atol=1e-12), parts
