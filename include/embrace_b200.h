@@ -209,7 +209,8 @@ int emb_predict_host(EmbEngine* e, const float* x_ffnn_host, const uint8_t* base
 /* Software-pipelined scoring loop over host batches (the batch-1 Python loop of Compare_Models_Result.get_model_predictions,
  * visual.py:263-295, as a stream of large batches): call i uploads batch i on an engine-owned copy stream while batch i-1 is
  * still being computed, enqueues its forward and the copy of its scores into `probs_host`, and returns when batch i-1 is complete
- * (*prev_done = 1: the buffer passed to the previous call holds its scores).  emb_predict_host_flush waits for the last batch. */
+ * (*prev_done = 1: the buffer passed to the previous call holds its scores).  emb_predict_host_flush waits for the last batch.
+ * The loop shares its two staging slots with emb_train_step_host_pipelined: flush one loop before starting the other. */
 int emb_predict_host_pipelined(EmbEngine* e, const float* x_ffnn_host, const uint8_t* bases_host,
                                const float* availabilities_host, int32_t B, float* probs_host, int32_t* prev_done, void* stream);
 int emb_predict_host_flush(EmbEngine* e, void* stream);
